@@ -1,0 +1,139 @@
+/*
+ * vnfr_b200.h -- C-ABI of the B200-native (sm_100a) face detect -> align -> embed -> classify hot path.
+ *
+ * Drop-in boundary: the reference (votnhan/VN_celeb_face_recognition) is pure Python and has
+ * no FFI layer; its boundary is the Python class API  models.MTCNN.detect / forward / inference,
+ * models.InceptionResnetV1.forward, models.MLPModel.forward  plus the glue functions of demo_image.py /
+ * find_embedding.py.  The host-side mirror of that API lives in vn_celeb_face_recognition_b200/models/*.py and calls
+ * ONLY the entry points declared here (via ctypes).  Every entry point replaces one or more library call sites of
+ * the reference, cited as file:line relative to the reference root.
+ *
+ * Conventions: plain pointers and sizes, no torch / C++ types; all pointers are DEVICE pointers unless the name ends
+ * in _host; `stream` is a cudaStream_t passed as void*; every function returns 0 on success or a VNFR_ERR_* code
+ * (message via vnfr_last_error()); no function allocates device memory -- workspaces are passed in; no function
+ * synchronises the stream.
+ */
+#ifndef VNFR_B200_H
+#define VNFR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNFR_OK 0
+#define VNFR_ERR_ARG 1
+#define VNFR_ERR_CUDA 2
+#define VNFR_ERR_UNSUPPORTED 3
+
+#define VNFR_MAX_LEVELS 24
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+const char* vnfr_last_error(void);
+int vnfr_version(void);
+/* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+long long vnfr_launch_count(void);
+
+/* ---- detection: pyramid plan ------------------------------------------------------------------------------------ */
+/* Scale pyramid of detect_face (models/mtcnn_utils/detect_face.py:48-60, :71) and the derived P-Net map geometry
+ * (models/mtcnn.py:38-49: conv3 -> pool2(ceil) -> conv3 -> conv3).  Host-side, fp64 like the reference. */
+typedef struct {
+  int32_t B, H, W;                       /* frames in the batch, frame size                                      */
+  int32_t n_levels;
+  float scale[VNFR_MAX_LEVELS];          /* (float) of the Python-double scale                                   */
+  double scale_d[VNFR_MAX_LEVELS];
+  int32_t lh[VNFR_MAX_LEVELS], lw[VNFR_MAX_LEVELS];   /* level size  int(H*s+1), int(W*s+1)                      */
+  int32_t oh[VNFR_MAX_LEVELS], ow[VNFR_MAX_LEVELS];   /* P-Net output map size                                   */
+  int64_t level_off[VNFR_MAX_LEVELS + 1];/* float offset of level l in the pyramid buffer, layout [l][b][3][lh][lw] */
+  int64_t map_off[VNFR_MAX_LEVELS + 1];  /* cell offset of level l in dense P-Net maps, layout [l][b][oh][ow]    */
+  int32_t tiles_x[VNFR_MAX_LEVELS], tiles_y[VNFR_MAX_LEVELS];
+  int32_t tile_off[VNFR_MAX_LEVELS + 1]; /* first P-Net tile of level l (per image)                              */
+  int64_t px_off[VNFR_MAX_LEVELS + 1];   /* pixel offset (per image) of level l, for the resize kernel grid      */
+} VnfrPyramid;
+
+int vnfr_pyramid_plan(int B, int H, int W, int min_face_size, double factor, VnfrPyramid* out_host);
+
+/* ---- detection stage kernels -------------------------------------------------------------------------------------
+ * frames: u8 [B][H][W][3] (RGB, the layout detect_face receives, detect_face.py:26-41).                            */
+
+/* imresample(area) + (x-127.5)*0.0078125 for EVERY pyramid level in one launch (detect_face.py:46, :71-72, :304-306).
+ * levels: fp32, layout given by VnfrPyramid.level_off.                                                             */
+int vnfr_pyramid_resize_norm(const VnfrPyramid* pyr_host, const uint8_t* frames, float* levels, void* stream);
+
+/* Upload P/R/O-Net weights.  `packed_host` layouts are produced by models/mtcnn.py:_pack_* (documented there).     */
+int vnfr_pnet_set_weights(const float* packed_host, int n_floats, void* stream);
+
+/* PNet.forward over every level + generateBoundingBox's threshold, fused (mtcnn.py:38-49; detect_face.py:73-75,
+ * :203-218).  Candidates of image b / level l go to segment seg = b*n_levels + l with capacity `cap`:
+ *   cand_count[seg]; cand_cell[seg][i] = (y<<16)|x; cand_score[seg][i]; cand_reg[seg][i][4].
+ * dense_prob / dense_reg (nullable, layout VnfrPyramid.map_off: prob [cell], reg [4][cell] per (l,b)) are for parity
+ * tests only.                                                                                                      */
+int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr_host, const float* levels, float threshold, int cap,
+                            int32_t* cand_count, uint32_t* cand_cell, float* cand_score, float* cand_reg,
+                            float* dense_prob, float* dense_reg, void* stream);
+
+/* Generic segmented NMS (torchvision.ops.nms semantics for mode 0: detect_face.py:79, :93, :128; nms_numpy "Min"
+ * semantics for mode 1: detect_face.py:221-257).  Segment s holds n = min(count[s], cap) boxes at boxes[s][i][4],
+ * scores[s][i]; visit order = score descending, ties by ascending i (mode 0) or descending i (mode 1).
+ * keep[s][0..keep_count[s]) = kept indices i in visit order.                                                       */
+int vnfr_nms_segments(int n_segments, int cap, const int32_t* count, const float* boxes, const float* scores,
+                      float threshold, int mode, int32_t* keep_count, int32_t* keep, void* stream);
+
+/* ---- encoder: implicit-GEMM convolution on tcgen05 / TMEM ---------------------------------------------------------
+ * One fused op = conv (no bias) + folded-BN bias + optional residual add + optional ReLU, NHWC bf16 in/out, writing
+ * into a channel slice of a (possibly wider) destination: replaces BasicConv2d (inception_resnet_v1.py:12-33), the
+ * block projections + `out*scale + x` + ReLU (:56-67, :85-95, :114-126), torch.cat (:63, :91, :120, :147, :179),
+ * last_linear + last_bn (:296-297) and both MLP layers (mlp_model.py:10-15).                                        */
+typedef struct {
+  unsigned char tmap_w[128];      /* CUtensorMap of the packed weights, filled by vnfr_conv_prepare                */
+  const void* in;                 /* bf16 NHWC; pixel pitch in_pitch elements; already offset to first channel     */
+  const void* weights;            /* bf16 [cout_pad][k_pad], k = (ky*KW + kx)*cin + c, zero padded                 */
+  const float* bias;              /* fp32 [cout_pad]                                                               */
+  const void* residual;           /* bf16, nullable: added before ReLU; pixel pitch res_pitch                      */
+  void* out0;                     /* bf16 destination for output channels [0, n_split)                             */
+  void* out1;                     /* bf16 destination for output channels [n_split, cout), nullable                */
+  float* out_f32;                 /* nullable: fp32 destination [M][out_f32_pitch] (used instead of out0/out1)     */
+  int32_t n_img, in_h, in_w, cin, in_pitch;
+  int32_t kh, kw, stride, pad_h, pad_w;
+  int32_t out_h, out_w;
+  int32_t cout, cout_pad, k_pad, block_n;
+  int32_t n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
+  int32_t relu;
+  int32_t reserved[3];
+} VnfrConvOp;
+
+/* Fills op->tmap_w (cuTensorMapEncodeTiled on op->weights, box {64, block_n}, 128B swizzle) and validates the op. */
+int vnfr_conv_prepare(VnfrConvOp* op_host);
+int vnfr_conv_run(const VnfrConvOp* op_host, void* stream);
+
+/* A flat op list = one encoder / classifier forward.  kind 0: convolution (all fields of `conv`); kind 1:
+ * MaxPool2d(3,2) and kind 2: AdaptiveAvgPool2d(1) reuse conv.{in, out0, n_img, in_h, in_w, cin, in_pitch, out0_pitch}.
+ * vnfr_run_ops launches them in order on `stream` (one host call per forward instead of one per layer). */
+typedef struct {
+  int32_t kind;
+  int32_t reserved;
+  VnfrConvOp conv;
+} VnfrOp;
+int vnfr_run_ops(const VnfrOp* ops_host, int n_ops, void* stream);
+
+/* MaxPool2d(3, stride 2) on NHWC bf16 (inception_resnet_v1.py:147 `branch2`, :179 `branch3`, :224 `maxpool_3a`). */
+int vnfr_maxpool3s2_nhwc(const void* in, int n_img, int in_h, int in_w, int c, int in_pitch, void* out, int out_pitch,
+                         void* stream);
+/* AdaptiveAvgPool2d(1) on NHWC bf16 -> bf16 [n_img][c] (inception_resnet_v1.py:294). */
+int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, void* stream);
+/* fp32 NCHW (3 channels) -> bf16 NHWC with 8 channels (3 real + 5 zero): input adapter of InceptionResnetV1.forward. */
+int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, void* stream);
+/* F.normalize(p=2, dim=1) (inception_resnet_v1.py:302): x fp32 [n][d] -> emb fp32 [n][d] and bf16 copy (nullable). */
+int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_bf16, void* stream);
+/* F.log_softmax(dim=1) + argmax + exp(max log-prob) (mlp_model.py:14; demo_image.py:126-130).
+ * logits fp32 [n][pitch] (first c valid) -> logp fp32 [n][c] (nullable), label int64 [n], prob fp32 [n].           */
+int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* logp, int64_t* label, float* prob,
+                           void* stream);
+/* Adds a per-column fp32 bias and applies ReLU then converts fp32 -> bf16 (helper for tests). */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNFR_B200_H */

@@ -1,0 +1,179 @@
+"""GPU parity: tcgen05 implicit-GEMM convolution, encoder companions, full InceptionResnetV1 + MLP vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_encoder_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "needs a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _conv_case(dev, n, h, w, cin, cout, k, stride, pad, cin_real=None, residual=False, relu=True, split=None, f32=False,
+               block_n=None, seed=0):
+    from vn_celeb_face_recognition_b200 import encoder_plan as ep
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    kh, kw = (k, k) if isinstance(k, int) else k
+    ph, pw = (pad, pad) if isinstance(pad, int) else pad
+    cin_real = cin_real or cin
+    x = torch.randn(n, h, w, cin, generator=g)
+    x[..., cin_real:] = 0
+    wt = torch.randn(cout, cin_real, kh, kw, generator=g) / (cin_real * kh * kw) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    xb = x.to(dev).to(torch.bfloat16)
+    pc = ep.pack_conv(wt, None, bias, dev, cin_pad=cin, block_n=block_n)
+    oh, ow = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
+    ref = torch.nn.functional.conv2d(xb.float().permute(0, 3, 1, 2)[:, :cin_real], wt.to(dev).to(torch.bfloat16).float(),
+                                     bias.to(dev), stride=stride, padding=(ph, pw))
+    res = None
+    if residual:
+        res = torch.randn(n, oh, ow, cout, generator=g).to(dev).to(torch.bfloat16)
+        ref = ref + res.float().permute(0, 3, 1, 2)
+    if relu:
+        ref = ref.relu()
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    ol = ep.OpList()
+    if f32:
+        out = torch.full((n * oh * ow, cout), float("nan"), dtype=torch.float32, device=dev)
+        ol.conv(pc, ep.View(xb), None, stride=stride, pad=(ph, pw), relu=relu, out_f32=out)
+        ol.run()
+        torch.cuda.synchronize()
+        got = out.view(n, oh, ow, cout)
+        tol = 2e-3
+    elif split:
+        wide = torch.full((n, oh, ow, split + 24), float("nan"), dtype=torch.bfloat16, device=dev)   # slice of a wider buffer
+        o1 = torch.full((n, oh, ow, cout - split), float("nan"), dtype=torch.bfloat16, device=dev)
+        ol.conv(pc, ep.View(xb), ep.View(wide, 8, split), stride=stride, pad=(ph, pw), relu=relu, dst1=ep.View(o1),
+                n_split=split, residual=None if res is None else ep.View(res))
+        ol.run()
+        torch.cuda.synchronize()
+        assert torch.isnan(wide[..., :8].float()).all() and torch.isnan(wide[..., 8 + split:].float()).all(), "wrote outside slice"
+        got = torch.cat([wide[..., 8:8 + split], o1], dim=-1).float()
+        tol = 2e-2
+    else:
+        out = torch.full((n, oh, ow, cout), float("nan"), dtype=torch.bfloat16, device=dev)
+        ol.conv(pc, ep.View(xb), ep.View(out), stride=stride, pad=(ph, pw), relu=relu,
+                residual=None if res is None else ep.View(res))
+        ol.run()
+        torch.cuda.synchronize()
+        got = out.float()
+        tol = 2e-2
+    assert torch.isfinite(got).all(), "non-finite / unwritten outputs"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= tol * max(scale, 1.0), "max abs err %g (ref max %g)" % (err, scale)
+
+
+@pytest.mark.parametrize("case", [
+    dict(n=2, h=9, w=9, cin=64, cout=64, k=1, stride=1, pad=0),                       # plain GEMM, K = 64
+    dict(n=3, h=8, w=8, cin=896, cout=256, k=1, stride=1, pad=0, block_n=128, split=128),   # Block17 fused 1x1, 2 N tiles
+    dict(n=2, h=17, w=17, cin=256, cout=96, k=1, stride=1, pad=0, split=32),          # Block35 fused 1x1, in-tile split
+    dict(n=2, h=17, w=17, cin=32, cout=32, k=3, stride=1, pad=1),                     # Block35 3x3, two taps per K block
+    dict(n=2, h=15, w=15, cin=8, cin_real=3, cout=32, k=3, stride=2, pad=0),          # stem conv2d_1a (padded channels)
+    dict(n=1, h=12, w=12, cin=80, cout=192, k=3, stride=1, pad=0),                    # conv2d_4a: K = 720 (tail block)
+    dict(n=2, h=8, w=8, cin=128, cout=128, k=(1, 7), stride=1, pad=(0, 3)),
+    dict(n=2, h=8, w=8, cin=128, cout=128, k=(7, 1), stride=1, pad=(3, 0)),
+    dict(n=2, h=17, w=17, cin=256, cout=384, k=3, stride=2, pad=0),                   # Mixed_6a branch0, 2 N tiles of 192
+    dict(n=5, h=3, w=3, cin=384, cout=1792, k=1, stride=1, pad=0, residual=True),     # Block8 projection + residual + ReLU
+    dict(n=5, h=3, w=3, cin=384, cout=1792, k=1, stride=1, pad=0, residual=True, relu=False),
+    dict(n=300, h=1, w=1, cin=1792, cout=512, k=1, stride=1, pad=0, relu=False, f32=True),   # last_linear, fp32 out
+    dict(n=130, h=1, w=1, cin=2048, cout=1008, k=1, stride=1, pad=0, relu=False, f32=True),  # MLP dense_2 (block_n 144)
+    dict(n=4, h=40, w=40, cin=64, cout=80, k=1, stride=1, pad=0),                     # many M tiles, N = 80
+])
+def test_igemm_conv_matches_torch(dev, case):
+    _conv_case(dev, **case)
+
+
+def test_pool_norm_softmax_kernels(dev):
+    from vn_celeb_face_recognition_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 17, 17, 264, generator=g).to(dev).to(torch.bfloat16)
+    out = torch.zeros(3, 8, 8, 64 + 256, dtype=torch.bfloat16, device=dev)
+    _lib.call("vnfr_maxpool3s2_nhwc", _lib.ptr(x), 3, 17, 17, 256, 264, _lib.ptr(out[..., 64:]), 320, _lib.stream_ptr())
+    ref = torch.nn.functional.max_pool2d(x[..., :256].float().permute(0, 3, 1, 2), 3, 2).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., 64:].float(), ref) and (out[..., :64] == 0).all()
+
+    y = torch.randn(5, 3, 3, 1792, generator=g).to(dev).to(torch.bfloat16)
+    pooled = torch.empty(5, 1792, dtype=torch.bfloat16, device=dev)
+    _lib.call("vnfr_avgpool_nhwc", _lib.ptr(y), 5, 9, 1792, 1792, _lib.ptr(pooled), _lib.stream_ptr())
+    torch.testing.assert_close(pooled.float(), y.float().mean(dim=(1, 2)), atol=1e-2, rtol=1e-2)
+
+    z = torch.randn(7, 3, 20, 24, generator=g).to(dev)
+    nhwc = torch.empty(7, 20, 24, 8, dtype=torch.bfloat16, device=dev)
+    _lib.call("vnfr_nchw3_to_nhwc8", _lib.ptr(z), 7, 20, 24, _lib.ptr(nhwc), _lib.stream_ptr())
+    assert torch.equal(nhwc[..., :3], z.permute(0, 2, 3, 1).to(torch.bfloat16)) and (nhwc[..., 3:] == 0).all()
+
+    e = torch.randn(9, 512, generator=g).to(dev)
+    emb = torch.empty_like(e)
+    emb16 = torch.empty(9, 512, dtype=torch.bfloat16, device=dev)
+    _lib.call("vnfr_l2norm_rows", _lib.ptr(e), 9, 512, 512, _lib.ptr(emb), _lib.ptr(emb16), _lib.stream_ptr())
+    torch.testing.assert_close(emb, torch.nn.functional.normalize(e, p=2, dim=1), atol=1e-6, rtol=1e-5)
+
+    lg = torch.randn(11, 1008, generator=g).to(dev)
+    logp = torch.empty(11, 1001, device=dev)
+    lab = torch.empty(11, dtype=torch.int64, device=dev)
+    pr = torch.empty(11, device=dev)
+    _lib.call("vnfr_logsoftmax_argmax", _lib.ptr(lg), 11, 1001, 1008, _lib.ptr(logp), _lib.ptr(lab), _lib.ptr(pr), _lib.stream_ptr())
+    ref = torch.log_softmax(lg[:, :1001], dim=1)
+    torch.testing.assert_close(logp, ref, atol=1e-5, rtol=1e-5)
+    assert torch.equal(lab, ref.argmax(1))
+    torch.testing.assert_close(pr, ref.max(1)[0].exp(), atol=1e-6, rtol=1e-5)
+
+
+def test_encoder_and_mlp_match_oracle_and_golden(dev):
+    """North-star tolerances: embedding cosine >= 0.999 (bf16), identical labels wherever the fp32 oracle's top-2
+    log-prob margin exceeds what bf16 rounding can move."""
+    from oracle import nets, synth
+    from vn_celeb_face_recognition_b200.models import InceptionResnetV1, MLPModel
+    sd = golden_encoder_state_dict()
+    mlp_sd = nets.make_mlp_state_dict(1001, seed=0)
+    enc = InceptionResnetV1(pretrained=None, device=dev).eval()
+    enc.load_state_dict(sd)
+    mlp = MLPModel(512, 1001).to(dev).eval()
+    mlp.load_state_dict(mlp_sd)
+    x = synth.crops_160(24, seed=1)
+    with torch.no_grad():
+        taps = {}
+        e_ref = nets.encoder_forward(sd, x, taps=taps)
+        lp_ref = nets.mlp_forward(mlp_sd, e_ref)
+        e = enc(x.to(dev))
+        lp = mlp(e)
+    torch.cuda.synchronize()
+    # per-stage taps first: a failure names the first broken stage
+    plan = enc._plans[(24, 160, 160)]
+    for name, key in [("conv2d_1a", "conv2d_1a"), ("conv2d_2b", "conv2d_2b"), ("conv2d_4b_repeat_1", "repeat_1.4"),
+                      ("repeat_2", "repeat_2.9"), ("block8", "block8")]:
+        got = plan.taps[name].float().permute(0, 3, 1, 2).cpu()
+        ref = taps[key]
+        rel = (got - ref).norm() / ref.norm()
+        assert rel < 0.03, "stage %s relative error %.4f" % (key, rel)
+    e = e.cpu()
+    cos = torch.nn.functional.cosine_similarity(e, e_ref, dim=1)
+    assert cos.min().item() >= 0.999, "embedding cosine %s" % cos
+    assert torch.allclose(e.norm(dim=1), torch.ones(24), atol=1e-5)
+    g = load_golden("encoder_seed0")
+    cos_g = torch.nn.functional.cosine_similarity(e[:8], torch.from_numpy(g["emb"]), dim=1)
+    assert cos_g.min().item() >= 0.999
+    top2 = lp_ref.topk(2, dim=1)[0]
+    margin = top2[:, 0] - top2[:, 1]
+    lab, lab_ref = lp.argmax(1).cpu(), lp_ref.argmax(1)
+    sure = margin > 0.05
+    assert sure.sum() >= 12
+    assert torch.equal(lab[sure], lab_ref[sure]), "labels differ where the oracle margin is > 0.05"
+    print("label agreement %d/24 (margin>0.05: %d), min cosine %.5f" % ((lab == lab_ref).sum(), sure.sum(), cos.min()))
+    # MLP alone on identical inputs: log-probs within bf16 GEMM tolerance
+    with torch.no_grad():
+        lp_same = mlp(e_ref.to(dev)).cpu()
+    assert (lp_same - lp_ref).abs().max().item() < 0.08
+    # 112x112 crops (demo_video default target size) also run
+    with torch.no_grad():
+        x112 = torch.nn.functional.interpolate(x[:2], size=(112, 112), mode="bilinear", align_corners=False)
+        e112 = enc(x112.to(dev)).cpu()
+    cos112 = torch.nn.functional.cosine_similarity(e112, torch.from_numpy(g["emb112"]), dim=1)
+    assert cos112.min().item() >= 0.999

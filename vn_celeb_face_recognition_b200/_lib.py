@@ -1,0 +1,109 @@
+"""ctypes binding of libvnfr_b200.so (include/vnfr_b200.h).  There is NO fallback: if the library is missing or a call
+fails, this raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvnfr_b200.so")
+
+MAX_LEVELS = 24
+
+
+class VnfrError(RuntimeError):
+    pass
+
+
+class Pyramid(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_levels", C.c_int32),
+        ("scale", C.c_float * MAX_LEVELS), ("scale_d", C.c_double * MAX_LEVELS),
+        ("lh", C.c_int32 * MAX_LEVELS), ("lw", C.c_int32 * MAX_LEVELS),
+        ("oh", C.c_int32 * MAX_LEVELS), ("ow", C.c_int32 * MAX_LEVELS),
+        ("level_off", C.c_int64 * (MAX_LEVELS + 1)), ("map_off", C.c_int64 * (MAX_LEVELS + 1)),
+        ("tiles_x", C.c_int32 * MAX_LEVELS), ("tiles_y", C.c_int32 * MAX_LEVELS),
+        ("tile_off", C.c_int32 * (MAX_LEVELS + 1)), ("px_off", C.c_int64 * (MAX_LEVELS + 1)),
+    ]
+
+
+class ConvOp(C.Structure):
+    _fields_ = [
+        ("tmap_w", C.c_ubyte * 128),
+        ("inp", C.c_void_p), ("weights", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("out0", C.c_void_p), ("out1", C.c_void_p), ("out_f32", C.c_void_p),
+        ("n_img", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("cin", C.c_int32), ("in_pitch", C.c_int32),
+        ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad_h", C.c_int32), ("pad_w", C.c_int32),
+        ("out_h", C.c_int32), ("out_w", C.c_int32),
+        ("cout", C.c_int32), ("cout_pad", C.c_int32), ("k_pad", C.c_int32), ("block_n", C.c_int32),
+        ("n_split", C.c_int32), ("out0_pitch", C.c_int32), ("out1_pitch", C.c_int32), ("res_pitch", C.c_int32),
+        ("out_f32_pitch", C.c_int32), ("relu", C.c_int32), ("reserved", C.c_int32 * 3),
+    ]
+
+
+class Op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("conv", ConvOp)]
+
+
+_lib = None
+
+# name -> argtypes (restype is always int unless listed in _SPECIAL)
+_P, _I, _F, _D, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
+_SIGS = {
+    "vnfr_pyramid_plan": [_I, _I, _I, _I, _D, C.POINTER(Pyramid)],
+    "vnfr_pyramid_resize_norm": [C.POINTER(Pyramid), _P, _P, _P],
+    "vnfr_pnet_set_weights": [_P, _I, _P],
+    "vnfr_pnet_sweep_compact": [C.POINTER(Pyramid), _P, _F, _I, _P, _P, _P, _P, _P, _P, _P],
+    "vnfr_nms_segments": [_I, _I, _P, _P, _P, _F, _I, _P, _P, _P],
+    "vnfr_conv_prepare": [C.POINTER(ConvOp)],
+    "vnfr_conv_run": [C.POINTER(ConvOp), _P],
+    "vnfr_run_ops": [C.POINTER(Op), _I, _P],
+    "vnfr_maxpool3s2_nhwc": [_P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "vnfr_avgpool_nhwc": [_P, _I, _I, _I, _I, _P, _P],
+    "vnfr_nchw3_to_nhwc8": [_P, _I, _I, _I, _P, _P],
+    "vnfr_l2norm_rows": [_P, _I, _I, _I, _P, _P, _P],
+    "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
+}
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it has not been built -- there is no CPU / PyTorch fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VnfrError("%s not found: run `python -m vn_celeb_face_recognition_b200.build` (needs nvcc); there is "
+                            "no CPU fallback for this package" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        l.vnfr_last_error.restype = C.c_char_p
+        l.vnfr_launch_count.restype = C.c_longlong
+        for name, args in _SIGS.items():
+            fn = getattr(l, name)      # AttributeError if the symbol is missing: fail loudly
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return ["vnfr_last_error", "vnfr_version", "vnfr_launch_count"] + sorted(_SIGS)
+
+
+def check(rc):
+    if rc != 0:
+        raise VnfrError("libvnfr_b200 call failed (%d): %s" % (rc, lib().vnfr_last_error().decode()))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))
+
+
+def launch_count():
+    return int(lib().vnfr_launch_count())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -1,0 +1,196 @@
+// Memory-bound companions of the tensor-core convolutions of the encoder / classifier: pooling, layout adapter,
+// L2 normalisation and log-softmax/argmax.  All are one pass over their input with 16-byte accesses.
+#include "common.cuh"
+#include <math_constants.h>
+
+extern long long g_vnfr_launches;
+
+namespace {
+
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// MaxPool2d(3, stride=2), floor mode, no padding (inception_resnet_v1.py:147, :179, :224).  One thread = 8 channels.
+__global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_img, int in_h, int in_w, int c8, int in_pitch,
+                                  __nv_bfloat16* __restrict__ out, int out_h, int out_w, int out_pitch) {
+  const long long total = (long long)n_img * out_h * out_w * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % c8);
+    long long t = i / c8;
+    const int ox = (int)(t % out_w); t /= out_w;
+    const int oy = (int)(t % out_h);
+    const int img = (int)(t / out_h);
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -CUDART_INF_F;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const size_t px = ((size_t)img * in_h + (2 * oy + ky)) * in_w + (2 * ox + kx);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + px * in_pitch + cg * 8));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          m[2 * e] = fmaxf(m[2 * e], bf_lo(w[e]));
+          m[2 * e + 1] = fmaxf(m[2 * e + 1], bf_hi(w[e]));
+        }
+      }
+    const size_t opx = ((size_t)img * out_h + oy) * out_w + ox;
+    *reinterpret_cast<uint4*>(out + opx * out_pitch + cg * 8) =
+        make_uint4(pack_bf2(m[0], m[1]), pack_bf2(m[2], m[3]), pack_bf2(m[4], m[5]), pack_bf2(m[6], m[7]));
+  }
+}
+
+// AdaptiveAvgPool2d(1): mean over hw pixels in fp32 (sum then one division), bf16 out.  One thread = 8 channels.
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, int n_img, int hw, int c8, int in_pitch,
+                               __nv_bfloat16* __restrict__ out) {
+  const int total = n_img * c8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cg = i % c8, img = i / c8;
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < hw; ++p) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)img * hw + p) * in_pitch + cg * 8));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s[2 * e] += bf_lo(w[e]); s[2 * e + 1] += bf_hi(w[e]); }
+    }
+    const float inv = 1.0f / (float)hw;
+    *reinterpret_cast<uint4*>(out + (size_t)img * c8 * 8 + cg * 8) =
+        make_uint4(pack_bf2(s[0] * inv, s[1] * inv), pack_bf2(s[2] * inv, s[3] * inv), pack_bf2(s[4] * inv, s[5] * inv),
+                   pack_bf2(s[6] * inv, s[7] * inv));
+  }
+}
+
+// fp32 NCHW (3 planes) -> bf16 NHWC, 8 channels per pixel (3 real + 5 zeros) = one 16-byte store per pixel.
+__global__ void nchw3_to_nhwc8_kernel(const float* __restrict__ in, int n_img, int hw, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)n_img * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, p = i % hw;
+    const float* b = in + img * 3 * hw + p;
+    const float r = __ldg(b), g = __ldg(b + hw), bl = __ldg(b + 2 * hw);
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf2(r, g), pack_bf2(bl, 0.f), 0u, 0u);
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// F.normalize(p=2, dim=1, eps=1e-12): x / max(||x||, eps).  One warp per row.
+__global__ void l2norm_kernel(const float* __restrict__ x, int n, int d, int x_pitch, float* __restrict__ emb,
+                              __nv_bfloat16* __restrict__ emb_bf16) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + (size_t)row * x_pitch;
+  float ss = 0.f;
+  for (int i = lane; i < d; i += 32) { const float v = xr[i]; ss += v * v; }
+  ss = warp_sum(ss);
+  const float denom = fmaxf(sqrtf(ss), 1e-12f);
+  for (int i = lane; i < d; i += 32) {
+    const float v = xr[i] / denom;
+    emb[(size_t)row * d + i] = v;
+    if (emb_bf16 != nullptr) emb_bf16[(size_t)row * d + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// log_softmax over the first c columns + argmax (first maximal index, like torch.argmax) + exp(max log-prob).
+__global__ void logsoftmax_argmax_kernel(const float* __restrict__ logits, int n, int c, int pitch, float* __restrict__ logp,
+                                         long long* __restrict__ label, float* __restrict__ prob) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = logits + (size_t)row * pitch;
+  float mx = -CUDART_INF_F;
+  int arg = 0x7fffffff;
+  for (int i = lane; i < c; i += 32) {
+    const float v = xr[i];
+    if (v > mx) { mx = v; arg = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+  }
+  float se = 0.f;
+  for (int i = lane; i < c; i += 32) se += expf(xr[i] - mx);
+  se = warp_sum(se);
+  const float lse = logf(se);
+  if (logp != nullptr)
+    for (int i = lane; i < c; i += 32) logp[(size_t)row * c + i] = xr[i] - mx - lse;
+  if (lane == 0) {
+    if (label != nullptr) label[row] = arg;
+    if (prob != nullptr) prob[row] = expf(-lse);
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int vnfr_maxpool3s2_nhwc(const void* in, int n_img, int in_h, int in_w, int c, int in_pitch, void* out,
+                                    int out_pitch, void* stream) {
+  VNFR_REQUIRE(c % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0, "channels and pitches must be multiples of 8");
+  VNFR_REQUIRE(in_h >= 3 && in_w >= 3, "input smaller than the pooling window");
+  const int out_h = (in_h - 3) / 2 + 1, out_w = (in_w - 3) / 2 + 1;
+  const long long total = (long long)n_img * out_h * out_w * (c / 8);
+  if (total == 0) return VNFR_OK;
+  maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, n_img, in_h, in_w, c / 8,
+                                                                          in_pitch, (__nv_bfloat16*)out, out_h, out_w, out_pitch);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, void* stream) {
+  VNFR_REQUIRE(c % 8 == 0 && in_pitch % 8 == 0, "channels and pitch must be multiples of 8");
+  if (n_img == 0) return VNFR_OK;
+  avgpool_kernel<<<grid_for((long long)n_img * (c / 8), 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, n_img, hw,
+                                                                                            c / 8, in_pitch, (__nv_bfloat16*)out);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, void* stream) {
+  if (n_img == 0) return VNFR_OK;
+  nchw3_to_nhwc8_kernel<<<grid_for((long long)n_img * h * w, 256), 256, 0, (cudaStream_t)stream>>>(in, n_img, h * w,
+                                                                                                 (__nv_bfloat16*)out);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_bf16, void* stream) {
+  if (n == 0) return VNFR_OK;
+  l2norm_kernel<<<ceil_div(n, 4), 128, 0, (cudaStream_t)stream>>>(x, n, d, x_pitch, emb, (__nv_bfloat16*)emb_bf16);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* logp, int64_t* label, float* prob,
+                                      void* stream) {
+  if (n == 0) return VNFR_OK;
+  logsoftmax_argmax_kernel<<<ceil_div(n, 4), 128, 0, (cudaStream_t)stream>>>(logits, n, c, pitch, logp, (long long*)label, prob);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}

@@ -1,0 +1,342 @@
+"""Host-side graph of the InceptionResnetV1 encoder and the MLP classifier as a flat list of C-ABI ops.
+
+Weight packing (done once per ``load_state_dict`` / first forward, on the GPU with torch tensor ops -- plumbing):
+  * BatchNorm (eval, eps 1e-3) is folded into the conv: W' = W * gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps)
+    (inception_resnet_v1.py:12-33); the residual scale of Block35/17/8 is folded into the projection conv
+    (``out*scale + x``, :64-66, :92-94, :121-125).
+  * weights go to bf16 [cout_pad][k_pad] with k = (ky*KW + kx)*cin + c (NHWC implicit-GEMM order), zero padded.
+  * sibling 1x1 branch convs that read the same input are concatenated along cout and run as ONE GEMM whose epilogue
+    scatters column ranges to different destinations (the concat buffer / the branch scratch).
+Activations are NHWC bf16; ``torch.cat`` never runs: every conv writes straight into its channel slice.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-3
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b * b
+
+
+class PackedConv:
+    """Device-resident packed weights of one (possibly branch-fused) convolution."""
+
+    def __init__(self, w, bias, kh, kw, cin, cout, block_n):
+        self.w, self.bias, self.kh, self.kw, self.cin, self.cout, self.block_n = w, bias, kh, kw, cin, cout, block_n
+        self.cout_pad, self.k_pad = w.shape
+
+
+def pick_block_n(cout):
+    if cout <= 256:
+        return cout
+    for bn in (256, 224, 192, 160, 144, 128, 112, 96, 80, 64):
+        if cout % bn == 0:
+            return bn
+    return 64
+
+
+def pack_conv(w, scale, bias, device, cin_pad=None, block_n=None):
+    """w (cout,cin,kh,kw) fp32, scale (cout,) or None, bias (cout,) fp32 -> PackedConv on ``device``."""
+    w = w.detach().to(device=device, dtype=torch.float32)
+    cout, cin, kh, kw = w.shape
+    if scale is not None:
+        w = w * scale.to(device).view(-1, 1, 1, 1)
+    cin_p = cin_pad or _ceil(cin, 8)
+    w = w.permute(0, 2, 3, 1)                                   # cout, kh, kw, cin
+    if cin_p != cin:
+        w = torch.nn.functional.pad(w, (0, cin_p - cin))
+    K = kh * kw * cin_p
+    bn = block_n or pick_block_n(_ceil(cout, 16))
+    cout16 = _ceil(cout, 16)
+    cout_pad = _ceil(cout16, bn)
+    k_pad = _ceil(K, 64)
+    wp = torch.zeros(cout_pad, k_pad, dtype=torch.bfloat16, device=device)
+    wp[:cout, :K] = w.reshape(cout, K).to(torch.bfloat16)
+    bp = torch.zeros(cout_pad, dtype=torch.float32, device=device)
+    bp[:cout] = bias.detach().to(device=device, dtype=torch.float32)
+    return PackedConv(wp, bp, kh, kw, cin_p, cout16, bn)
+
+
+def fold_bn(sd, p):
+    """BasicConv2d ``p`` -> (weight, scale, bias) with eval-mode BN folded."""
+    g, b = sd[p + ".bn.weight"].float(), sd[p + ".bn.bias"].float()
+    m, v = sd[p + ".bn.running_mean"].float(), sd[p + ".bn.running_var"].float()
+    s = g / torch.sqrt(v + BN_EPS)
+    return sd[p + ".conv.weight"].float(), s, b - m * s
+
+
+def pack_basic(sd, prefixes, device, cin_pad=None, block_n=None):
+    """One or more sibling BasicConv2d (same input, same kernel) fused along cout."""
+    ws, bs = [], []
+    for p in prefixes:
+        w, s, b = fold_bn(sd, p)
+        ws.append(w * s.view(-1, 1, 1, 1))
+        bs.append(b)
+    return pack_conv(torch.cat(ws, 0), None, torch.cat(bs, 0), device, cin_pad, block_n)
+
+
+def pack_projection(sd, p, scale, device, block_n=None):
+    """Block projection conv2d (with bias), residual scale folded in."""
+    return pack_conv(sd[p + ".weight"].float() * scale, None, sd[p + ".bias"].float() * scale, device, None, block_n)
+
+
+class View:
+    """A channel slice of an NHWC bf16 activation buffer."""
+
+    def __init__(self, t, c0=0, c=None):
+        self.t, self.c0 = t, c0
+        self.c = (t.shape[-1] - c0) if c is None else c
+
+    @property
+    def pitch(self):
+        return self.t.shape[-1]
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr() + 2 * self.c0
+
+    @property
+    def n(self):
+        return self.t.shape[0]
+
+    @property
+    def h(self):
+        return self.t.shape[1]
+
+    @property
+    def w(self):
+        return self.t.shape[2]
+
+
+class OpList:
+    """Builds and owns a ctypes array of VnfrOp plus references to every tensor it points at."""
+
+    def __init__(self):
+        self.ops = []
+        self.keep = []
+        self._arr = None
+
+    def conv(self, pc, src, dst0, stride=1, pad=(0, 0), relu=True, dst1=None, n_split=None, residual=None, out_f32=None):
+        assert src.c == pc.cin, (src.c, pc.cin)
+        op = _lib.Op()
+        op.kind = 0
+        c = op.conv
+        c.inp, c.weights, c.bias = src.ptr, pc.w.data_ptr(), pc.bias.data_ptr()
+        c.n_img, c.in_h, c.in_w, c.cin, c.in_pitch = src.n, src.h, src.w, src.c, src.pitch
+        c.kh, c.kw, c.stride, c.pad_h, c.pad_w = pc.kh, pc.kw, stride, pad[0], pad[1]
+        c.out_h = (src.h + 2 * pad[0] - pc.kh) // stride + 1
+        c.out_w = (src.w + 2 * pad[1] - pc.kw) // stride + 1
+        c.cout, c.cout_pad, c.k_pad, c.block_n = pc.cout, pc.cout_pad, pc.k_pad, pc.block_n
+        c.relu = 1 if relu else 0
+        if out_f32 is not None:
+            c.out_f32, c.out_f32_pitch = out_f32.data_ptr(), out_f32.shape[-1]
+            c.n_split = pc.cout
+            self.keep.append(out_f32)
+        else:
+            c.out0, c.out0_pitch = dst0.ptr, dst0.pitch
+            assert (dst0.n, dst0.h, dst0.w) == (src.n, c.out_h, c.out_w), "destination geometry mismatch"
+            if dst1 is not None:
+                c.out1, c.out1_pitch, c.n_split = dst1.ptr, dst1.pitch, n_split
+                assert dst0.c == n_split and dst1.c == pc.cout - n_split
+            else:
+                c.n_split = pc.cout
+                assert dst0.c == pc.cout, (dst0.c, pc.cout)
+        if residual is not None:
+            c.residual, c.res_pitch = residual.ptr, residual.pitch
+        _lib.call("vnfr_conv_prepare", C.byref(c))
+        self.ops.append(op)
+        self.keep += [pc, src, dst0, dst1, residual]
+        self._arr = None
+
+    def maxpool(self, src, dst):
+        op = _lib.Op()
+        op.kind = 1
+        c = op.conv
+        c.inp, c.out0 = src.ptr, dst.ptr
+        c.n_img, c.in_h, c.in_w, c.cin, c.in_pitch, c.out0_pitch = src.n, src.h, src.w, src.c, src.pitch, dst.pitch
+        assert dst.c == src.c and dst.h == (src.h - 3) // 2 + 1
+        self.ops.append(op)
+        self.keep += [src, dst]
+        self._arr = None
+
+    def avgpool(self, src, dst2d):
+        op = _lib.Op()
+        op.kind = 2
+        c = op.conv
+        c.inp, c.out0 = src.ptr, dst2d.data_ptr()
+        c.n_img, c.in_h, c.in_w, c.cin, c.in_pitch = src.n, src.h, src.w, src.c, src.pitch
+        self.ops.append(op)
+        self.keep += [src, dst2d]
+        self._arr = None
+
+    def run(self):
+        if not self.ops:
+            return
+        if self._arr is None:
+            self._arr = (_lib.Op * len(self.ops))(*self.ops)
+        _lib.call("vnfr_run_ops", self._arr, len(self.ops), _lib.stream_ptr())
+
+
+class EncoderWeights:
+    """All packed convolutions of InceptionResnetV1 (inception_resnet_v1.py:219-257), fused per the module doc."""
+
+    def __init__(self, sd, device):
+        d = device
+        P = {}
+        P["conv2d_1a"] = pack_basic(sd, ["conv2d_1a"], d, cin_pad=8)
+        for n in ["conv2d_2a", "conv2d_2b", "conv2d_3b", "conv2d_4a", "conv2d_4b"]:
+            P[n] = pack_basic(sd, [n], d)
+        for i in range(5):
+            p = "repeat_1.%d" % i
+            P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0", p + ".branch2.0"], d)      # N = 96
+            P[p + ".b1"] = pack_basic(sd, [p + ".branch1.1"], d)
+            P[p + ".b2a"] = pack_basic(sd, [p + ".branch2.1"], d)
+            P[p + ".b2b"] = pack_basic(sd, [p + ".branch2.2"], d)
+            P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.17, d)
+        P["m6a.b0"] = pack_basic(sd, ["mixed_6a.branch0"], d)
+        P["m6a.b1a"] = pack_basic(sd, ["mixed_6a.branch1.0"], d)
+        P["m6a.b1b"] = pack_basic(sd, ["mixed_6a.branch1.1"], d)
+        P["m6a.b1c"] = pack_basic(sd, ["mixed_6a.branch1.2"], d)
+        for i in range(10):
+            p = "repeat_2.%d" % i
+            P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0"], d, block_n=128)            # N = 256
+            P[p + ".b1a"] = pack_basic(sd, [p + ".branch1.1"], d)
+            P[p + ".b1b"] = pack_basic(sd, [p + ".branch1.2"], d)
+            P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.10, d)
+        P["m7a.in"] = pack_basic(sd, ["mixed_7a.branch0.0", "mixed_7a.branch1.0", "mixed_7a.branch2.0"], d)   # N = 768
+        P["m7a.b0"] = pack_basic(sd, ["mixed_7a.branch0.1"], d)
+        P["m7a.b1"] = pack_basic(sd, ["mixed_7a.branch1.1"], d)
+        P["m7a.b2a"] = pack_basic(sd, ["mixed_7a.branch2.1"], d)
+        P["m7a.b2b"] = pack_basic(sd, ["mixed_7a.branch2.2"], d)
+        for i in list(range(5)) + [None]:
+            p = "repeat_3.%d" % i if i is not None else "block8"
+            P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0"], d, block_n=192)            # N = 384
+            P[p + ".b1a"] = pack_basic(sd, [p + ".branch1.1"], d)
+            P[p + ".b1b"] = pack_basic(sd, [p + ".branch1.2"], d)
+            P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.20 if i is not None else 1.0, d)
+        # last_linear (no bias) + last_bn folded (inception_resnet_v1.py:296-297)
+        g, b = sd["last_bn.weight"].float(), sd["last_bn.bias"].float()
+        m, v = sd["last_bn.running_mean"].float(), sd["last_bn.running_var"].float()
+        s = g / torch.sqrt(v + BN_EPS)
+        P["last"] = pack_conv(sd["last_linear.weight"].float().view(512, 1792, 1, 1), s, b - m * s, d)
+        if "logits.weight" in sd:
+            P["logits"] = pack_conv(sd["logits.weight"].float()[:, :, None, None], None, sd["logits.bias"].float(), d)
+        self.P = P
+
+
+def _out_hw(h, k, s, p=0):
+    return (h + 2 * p - k) // s + 1
+
+
+class EncoderPlan:
+    """Op list + activation buffers of one forward for a fixed (batch, H, W).  Input: ``self.x0`` NHWC8 bf16; output:
+    ``self.emb_raw`` fp32 (n, 512) = last_bn(last_linear(avgpool)), before L2 normalisation."""
+
+    def __init__(self, weights, n, h, w, device):
+        P = weights.P
+        bf = dict(dtype=torch.bfloat16, device=device)
+        buf = lambda hh, ww, c: torch.empty(n, hh, ww, c, **bf)
+        ol = OpList()
+        self.ol = ol
+        self.n = n
+        self.x0 = torch.zeros(n, h, w, 8, **bf)
+        h1, w1 = _out_hw(h, 3, 2), _out_hw(w, 3, 2)
+        c1a = buf(h1, w1, 32)
+        h2, w2 = h1 - 2, w1 - 2
+        c2a, c2b = buf(h2, w2, 32), buf(h2, w2, 64)
+        h3, w3 = _out_hw(h2, 3, 2), _out_hw(w2, 3, 2)
+        mp, c3b = buf(h3, w3, 64), buf(h3, w3, 80)
+        h4, w4 = h3 - 2, w3 - 2
+        c4a = buf(h4, w4, 192)
+        h5, w5 = _out_hw(h4, 3, 2), _out_hw(w4, 3, 2)
+        x35 = buf(h5, w5, 256)
+        ol.conv(P["conv2d_1a"], View(self.x0), View(c1a), stride=2)
+        ol.conv(P["conv2d_2a"], View(c1a), View(c2a))
+        ol.conv(P["conv2d_2b"], View(c2a), View(c2b), pad=(1, 1))
+        ol.maxpool(View(c2b), View(mp))
+        ol.conv(P["conv2d_3b"], View(mp), View(c3b))
+        ol.conv(P["conv2d_4a"], View(c3b), View(c4a))
+        ol.conv(P["conv2d_4b"], View(c4a), View(x35), stride=2)
+        # ---- 5 x Block35 (scale 0.17)
+        cat, t1, t2 = buf(h5, w5, 96), buf(h5, w5, 64), buf(h5, w5, 32)
+        for i in range(5):
+            p = "repeat_1.%d" % i
+            ol.conv(P[p + ".in"], View(x35), View(cat, 0, 32), dst1=View(t1), n_split=32)
+            ol.conv(P[p + ".b1"], View(t1, 0, 32), View(cat, 32, 32), pad=(1, 1))
+            ol.conv(P[p + ".b2a"], View(t1, 32, 32), View(t2), pad=(1, 1))
+            ol.conv(P[p + ".b2b"], View(t2), View(cat, 64, 32), pad=(1, 1))
+            ol.conv(P[p + ".out"], View(cat), View(x35), residual=View(x35), relu=True)
+        # ---- Mixed_6a
+        h6, w6 = _out_hw(h5, 3, 2), _out_hw(w5, 3, 2)
+        x17 = buf(h6, w6, 896)
+        t6a, t6b = buf(h5, w5, 192), buf(h5, w5, 192)
+        ol.conv(P["m6a.b0"], View(x35), View(x17, 0, 384), stride=2)
+        ol.conv(P["m6a.b1a"], View(x35), View(t6a))
+        ol.conv(P["m6a.b1b"], View(t6a), View(t6b), pad=(1, 1))
+        ol.conv(P["m6a.b1c"], View(t6b), View(x17, 384, 256), stride=2)
+        ol.maxpool(View(x35), View(x17, 640, 256))
+        # ---- 10 x Block17 (scale 0.10)
+        cat17, t17a, t17b = buf(h6, w6, 256), buf(h6, w6, 128), buf(h6, w6, 128)
+        for i in range(10):
+            p = "repeat_2.%d" % i
+            ol.conv(P[p + ".in"], View(x17), View(cat17, 0, 128), dst1=View(t17a), n_split=128)
+            ol.conv(P[p + ".b1a"], View(t17a), View(t17b), pad=(0, 3))
+            ol.conv(P[p + ".b1b"], View(t17b), View(cat17, 128, 128), pad=(3, 0))
+            ol.conv(P[p + ".out"], View(cat17), View(x17), residual=View(x17), relu=True)
+        # ---- Mixed_7a
+        h7, w7 = _out_hw(h6, 3, 2), _out_hw(w6, 3, 2)
+        x8 = buf(h7, w7, 1792)
+        t7, t7b = buf(h6, w6, 768), buf(h6, w6, 256)
+        ol.conv(P["m7a.in"], View(x17), View(t7))
+        ol.conv(P["m7a.b0"], View(t7, 0, 256), View(x8, 0, 384), stride=2)
+        ol.conv(P["m7a.b1"], View(t7, 256, 256), View(x8, 384, 256), stride=2)
+        ol.conv(P["m7a.b2a"], View(t7, 512, 256), View(t7b), pad=(1, 1))
+        ol.conv(P["m7a.b2b"], View(t7b), View(x8, 640, 256), stride=2)
+        ol.maxpool(View(x17), View(x8, 896, 896))
+        # ---- 5 x Block8 (scale 0.20) + block8 (scale 1, no ReLU)
+        cat8, t8a, t8b = buf(h7, w7, 384), buf(h7, w7, 192), buf(h7, w7, 192)
+        for i in list(range(5)) + [None]:
+            p = "repeat_3.%d" % i if i is not None else "block8"
+            ol.conv(P[p + ".in"], View(x8), View(cat8, 0, 192), dst1=View(t8a), n_split=192)
+            ol.conv(P[p + ".b1a"], View(t8a), View(t8b), pad=(0, 1))
+            ol.conv(P[p + ".b1b"], View(t8b), View(cat8, 192, 192), pad=(1, 0))
+            ol.conv(P[p + ".out"], View(cat8), View(x8), residual=View(x8), relu=(i is not None))
+        # ---- avgpool -> last_linear + last_bn (fp32 out)
+        pooled = torch.empty(n, 1, 1, 1792, **bf)
+        self.emb_raw = torch.empty(n, 512, dtype=torch.float32, device=device)
+        ol.avgpool(View(x8), pooled)
+        ol.conv(P["last"], View(pooled), None, relu=False, out_f32=self.emb_raw)
+        self.taps = {"conv2d_1a": c1a, "conv2d_2b": c2b, "conv2d_4b_repeat_1": x35, "repeat_2": x17, "block8": x8}
+
+    def run(self):
+        self.ol.run()
+
+
+class MlpWeights:
+    """MLPModel (mlp_model.py:6-8): dense_1 512->2048 (+ReLU), dense_2 2048->C."""
+
+    def __init__(self, sd, device):
+        self.num_classes = sd["dense_2.weight"].shape[0]
+        self.input_dim = sd["dense_1.weight"].shape[1]
+        self.d1 = pack_conv(sd["dense_1.weight"].float()[:, :, None, None], None, sd["dense_1.bias"].float(), device)
+        self.d2 = pack_conv(sd["dense_2.weight"].float()[:, :, None, None], None, sd["dense_2.bias"].float(), device)
+
+
+class MlpPlan:
+    """x bf16 (n, input_dim) -> logits fp32 (n, cout16) (first num_classes columns valid)."""
+
+    def __init__(self, weights, n, device):
+        self.w = weights
+        self.x = torch.zeros(n, 1, 1, weights.input_dim, dtype=torch.bfloat16, device=device)
+        self.hid = torch.empty(n, 1, 1, 2048, dtype=torch.bfloat16, device=device)
+        self.logits = torch.empty(n, weights.d2.cout, dtype=torch.float32, device=device)
+        self.ol = OpList()
+        self.ol.conv(weights.d1, View(self.x), View(self.hid), relu=True)
+        self.ol.conv(weights.d2, View(self.hid), None, relu=False, out_f32=self.logits)
+
+    def run(self):
+        self.ol.run()
