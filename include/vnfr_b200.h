@@ -82,7 +82,7 @@ int vnfr_nms_segments(int n_segments, int cap, const int32_t* count, const float
                       float threshold, int mode, int32_t* keep_count, int32_t* keep, void* stream);
 
 /* ---- encoder: implicit-GEMM convolution on tcgen05 / TMEM ---------------------------------------------------------
- * One fused op = conv (no bias) + folded-BN bias + optional residual add + optional ReLU, NHWC bf16 in/out, writing
+ * One fused op = conv (no bias) + folded-BN bias + optional residual add + optional ReLU, NHWC bf16 (or fp16, see `dtype`) in/out, writing
  * into a channel slice of a (possibly wider) destination: replaces BasicConv2d (inception_resnet_v1.py:12-33), the
  * block projections + `out*scale + x` + ReLU (:56-67, :85-95, :114-126), torch.cat (:63, :91, :120, :147, :179),
  * last_linear + last_bn (:296-297) and both MLP layers (mlp_model.py:10-15).                                        */
@@ -101,7 +101,8 @@ typedef struct {
   int32_t cout, cout_pad, k_pad, block_n;
   int32_t n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
   int32_t relu;
-  int32_t reserved[3];
+  int32_t dtype;                  /* storage type of in/weights/residual/out0/out1: 0 = bf16, 1 = fp16             */
+  int32_t reserved[2];
 } VnfrConvOp;
 
 /* Fills op->tmap_w (cuTensorMapEncodeTiled on op->weights, box {64, block_n}, 128B swizzle) and validates the op. */
@@ -120,13 +121,13 @@ int vnfr_run_ops(const VnfrOp* ops_host, int n_ops, void* stream);
 
 /* MaxPool2d(3, stride 2) on NHWC bf16 (inception_resnet_v1.py:147 `branch2`, :179 `branch3`, :224 `maxpool_3a`). */
 int vnfr_maxpool3s2_nhwc(const void* in, int n_img, int in_h, int in_w, int c, int in_pitch, void* out, int out_pitch,
-                         void* stream);
+                         int dtype, void* stream);
 /* AdaptiveAvgPool2d(1) on NHWC bf16 -> bf16 [n_img][c] (inception_resnet_v1.py:294). */
-int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, void* stream);
+int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, int dtype, void* stream);
 /* fp32 NCHW (3 channels) -> bf16 NHWC with 8 channels (3 real + 5 zero): input adapter of InceptionResnetV1.forward. */
-int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, void* stream);
+int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream);
 /* F.normalize(p=2, dim=1) (inception_resnet_v1.py:302): x fp32 [n][d] -> emb fp32 [n][d] and bf16 copy (nullable). */
-int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_bf16, void* stream);
+int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_half, int dtype, void* stream);
 /* F.log_softmax(dim=1) + argmax + exp(max log-prob) (mlp_model.py:14; demo_image.py:126-130).
  * logits fp32 [n][pitch] (first c valid) -> logp fp32 [n][c] (nullable), label int64 [n], prob fp32 [n].           */
 int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* logp, int64_t* label, float* prob,

@@ -2,19 +2,39 @@
 // L2 normalisation and log-softmax/argmax.  All are one pass over their input with 16-byte accesses.
 #include "common.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 
 extern long long g_vnfr_launches;
 
 namespace {
 
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
-__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+// 16-bit storage helpers: F16 = true -> IEEE half, false -> bfloat16
+template <bool F16>
+__device__ __forceinline__ float h_lo(uint32_t w) {
+  return F16 ? __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))) : __uint_as_float(w << 16);
+}
+template <bool F16>
+__device__ __forceinline__ float h_hi(uint32_t w) {
+  return F16 ? __half2float(__ushort_as_half((unsigned short)(w >> 16))) : __uint_as_float(w & 0xFFFF0000u);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  if (F16) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+template <bool F16>
+__device__ __forceinline__ unsigned short pack_h1(float a) {
+  if (F16) return __half_as_ushort(__float2half_rn(fminf(fmaxf(a, -65504.f), 65504.f)));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(a));
+}
 
 // MaxPool2d(3, stride=2), floor mode, no padding (inception_resnet_v1.py:147, :179, :224).  One thread = 8 channels.
+template <bool F16>
 __global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_img, int in_h, int in_w, int c8, int in_pitch,
                                   __nv_bfloat16* __restrict__ out, int out_h, int out_w, int out_pitch) {
   const long long total = (long long)n_img * out_h * out_w * c8;
@@ -36,17 +56,18 @@ __global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_im
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          m[2 * e] = fmaxf(m[2 * e], bf_lo(w[e]));
-          m[2 * e + 1] = fmaxf(m[2 * e + 1], bf_hi(w[e]));
+          m[2 * e] = fmaxf(m[2 * e], h_lo<F16>(w[e]));
+          m[2 * e + 1] = fmaxf(m[2 * e + 1], h_hi<F16>(w[e]));
         }
       }
     const size_t opx = ((size_t)img * out_h + oy) * out_w + ox;
     *reinterpret_cast<uint4*>(out + opx * out_pitch + cg * 8) =
-        make_uint4(pack_bf2(m[0], m[1]), pack_bf2(m[2], m[3]), pack_bf2(m[4], m[5]), pack_bf2(m[6], m[7]));
+        make_uint4(pack_h2<F16>(m[0], m[1]), pack_h2<F16>(m[2], m[3]), pack_h2<F16>(m[4], m[5]), pack_h2<F16>(m[6], m[7]));
   }
 }
 
 // AdaptiveAvgPool2d(1): mean over hw pixels in fp32 (sum then one division), bf16 out.  One thread = 8 channels.
+template <bool F16>
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, int n_img, int hw, int c8, int in_pitch,
                                __nv_bfloat16* __restrict__ out) {
   const int total = n_img * c8;
@@ -57,23 +78,24 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ in, int n_img, 
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)img * hw + p) * in_pitch + cg * 8));
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { s[2 * e] += bf_lo(w[e]); s[2 * e + 1] += bf_hi(w[e]); }
+      for (int e = 0; e < 4; ++e) { s[2 * e] += h_lo<F16>(w[e]); s[2 * e + 1] += h_hi<F16>(w[e]); }
     }
     const float inv = 1.0f / (float)hw;
     *reinterpret_cast<uint4*>(out + (size_t)img * c8 * 8 + cg * 8) =
-        make_uint4(pack_bf2(s[0] * inv, s[1] * inv), pack_bf2(s[2] * inv, s[3] * inv), pack_bf2(s[4] * inv, s[5] * inv),
-                   pack_bf2(s[6] * inv, s[7] * inv));
+        make_uint4(pack_h2<F16>(s[0] * inv, s[1] * inv), pack_h2<F16>(s[2] * inv, s[3] * inv), pack_h2<F16>(s[4] * inv, s[5] * inv),
+                   pack_h2<F16>(s[6] * inv, s[7] * inv));
   }
 }
 
 // fp32 NCHW (3 planes) -> bf16 NHWC, 8 channels per pixel (3 real + 5 zeros) = one 16-byte store per pixel.
+template <bool F16>
 __global__ void nchw3_to_nhwc8_kernel(const float* __restrict__ in, int n_img, int hw, __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)n_img * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long img = i / hw, p = i % hw;
     const float* b = in + img * 3 * hw + p;
     const float r = __ldg(b), g = __ldg(b + hw), bl = __ldg(b + 2 * hw);
-    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf2(r, g), pack_bf2(bl, 0.f), 0u, 0u);
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_h2<F16>(r, g), pack_h2<F16>(bl, 0.f), 0u, 0u);
   }
 }
 
@@ -89,8 +111,9 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // F.normalize(p=2, dim=1, eps=1e-12): x / max(||x||, eps).  One warp per row.
+template <bool F16>
 __global__ void l2norm_kernel(const float* __restrict__ x, int n, int d, int x_pitch, float* __restrict__ emb,
-                              __nv_bfloat16* __restrict__ emb_bf16) {
+                              unsigned short* __restrict__ emb_half) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -102,7 +125,7 @@ __global__ void l2norm_kernel(const float* __restrict__ x, int n, int d, int x_p
   for (int i = lane; i < d; i += 32) {
     const float v = xr[i] / denom;
     emb[(size_t)row * d + i] = v;
-    if (emb_bf16 != nullptr) emb_bf16[(size_t)row * d + i] = __float2bfloat16_rn(v);
+    if (emb_half != nullptr) emb_half[(size_t)row * d + i] = pack_h1<F16>(v);
   }
 }
 
@@ -146,41 +169,44 @@ inline int grid_for(long long total, int block) {
 }  // namespace
 
 extern "C" int vnfr_maxpool3s2_nhwc(const void* in, int n_img, int in_h, int in_w, int c, int in_pitch, void* out,
-                                    int out_pitch, void* stream) {
+                                    int out_pitch, int dtype, void* stream) {
   VNFR_REQUIRE(c % 8 == 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0, "channels and pitches must be multiples of 8");
   VNFR_REQUIRE(in_h >= 3 && in_w >= 3, "input smaller than the pooling window");
   const int out_h = (in_h - 3) / 2 + 1, out_w = (in_w - 3) / 2 + 1;
   const long long total = (long long)n_img * out_h * out_w * (c / 8);
   if (total == 0) return VNFR_OK;
-  maxpool3s2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, n_img, in_h, in_w, c / 8,
-                                                                          in_pitch, (__nv_bfloat16*)out, out_h, out_w, out_pitch);
+  auto kern = dtype == 1 ? maxpool3s2_kernel<true> : maxpool3s2_kernel<false>;
+  kern<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, n_img, in_h, in_w, c / 8, in_pitch,
+                                                             (__nv_bfloat16*)out, out_h, out_w, out_pitch);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
 }
 
-extern "C" int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, void* stream) {
+extern "C" int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, int dtype, void* stream) {
   VNFR_REQUIRE(c % 8 == 0 && in_pitch % 8 == 0, "channels and pitch must be multiples of 8");
   if (n_img == 0) return VNFR_OK;
-  avgpool_kernel<<<grid_for((long long)n_img * (c / 8), 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, n_img, hw,
-                                                                                            c / 8, in_pitch, (__nv_bfloat16*)out);
+  auto kern = dtype == 1 ? avgpool_kernel<true> : avgpool_kernel<false>;
+  kern<<<grid_for((long long)n_img * (c / 8), 128), 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, n_img, hw, c / 8,
+                                                                                  in_pitch, (__nv_bfloat16*)out);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
 }
 
-extern "C" int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, void* stream) {
+extern "C" int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream) {
   if (n_img == 0) return VNFR_OK;
-  nchw3_to_nhwc8_kernel<<<grid_for((long long)n_img * h * w, 256), 256, 0, (cudaStream_t)stream>>>(in, n_img, h * w,
-                                                                                                 (__nv_bfloat16*)out);
+  auto kern = dtype == 1 ? nchw3_to_nhwc8_kernel<true> : nchw3_to_nhwc8_kernel<false>;
+  kern<<<grid_for((long long)n_img * h * w, 256), 256, 0, (cudaStream_t)stream>>>(in, n_img, h * w, (__nv_bfloat16*)out);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
 }
 
-extern "C" int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_bf16, void* stream) {
+extern "C" int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_half, int dtype, void* stream) {
   if (n == 0) return VNFR_OK;
-  l2norm_kernel<<<ceil_div(n, 4), 128, 0, (cudaStream_t)stream>>>(x, n, d, x_pitch, emb, (__nv_bfloat16*)emb_bf16);
+  auto kern = dtype == 1 ? l2norm_kernel<true> : l2norm_kernel<false>;
+  kern<<<ceil_div(n, 4), 128, 0, (cudaStream_t)stream>>>(x, n, d, x_pitch, emb, (unsigned short*)emb_half);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

@@ -14,6 +14,7 @@
 // <= 256 TMEM columns per CTA so that two CTAs share an SM and one's epilogue overlaps the other's main loop.
 #include "common.cuh"
 #include <string.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -38,6 +39,7 @@ struct ConvParams {
   int n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
   int relu;
   int stages, tmem_cols;
+  int dtype;   // 0 = bf16, 1 = fp16 (both: fp32 accumulation in TMEM)
 };
 
 // ------------------------------------------------------------------------------------------------------------ PTX
@@ -105,9 +107,32 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, int is_fp16) {
+  const uint32_t fmt = is_fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+// 16-bit float helpers parameterised on the storage type (F16 = true: IEEE half, false: bfloat16)
+template <bool F16>
+__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi) {
+  if (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  } else {
+    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xFFFF0000u);
+  }
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (F16) {
+    // saturate instead of overflowing to inf (fp16 range 65504)
+    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -134,6 +159,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // ---------------------------------------------------------------------------------------------------------- kernel
 // Shared memory: [A stage 0..S) 16 KB each][W stage 0..S) block_n*128 B each][barriers], base aligned to 1024 B.
+template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -258,8 +284,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
           const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            v[8 * q + 2 * e + 0] += __uint_as_float(w[e] << 16);
-            v[8 * q + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+            float lo, hi;
+            unpack2<F16>(w[e], lo, hi);
+            v[8 * q + 2 * e + 0] += lo;
+            v[8 * q + 2 * e + 1] += hi;
           }
         }
       }
@@ -274,10 +302,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
       } else {
         uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-          pk[i] = *reinterpret_cast<const uint32_t*>(&h);
-        }
+        for (int i = 0; i < 8; ++i) pk[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
         __nv_bfloat16* dst = (n < p.n_split) ? p.out0 + (size_t)m * p.out0_pitch + n
                                              : p.out1 + (size_t)m * p.out1_pitch + (n - p.n_split);
         uint4* o = reinterpret_cast<uint4*>(dst);
@@ -300,7 +325,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
   } else {
     // ================================================= MMA issuer: one elected lane
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(p.block_n);
+      const uint32_t idesc = make_idesc_f16(p.block_n, F16 ? 1 : 0);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % S;
         mbar_wait(bar_full + 8u * s, (kb / S) & 1);
@@ -366,6 +391,7 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
   VNFR_REQUIRE(op->cout % 16 == 0 && op->cout_pad % op->block_n == 0 && op->cout_pad >= op->cout, "bad cout / cout_pad");
   VNFR_REQUIRE(op->k_pad % BLOCK_K == 0 && op->k_pad >= op->kh * op->kw * op->cin, "k_pad must be a multiple of 64 covering K");
   VNFR_REQUIRE(op->n_split % 16 == 0, "n_split must be a multiple of 16");
+  VNFR_REQUIRE(op->dtype == 0 || op->dtype == 1, "dtype must be 0 (bf16) or 1 (fp16)");
   VNFR_REQUIRE(op->out_f32 != nullptr || op->out0 != nullptr, "no destination");
   VNFR_REQUIRE(op->out_f32 != nullptr || ((op->out0_pitch % 8 == 0) && (op->n_split >= op->cout || (op->out1 != nullptr && op->out1_pitch % 8 == 0))),
                "bf16 destinations need pitches that are multiples of 8");
@@ -383,7 +409,7 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
   const cuuint64_t strides[1] = {(cuuint64_t)op->k_pad * 2};
   const cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)op->block_n};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op->weights), dims, strides, box, estr,
+  CUresult r = enc(&tm, op->dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op->weights), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -398,7 +424,8 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   VNFR_REQUIRE(op != nullptr, "op is null");
   static bool attr_set = false;
   if (!attr_set) {
-    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   ConvParams p;
@@ -419,6 +446,7 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   p.n_split = op->n_split; p.out0_pitch = op->out0_pitch; p.out1_pitch = op->out1_pitch;
   p.res_pitch = op->res_pitch; p.out_f32_pitch = op->out_f32_pitch;
   p.relu = op->relu;
+  p.dtype = op->dtype;
   p.stages = pick_stages(op->block_n);
   int cols = 32;
   while (cols < op->block_n) cols <<= 1;
@@ -427,7 +455,10 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   CUtensorMap tm;
   memcpy(&tm, op->tmap_w, sizeof(tm));
   dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(op->cout, op->block_n));
-  igemm_conv_kernel<<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, p);
+  if (op->dtype == 1)
+    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, p);
+  else
+    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, p);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
@@ -440,8 +471,8 @@ extern "C" int vnfr_run_ops(const VnfrOp* ops, int n_ops, void* stream) {
     int rc;
     switch (ops[i].kind) {
       case 0: rc = vnfr_conv_run(c, stream); break;
-      case 1: rc = vnfr_maxpool3s2_nhwc(c->in, c->n_img, c->in_h, c->in_w, c->cin, c->in_pitch, c->out0, c->out0_pitch, stream); break;
-      case 2: rc = vnfr_avgpool_nhwc(c->in, c->n_img, c->in_h * c->in_w, c->cin, c->in_pitch, c->out0, stream); break;
+      case 1: rc = vnfr_maxpool3s2_nhwc(c->in, c->n_img, c->in_h, c->in_w, c->cin, c->in_pitch, c->out0, c->out0_pitch, c->dtype, stream); break;
+      case 2: rc = vnfr_avgpool_nhwc(c->in, c->n_img, c->in_h * c->in_w, c->cin, c->in_pitch, c->out0, c->dtype, stream); break;
       default: vnfr_set_error(__FILE__, __LINE__, "unknown op kind"); return VNFR_ERR_ARG;
     }
     if (rc != VNFR_OK) return rc;

@@ -112,9 +112,12 @@ class InceptionResnetV1(nn.Module):
             pass
         return super().train(mode)
 
+    #: 16-bit compute type (torch.float16 default / torch.bfloat16); None = encoder_plan.HALF
+    half_dtype = None
+
     def _ensure(self, dev):
         if self._packed is None:
-            self._packed = encoder_plan.EncoderWeights(self.state_dict(), dev)
+            self._packed = encoder_plan.EncoderWeights(self.state_dict(), dev, self.half_dtype)
             self._plans = {}
         return self._packed
 
@@ -125,19 +128,19 @@ class InceptionResnetV1(nn.Module):
         return self._plans[key]
 
     def embed_nhwc8(self, x_nhwc8):
-        """Device-resident fast path used by the fused pipeline: x bf16 (n,H,W,8) NHWC -> (emb fp32 (n,512),
-        emb bf16 (n,512)), both L2-normalised.  Chunked by ``self.chunk``."""
+        """Device-resident fast path used by the fused pipeline: x 16-bit (n,H,W,8) NHWC -> (emb fp32 (n,512),
+        emb 16-bit (n,512)), both L2-normalised.  Chunked by ``self.chunk``."""
         n, h, w, _ = x_nhwc8.shape
         dev = x_nhwc8.device
         emb = torch.empty(n, 512, dtype=torch.float32, device=dev)
-        emb16 = torch.empty(n, 512, dtype=torch.bfloat16, device=dev)
+        emb16 = torch.empty(n, 512, dtype=x_nhwc8.dtype, device=dev)
         for s in range(0, n, self.chunk):
             m = min(self.chunk, n - s)
             plan = self._plan(m, h, w, dev)
             plan.x0.copy_(x_nhwc8[s:s + m])
             plan.run()
             _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(emb[s:s + m]),
-                      _lib.ptr(emb16[s:s + m]), _lib.stream_ptr())
+                      _lib.ptr(emb16[s:s + m]), encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())
         return emb, emb16
 
     def forward(self, x):
@@ -155,12 +158,13 @@ class InceptionResnetV1(nn.Module):
             for s in range(0, n, self.chunk):
                 m = min(self.chunk, n - s)
                 plan = self._plan(m, h, w, dev)
-                _lib.call("vnfr_nchw3_to_nhwc8", _lib.ptr(x[s:s + m]), m, h, w, _lib.ptr(plan.x0), _lib.stream_ptr())
+                _lib.call("vnfr_nchw3_to_nhwc8", _lib.ptr(x[s:s + m]), m, h, w, _lib.ptr(plan.x0),
+                          encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())
                 plan.run()
                 if self.classify:
                     self._classify(plan, m, out[s:s + m])
                 else:
-                    _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(out[s:s + m]), None,
+                    _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(out[s:s + m]), None, 0,
                               _lib.stream_ptr())
         return out
 
@@ -168,7 +172,7 @@ class InceptionResnetV1(nn.Module):
         # logits + log_softmax (inception_resnet_v1.py:298-300)
         pc = self._packed.P["logits"]
         if not hasattr(plan, "cls"):
-            x16 = torch.empty(m, 1, 1, 512, dtype=torch.bfloat16, device=out.device)
+            x16 = torch.empty(m, 1, 1, 512, dtype=plan.dtype, device=out.device)
             logits = torch.empty(m, pc.cout, dtype=torch.float32, device=out.device)
             ol = encoder_plan.OpList()
             ol.conv(pc, encoder_plan.View(x16), None, relu=False, out_f32=logits)

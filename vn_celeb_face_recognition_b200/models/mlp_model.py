@@ -10,6 +10,8 @@ from .. import _lib, encoder_plan
 
 class MLPModel(nn.Module):
     chunk = 4096
+    #: 16-bit compute type (torch.float16 default / torch.bfloat16); None = encoder_plan.HALF
+    half_dtype = None
 
     def __init__(self, input_dim, num_classes):
         super().__init__()
@@ -36,14 +38,14 @@ class MLPModel(nn.Module):
     def _plan(self, n, dev):
         if self._packed is None:
             assert self.input_dim % 8 == 0, "input_dim must be a multiple of 8"
-            self._packed = encoder_plan.MlpWeights(self.state_dict(), dev)
+            self._packed = encoder_plan.MlpWeights(self.state_dict(), dev, self.half_dtype)
             self._plans = {}
         if n not in self._plans:
             self._plans[n] = encoder_plan.MlpPlan(self._packed, n, dev)
         return self._plans[n]
 
-    def classify_bf16(self, emb16, logp=None):
-        """Device fast path: emb bf16 (n, input_dim) -> (label int64 (n,), prob fp32 (n,)) [+ log-probs into ``logp``]:
+    def classify_half(self, emb16, logp=None):
+        """Device fast path: emb 16-bit (n, input_dim) -> (label int64 (n,), prob fp32 (n,)) [+ log-probs into ``logp``]:
         argmax / exp(max log-prob) of identify_person (demo_image.py:126-130) fused with the log-softmax."""
         n = emb16.shape[0]
         dev = emb16.device
@@ -65,7 +67,7 @@ class MLPModel(nn.Module):
         if self.training:
             raise _lib.VnfrError("training-mode forward (dropout p=0.5) is out of scope; call .eval()")
         with torch.no_grad():
-            x16 = input.detach().to(torch.bfloat16).contiguous()
+            x16 = input.detach().to(self.half_dtype or encoder_plan.HALF).contiguous()
             logp = torch.empty(input.shape[0], self.num_classes, dtype=torch.float32, device=input.device)
-            self.classify_bf16(x16, logp)
+            self.classify_half(x16, logp)
         return logp
