@@ -81,6 +81,48 @@ int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr_host, const float* levels, fl
 int vnfr_nms_segments(int n_segments, int cap, const int32_t* count, const float* boxes, const float* scores,
                       float threshold, int mode, int32_t* keep_count, int32_t* keep, void* stream);
 
+/* Stage-1 tail on the device (detect_face.py:79-104): NMS(0.5) per (image, level), NMS(0.7) per image across levels,
+ * regression without +1, rerec, pad.  keep1_count [B*L] / keep1 [B*L][cap1] are scratch.  Outputs per image b:
+ * s2_count[b], s2_box[b][i][4] (squared-up float boxes), s2_pad[b][i] = (x, y, ex, ey) int32 (detect_face.py:277-289).
+ * status: bit 0/1/2/3/4 set when cap1/cap2/cap3/capf/max_faces overflowed (results are then truncated).             */
+int vnfr_stage1_boxes(const VnfrPyramid* pyr_host, int cap1, const int32_t* cand_count, const uint32_t* cand_cell,
+                      const float* cand_score, const float* cand_reg, int32_t* keep1_count, int32_t* keep1, int cap2,
+                      int32_t* s2_count, float* s2_box, int32_t* s2_pad, int32_t* status, void* stream);
+
+/* R-Net / O-Net over every candidate box of every frame: crop imgs[b,:,y-1:ey,x-1:ex], area-resize to 24 / 48,
+ * normalise, network forward (detect_face.py:108-117, :136-146, :16-23; mtcnn.py:84-99, :138-157).
+ * weights: packed fp32 device buffer (vnfr_rnet_weight_floats() / vnfr_onet_weight_floats() floats; layout in
+ * csrc/detect_heads.cu, produced by models/mtcnn.py).  prob[b][i] = softmax[:,1], reg[b][i][4], lmk[b][i][10].
+ * offs [B+1] is scratch (exclusive scan of counts); crops_out (nullable) receives the resized crops for parity tests.*/
+int vnfr_rnet_weight_floats(void);
+int vnfr_onet_weight_floats(void);
+int vnfr_rnet_forward(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                      const float* weights, float* prob, float* reg, int32_t* offs, float* crops_out, void* stream);
+int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                      const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops_out,
+                      void* stream);
+
+/* Stage-2 tail (detect_face.py:119-136): score > threshold, NMS(0.7), bbreg, rerec, pad. */
+int vnfr_stage2_boxes(int B, int H, int W, int cap2, const int32_t* s2_count, const float* s2_box, const float* s2_prob,
+                      const float* s2_reg, float threshold, int cap3, int32_t* s3_count, float* s3_box, int32_t* s3_pad,
+                      int32_t* status, void* stream);
+
+/* Stage-3 tail (detect_face.py:148-169 incl. the host NumPy "Min" NMS :221-274; mtcnn.py:334-340 when select_largest):
+ * out_box[b][i] = (x1,y1,x2,y2,score), out_pts[b][i] = (x0,y0,...,x4,y4), in the order MTCNN.detect returns them.  */
+int vnfr_stage3_faces(int B, int cap3, const int32_t* s3_count, const float* s3_box, const float* s3_prob,
+                      const float* s3_reg, const float* s3_lmk, float threshold, int select_largest, int capf,
+                      int32_t* out_count, float* out_box, float* out_pts, int32_t* status, void* stream);
+
+/* Faces -> encoder inputs, one gather kernel.  mode 0: MTCNN.extract semantics for tensor frames (mtcnn.py:458-518,
+ * detect_face.py:317-322, :342-378); mode 1: demo_video alignment (demo_image.py:174-199, :236-239;
+ * align_face.py:51-57: 5-point similarity + cv2.warpAffine) with template_host[10] = center points (x,y)*5.
+ * Faces are numbered image-major in detection order; offs [B+1] scratch.  face_u8 [max_faces][S][S][3],
+ * face_half [max_faces][S][S][8] (standardised, dtype 0 = bf16 / 1 = fp16), face_img [max_faces] (nullable).        */
+int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int capf, const int32_t* count, const float* box,
+                    const float* pts, int mode, int image_size, int margin, const float* template_host, int dtype,
+                    int max_faces, int32_t* offs, uint8_t* face_u8, void* face_half, int32_t* face_img, int32_t* status,
+                    void* stream);
+
 /* ---- encoder: implicit-GEMM convolution on tcgen05 / TMEM ---------------------------------------------------------
  * One fused op = conv (no bias) + folded-BN bias + optional residual add + optional ReLU, NHWC bf16 (or fp16, see `dtype`) in/out, writing
  * into a channel slice of a (possibly wider) destination: replaces BasicConv2d (inception_resnet_v1.py:12-33), the

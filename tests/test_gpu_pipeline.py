@@ -1,0 +1,251 @@
+"""GPU parity of the detection cascade, face extraction / alignment and the end-to-end recognition path against the
+oracle and against the golden vectors produced by the unmodified reference (north-star tolerances: identical face
+counts, boxes IoU >= 0.99, identical labels)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, ragged, golden_encoder_state_dict, assert_boxes_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "needs a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def models(dev):
+    from oracle import nets
+    from vn_celeb_face_recognition_b200.models import MTCNN, InceptionResnetV1, MLPModel
+    enc = InceptionResnetV1(pretrained=None, device=dev).eval()
+    enc.load_state_dict(golden_encoder_state_dict())
+    mlp = MLPModel(512, 1001).to(dev).eval()
+    mlp.load_state_dict(nets.make_mlp_state_dict(1001, seed=0))
+    return {"MTCNN": MTCNN, "enc": enc, "mlp": mlp}
+
+
+def _check_detect(got, g, tag, n):
+    b, p, l = got
+    for i in range(n):
+        rb, rp, rl = ragged(g, "boxes_" + tag)[i], ragged(g, "probs_" + tag)[i], ragged(g, "points_" + tag)[i]
+        assert_boxes_match(b[i], rb, 0.99)
+        assert len(p[i]) == len(rp)
+        if len(rp):
+            np.testing.assert_allclose(np.asarray(b[i], np.float32), rb, atol=0.05)       # far tighter than IoU 0.99
+            np.testing.assert_allclose(np.asarray(p[i], np.float32), rp, atol=2e-4)
+            np.testing.assert_allclose(np.asarray(l[i], np.float32), rl, atol=0.05)
+
+
+@pytest.mark.parametrize("name,kind,n,seed", [("detect_small_min50", "small", 3, 0), ("detect_small_min20", "small", 2, 7),
+                                              ("detect_1080p_min50", "1080p", 2, 0), ("detect_4k_min20", "4k", 1, 0)])
+def test_detect_matches_reference_golden(dev, models, name, kind, n, seed):
+    from oracle import synth
+    g = load_golden(name)
+    fr = synth.frames(kind, n, first_seed=seed)
+    for sl, tag in ((True, "largest"), (False, "prob")):
+        m = models["MTCNN"](image_size=160, keep_all=True, min_face_size=int(g["min_face_size"]), select_largest=sl, device=dev)
+        _check_detect(m.detect(fr, landmarks=True), g, tag, n)
+    # input type variants of detect_face.py:26-41: torch tensor, list of ndarrays, list of PIL images
+    from PIL import Image
+    m = models["MTCNN"](image_size=160, keep_all=True, min_face_size=int(g["min_face_size"]), device=dev)
+    if kind == "small":
+        _check_detect(m.detect(torch.from_numpy(fr), landmarks=True), g, "largest", n)
+        _check_detect(m.detect([Image.fromarray(f) for f in fr], landmarks=True), g, "largest", n)
+        single = m.detect(fr[0], landmarks=True)                      # un-batched (mtcnn.py:349-356)
+        assert_boxes_match(single[0], ragged(g, "boxes_largest")[0], 0.99)
+        assert np.asarray(single[2]).shape == (len(single[0]), 5, 2)
+        b2, p2 = m.detect(fr[0])
+        assert len(b2) == len(p2)
+
+
+def test_detect_bundled_images_and_empty(dev, models):
+    from oracle import synth
+    g = load_golden("detect_bundled")
+    m = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    for i, (_, img) in enumerate(synth.bundled_faces()):
+        b, p, l = m.detect(img, landmarks=True)
+        assert_boxes_match(b, ragged(g, "boxes")[i], 0.99)
+        np.testing.assert_allclose(p, ragged(g, "probs")[i], atol=2e-4)
+    # no faces: [] per image (mtcnn.py:329-332); tiny image with an empty pyramid
+    noise = (np.random.RandomState(0).rand(2, 120, 160, 3) * 20 + 100).astype(np.uint8)
+    b, p = m.detect(noise)
+    assert len(b) == 2 and all(len(x) == 0 for x in b)
+    b, p = m.detect(np.zeros((30, 30, 3), np.uint8))
+    assert len(b) == 0
+    with pytest.raises(Exception, match="equal-dimension"):
+        from PIL import Image
+        m.detect([Image.new("RGB", (64, 64)), Image.new("RGB", (65, 64))])
+
+
+def test_rnet_onet_kernels_match_oracle(dev, models):
+    """Crops bit-exact, network outputs to fp32 conv tolerance, given the oracle's own boxes."""
+    from oracle import detect, nets, synth
+    from vn_celeb_face_recognition_b200 import _lib
+    from vn_celeb_face_recognition_b200.models import mtcnn as M
+    sds = synth.mtcnn_state_dicts()
+    fr = synth.frames("small", 3)
+    B, H, W, _ = fr.shape
+    taps = {}
+    detect.detect_face(fr, 50, sds["pnet"], sds["rnet"], sds["onet"], [0.6, 0.7, 0.7], 0.709, taps=taps)
+    d_fr = torch.from_numpy(fr).to(dev)
+    for net, size, key_in, key_out, key_box in (("rnet", 24, "rnet_in", "rnet_out", "stage1_boxes"),
+                                               ("onet", 48, "onet_in", "onet_out", "stage2_boxes")):
+        boxes, inds = taps[key_box]
+        y, ey, x, ex = detect.pad(boxes, W, H)
+        cap = 512
+        cnt = torch.zeros(B, dtype=torch.int32)
+        pad = torch.zeros(B, cap, 4, dtype=torch.int32)
+        slot_of = []
+        for k in range(len(y)):
+            b = int(inds[k]); s = int(cnt[b]); cnt[b] += 1
+            pad[b, s] = torch.tensor([x[k], y[k], ex[k], ey[k]], dtype=torch.int32)
+            slot_of.append((b, s))
+        order = sorted(range(len(y)), key=lambda k: slot_of[k])          # flat index = image-major
+        w = (M._pack_rnet if net == "rnet" else M._pack_onet)(sds[net]).to(dev)
+        prob = torch.zeros(B, cap, device=dev); reg = torch.zeros(B, cap, 4, device=dev); lmk = torch.zeros(B, cap, 10, device=dev)
+        offs = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        crops = torch.full((len(y), 3, size, size), float("nan"), device=dev)
+        P = _lib.ptr
+        d_cnt, d_pad = cnt.to(dev), pad.to(dev)
+        if net == "rnet":
+            _lib.call("vnfr_rnet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(offs),
+                      P(crops), _lib.stream_ptr())
+        else:
+            _lib.call("vnfr_onet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(lmk),
+                      P(offs), P(crops), _lib.stream_ptr())
+        torch.cuda.synchronize()
+        ref_in = taps[key_in][order]
+        assert torch.equal(crops.cpu(), ref_in), "%s crops differ: %g" % (net, (crops.cpu() - ref_in).abs().max())
+        outs = taps[key_out]
+        for j, k in enumerate(order):
+            b, s = slot_of[k]
+            assert abs(prob[b, s].item() - outs[-1][k, 1].item()) < 2e-5
+            assert (reg[b, s].cpu() - outs[0][k]).abs().max().item() < 2e-4
+            if net == "onet":
+                assert (lmk[b, s].cpu() - outs[1][k]).abs().max().item() < 2e-4
+
+
+def test_extract_matches_reference_golden(dev, models):
+    """MTCNN.extract on the reference's own boxes: bit-exact against the reference's torch.Tensor crop path."""
+    from oracle import synth
+    g = load_golden("extract_small")
+    fr = synth.frames("small", 2)
+    m = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    faces = m.extract(torch.from_numpy(fr), [g["boxes_0"], g["boxes_1"]], None)
+    for i in range(2):
+        np.testing.assert_array_equal(faces[i].cpu().numpy(), g["faces_tensor_%d" % i])
+        # ndarray inputs use cv2.INTER_AREA in the reference (fractional-coverage weights / bilinear when enlarging):
+        # the same crop through a different resampler -- close on average, not pixel-identical
+        d = np.abs(faces[i].cpu().numpy() - g["faces_ndarray_%d" % i]) * 128.0
+        assert d.mean() < 2.0
+    # forward(): detection + extraction, keep_all and single-face (+margin) variants
+    f, b = m(torch.from_numpy(fr))
+    for i in range(2):
+        assert f[i].shape == g["faces_tensor_%d" % i].shape
+        assert (np.abs(f[i].cpu().numpy() - g["faces_tensor_%d" % i]) * 128.0 > 1.5).mean() < 0.01
+    m2 = models["MTCNN"](image_size=160, margin=14, keep_all=False, min_face_size=50, device=dev)
+    f2, b2, p2 = m2(torch.from_numpy(fr), return_prob=True)
+    got = torch.stack(f2).cpu().numpy()
+    assert got.shape == g["faces_margin14_single"].shape
+    assert (np.abs(got - g["faces_margin14_single"]) * 128.0 > 1.5).mean() < 0.01
+    np.testing.assert_allclose(np.asarray(p2, np.float32), g["probs_margin14_single"], atol=2e-4)
+
+
+def test_alignment_kernel_matches_cv2_path(dev, models):
+    """vnfr_face_crops mode 1 on the reference's own boxes / landmarks vs the oracle's Umeyama + cv2.warpAffine."""
+    import cv2
+    from oracle import align, detect, synth
+    from vn_celeb_face_recognition_b200 import _lib, pipeline
+    sds = synth.mtcnn_state_dicts()
+    fr = synth.frames("small", 2, first_seed=3)
+    B, H, W, _ = fr.shape
+    boxes, probs, lms = detect.mtcnn_detect(fr, sds, min_face_size=50)
+    capf = 8
+    cnt = torch.tensor([len(b) for b in boxes], dtype=torch.int32)
+    box = torch.zeros(B, capf, 5); pts = torch.zeros(B, capf, 10)
+    for i in range(B):
+        box[i, :len(boxes[i]), :4] = torch.from_numpy(boxes[i])
+        pts[i, :len(boxes[i])] = torch.from_numpy(lms[i].reshape(-1, 10))
+    for S in (160, 112):
+        tmpl = pipeline.center_point_dict["(%d, %d)" % (S, S)]
+        F = int(cnt.sum())
+        u8 = torch.zeros(F, S, S, 3, dtype=torch.uint8, device=dev)
+        half = torch.zeros(F, S, S, 8, dtype=torch.float16, device=dev)
+        offs = torch.zeros(B + 1, dtype=torch.int32, device=dev); status = torch.zeros(1, dtype=torch.int32, device=dev)
+        fimg = torch.zeros(F, dtype=torch.int32, device=dev)
+        t = (C.c_float * 10)(*tmpl.reshape(-1).tolist())
+        P = _lib.ptr
+        d_fr, d_cnt, d_box, d_pts = torch.from_numpy(fr).to(dev), cnt.to(dev), box.to(dev), pts.to(dev)
+        _lib.call("vnfr_face_crops", P(d_fr), B, H, W, capf, P(d_cnt), P(d_box), P(d_pts),
+                  1, S, 0, t, 1, F, P(offs), P(u8), P(half), P(fimg), P(status), _lib.stream_ptr())
+        torch.cuda.synchronize()
+        got = u8.cpu().numpy()
+        k = 0
+        for i in range(B):
+            crops, idx = align.get_face_from_boxes(fr[i], boxes[i])
+            for c, j in zip(crops, idx):
+                ref = align.alignment(c, tmpl, lms[i][j] - boxes[i][j][:2], S, S)
+                d = np.abs(got[k].astype(int) - ref.astype(int))
+                assert d.max() <= 1 and (d > 0).mean() < 2e-3, "face %d: max %d, frac %.4f" % (k, d.max(), (d > 0).mean())
+                exp_h = (torch.from_numpy(got[k]).float() - 127.5) / 128.0
+                assert torch.equal(half[k, :, :, :3].cpu().float(), exp_h.half().float()) and (half[k, :, :, 3:] == 0).all()
+                assert fimg[k].item() == i
+                k += 1
+
+
+def test_demo_video_path_matches_reference_golden(dev, models):
+    """parallel_detect_and_align + recognize_celeb (demo_video.py:117-129) end to end: aligned faces, boxes, labels."""
+    import pandas as pd
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import pipeline
+    g = load_golden("demo_video_small")
+    fr = synth.frames("small", 2, first_seed=3)
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    cp = pipeline.center_point_dict["(160, 160)"]
+    faces, boxes = pipeline.parallel_detect_and_align(list(fr), det, cp, (160, 160))
+    name_df = pd.DataFrame({"label": np.arange(1001), "name": ["id%d" % i for i in range(1001)]})
+    names = pipeline.recognize_celeb(faces, dev, models["enc"], models["mlp"], pipeline.transforms_default, name_df, 0.0)
+    for i in range(2):
+        assert_boxes_match(np.asarray(boxes[i]), g["boxes_%d" % i], 0.99)
+        # boxes / landmarks agree with the reference to ~1e-4 px (fp32 conv order); a 1/32-px flip in the warp's fixed
+        # point coordinates moves a pixel by a few grey levels at sharp edges -- the kernel itself is pinned to <= 1
+        # level on identical inputs in test_alignment_kernel_matches_cv2_path
+        d = np.abs(np.stack(faces[i]).astype(int) - g["aligned_%d" % i].astype(int))
+        assert d.max() <= 16 and (d > 1).mean() < 0.01 and d.mean() < 0.1
+        assert [int(n[2:]) for n in names[i]] == g["labels_%d" % i].tolist()
+    # fused device pipeline == staged API
+    fp = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", cp)
+    res = fp(fr)
+    for i in range(2):
+        assert res[i]["labels"].tolist() == g["labels_%d" % i].tolist()
+        assert_boxes_match(res[i]["boxes"], g["boxes_%d" % i], 0.99)
+    # threshold -> "Unknown" = num_classes (demo_image.py:131-137)
+    fp2 = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", cp, threshold=1.1)
+    assert all((r["labels"] == 1001).all() for r in fp2(fr))
+    names_unknown = pipeline.recognize_celeb(faces, dev, models["enc"], models["mlp"], pipeline.transforms_default, name_df, 1.1)
+    assert all(n == "Unknown" for x in names_unknown for n in x)
+
+
+def test_cal_embedding_matches_reference_golden(dev, models, tmp_path):
+    """find_embedding.cal_embedding (find_embedding.py:45-59) on the 20 bundled PNGs: same files, same .npz format."""
+    import os
+    import torchvision.transforms as tf
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import pipeline
+    g = load_golden("find_embedding_bundled")
+    tr = tf.Compose([tf.Resize(160), pipeline.transforms_default])
+    pipeline.cal_embedding(os.path.join(synth.ASSETS, "faces"), 64, models["enc"], tr, str(tmp_path), dev)
+    files = sorted(os.listdir(tmp_path))
+    assert files == [str(f) for f in g["files"]]
+    embs = np.stack([np.load(os.path.join(tmp_path, f))["arr_0"] for f in files])
+    assert embs.shape == (20, 512) and embs.dtype == np.float32
+    cos = (embs * g["emb"]).sum(1)
+    assert cos.min() >= 0.999, cos
+    # batch size dividing the file count: the reference crashes on the empty trailing batch, we skip it
+    pipeline.cal_embedding(os.path.join(synth.ASSETS, "faces"), 10, models["enc"], tr, str(tmp_path / "b10"), dev)
+    assert len(os.listdir(tmp_path / "b10")) == 20

@@ -53,6 +53,12 @@ _SIGS = {
     "vnfr_pnet_set_weights": [_P, _I, _P],
     "vnfr_pnet_sweep_compact": [C.POINTER(Pyramid), _P, _F, _I, _P, _P, _P, _P, _P, _P, _P],
     "vnfr_nms_segments": [_I, _I, _P, _P, _P, _F, _I, _P, _P, _P],
+    "vnfr_stage1_boxes": [C.POINTER(Pyramid), _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "vnfr_rnet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
+    "vnfr_onet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "vnfr_stage2_boxes": [_I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P],
+    "vnfr_stage3_faces": [_I, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P],
+    "vnfr_face_crops": [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P],
     "vnfr_conv_prepare": [C.POINTER(ConvOp)],
     "vnfr_conv_run": [C.POINTER(ConvOp), _P],
     "vnfr_run_ops": [C.POINTER(Op), _I, _P],
@@ -74,6 +80,8 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.vnfr_last_error.restype = C.c_char_p
         l.vnfr_launch_count.restype = C.c_longlong
+        l.vnfr_rnet_weight_floats.restype = C.c_int
+        l.vnfr_onet_weight_floats.restype = C.c_int
         for name, args in _SIGS.items():
             fn = getattr(l, name)      # AttributeError if the symbol is missing: fail loudly
             fn.argtypes = args
@@ -83,7 +91,8 @@ def lib():
 
 
 def exported_symbols():
-    return ["vnfr_last_error", "vnfr_version", "vnfr_launch_count"] + sorted(_SIGS)
+    return ["vnfr_last_error", "vnfr_version", "vnfr_launch_count", "vnfr_rnet_weight_floats",
+            "vnfr_onet_weight_floats"] + sorted(_SIGS)
 
 
 def check(rc):

@@ -1,0 +1,410 @@
+// R-Net and O-Net: batched crop -> area-resize -> normalise -> network heads, one persistent kernel per net.
+//
+// Replaces the per-candidate Python loops detect_face.py:108-114 / :136-143 (slice + imresample(24|48) + cat +
+// normalise; ~256 launch chains per 1080p frame in the reference), fixed_batch_process (:16-23) and RNet.forward /
+// ONet.forward (mtcnn.py:84-99, :138-157).  Each CTA takes G candidates at a time: the crops are area-resized straight
+// from the u8 frame into shared memory (exact integer window sums, sum/kh/kw in fp32 like torch), every layer's
+// activations stay in shared memory, weights ([K][Cout] fp32, L2-resident) are read with warp-uniform 16-byte loads.
+// Arithmetic is fp32 FMA: the `score > threshold` decisions of stages 2/3 must match the fp32 reference.
+#include "common.cuh"
+#include <math_constants.h>
+
+extern long long g_vnfr_launches;
+
+namespace {
+
+constexpr int NT = 512;   // threads per CTA
+
+__device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv (valid, stride 1) + bias + PReLU on shared-memory activations for output channels [c_begin, c_end).
+//   in  [G][CIN][IH][IW]   out [G][c_end - c_begin][OH][OW] (channel c stored at index c - c_begin)
+//   w   [CIN*KH*KW][COUT] global, k = (ci*KH + ky)*KW + kx
+// Thread item = (4 output channels) x (4 positions p, p+NQ, p+2NQ, p+3NQ): 16 FMA per 4 LDS + one 16-byte weight load.
+template <int CIN, int COUT, int KH, int KW, int IH, int IW, int G>
+__device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
+                                                const float* __restrict__ bias, const float* __restrict__ alpha, int c_begin,
+                                                int c_end) {
+  constexpr int OH = IH - KH + 1, OW = IW - KW + 1, NPOS = G * OH * OW, NQ = (NPOS + 3) / 4;
+  const int ngroups = (c_end - c_begin) >> 2;
+  for (int item = threadIdx.x; item < ngroups * NQ; item += NT) {
+    const int cg = item / NQ, q = item - cg * NQ;
+    const int c0 = c_begin + 4 * cg;
+    int off[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = q + j * NQ;
+      ok[j] = p < NPOS;
+      const int pp = ok[j] ? p : 0;
+      const int g = pp / (OH * OW), r = pp - g * (OH * OW);
+      const int oy = r / OW, ox = r - oy * OW;
+      off[j] = (g * CIN * IH + oy) * IW + ox;
+    }
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+    const float* wp = w + c0;
+#pragma unroll 2
+    for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + ((ci * KH + ky) * KW + kx) * COUT));
+          const int o = (ci * IH + ky) * IW + kx;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v = in[off[j] + o];
+            acc[j][0] = fmaf(w4.x, v, acc[j][0]);
+            acc[j][1] = fmaf(w4.y, v, acc[j][1]);
+            acc[j][2] = fmaf(w4.z, v, acc[j][2]);
+            acc[j][3] = fmaf(w4.w, v, acc[j][3]);
+          }
+        }
+    }
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + c0));
+    const float al[4] = {a4.x, a4.y, a4.z, a4.w};
+    const int cn = c_end - c_begin;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      const int p = q + j * NQ;
+      const int g = p / (OH * OW), r = p - g * (OH * OW);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) out[(g * cn + 4 * cg + c) * (OH * OW) + r] = prelu(acc[j][c], al[c]);
+    }
+  }
+}
+
+// MaxPool2d(K, stride 2, ceil_mode=True) on [NC][IH][IW] -> [NC][OH][OW]  (windows clipped at the border)
+template <int K, int IH, int IW>
+__device__ __forceinline__ void maxpool_smem(const float* __restrict__ in, float* __restrict__ out, int nc) {
+  constexpr int OH = (IH - K + 1) / 2 + 1, OW = (IW - K + 1) / 2 + 1;
+  for (int i = threadIdx.x; i < nc * OH * OW; i += NT) {
+    const int c = i / (OH * OW), r = i - c * (OH * OW);
+    const int oy = r / OW, ox = r - oy * OW;
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int y = 2 * oy + ky, x = 2 * ox + kx;
+        if (y < IH && x < IW) m = fmaxf(m, in[(c * IH + y) * IW + x]);
+      }
+    out[i] = m;
+  }
+}
+
+// Fully connected + bias + PReLU: in [G][K] smem, w [K][COUT] global, out [G][COUT] smem.  The K range is split over the
+// 16 warps (each lane owns COUT/32 consecutive outputs), partial sums are combined through `scratch` [16][G][COUT].
+template <int K, int COUT, int G>
+__device__ __forceinline__ void fc_prelu_smem(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ scratch,
+                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                              const float* __restrict__ alpha) {
+  constexpr int V = COUT / 32, NW = NT / 32, KS = (K + NW - 1) / NW;
+  static_assert(V == 4 || V == 8, "COUT must be 128 or 256");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[G][V];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[g][v] = 0.f;
+  const int k0 = warp * KS, k1 = min(K, k0 + KS);
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    float wv[V];
+    const float4* wr = reinterpret_cast<const float4*>(w + (size_t)k * COUT + lane * V);
+#pragma unroll
+    for (int v4 = 0; v4 < V / 4; ++v4) {
+      const float4 t = __ldg(wr + v4);
+      wv[4 * v4] = t.x; wv[4 * v4 + 1] = t.y; wv[4 * v4 + 2] = t.z; wv[4 * v4 + 3] = t.w;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float x = in[g * K + k];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[g][v] = fmaf(wv[v], x, acc[g][v]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int v = 0; v < V; ++v) scratch[(warp * G + g) * COUT + lane * V + v] = acc[g][v];
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * COUT; i += NT) {
+    const int j = i % COUT;
+    float s = __ldg(bias + j);
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) s += scratch[ww * G * COUT + i];
+    out[i] = prelu(s, __ldg(alpha + j));
+  }
+}
+
+// crop imgs[b, :, y-1:ey, x-1:ex] -> adaptive-average-pool to SxS -> (v-127.5)*0.0078125   (detect_face.py:111-114)
+template <int S>
+__device__ __forceinline__ void crop_resize_smem(const uint8_t* __restrict__ frame, int W, int4 pad, float* __restrict__ dst) {
+  const int x0 = pad.x - 1, y0 = pad.y - 1;
+  const int cw = pad.z - x0, ch = pad.w - y0;
+  for (int i = threadIdx.x; i < S * S; i += NT) {
+    const int oy = i / S, ox = i - oy * S;
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (cw > 0 && ch > 0) {
+      const int ys = (oy * ch) / S, ye = ((oy + 1) * ch + S - 1) / S;
+      const int xs = (ox * cw) / S, xe = ((ox + 1) * cw + S - 1) / S;
+      unsigned s0 = 0, s1 = 0, s2 = 0;
+      for (int y = ys; y < ye; ++y) {
+        const uint8_t* row = frame + ((size_t)(y0 + y) * W + (x0 + xs)) * 3;
+        for (int x = 0; x < xe - xs; ++x) {
+          s0 += __ldg(row + 3 * x); s1 += __ldg(row + 3 * x + 1); s2 += __ldg(row + 3 * x + 2);
+        }
+      }
+      const float kh = (float)(ye - ys), kw = (float)(xe - xs);
+      r0 = mul_rn(sub_rn(div_rn(div_rn((float)s0, kh), kw), 127.5f), 0.0078125f);
+      r1 = mul_rn(sub_rn(div_rn(div_rn((float)s1, kh), kw), 127.5f), 0.0078125f);
+      r2 = mul_rn(sub_rn(div_rn(div_rn((float)s2, kh), kw), 127.5f), 0.0078125f);
+    }
+    dst[i] = r0; dst[S * S + i] = r1; dst[2 * S * S + i] = r2;
+  }
+}
+
+// flat crop index -> (image, slot) through the exclusive scan of per-image counts
+__device__ __forceinline__ void locate(const int* __restrict__ offs, int B, int flat, int& b, int& slot) {
+  int lo = 0, hi = B;            // largest b with offs[b] <= flat
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offs[mid] <= flat) lo = mid; else hi = mid;
+  }
+  b = lo;
+  slot = flat - offs[lo];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed weight layouts (floats); produced by models/mtcnn.py::_pack_rnet / _pack_onet
+struct RW {   // R-Net
+  static constexpr int W1 = 0, B1 = W1 + 27 * 28, A1 = B1 + 28;
+  static constexpr int W2 = A1 + 28, B2 = W2 + 252 * 48, A2 = B2 + 48;
+  static constexpr int W3 = A2 + 48, B3 = W3 + 192 * 64, A3 = B3 + 64;
+  static constexpr int W4 = A3 + 64, B4 = W4 + 576 * 128, A4 = B4 + 128;
+  static constexpr int W5 = A4 + 128, B5 = W5 + 128 * 8, END = B5 + 8;   // heads: cols 0-1 logits, 2-5 reg
+};
+struct OW_ {  // O-Net
+  static constexpr int W1 = 0, B1 = W1 + 27 * 32, A1 = B1 + 32;
+  static constexpr int W2 = A1 + 32, B2 = W2 + 288 * 64, A2 = B2 + 64;
+  static constexpr int W3 = A2 + 64, B3 = W3 + 576 * 64, A3 = B3 + 64;
+  static constexpr int W4 = A3 + 64, B4 = W4 + 256 * 128, A4 = B4 + 128;
+  static constexpr int W5 = A4 + 128, B5 = W5 + 1152 * 256, A5 = B5 + 256;
+  static constexpr int W6 = A5 + 256, B6 = W6 + 256 * 16, END = B6 + 16;  // heads: 0-1 logits, 2-5 reg, 6-15 landmarks
+};
+
+struct HeadArgs {
+  const uint8_t* frames;
+  int B, H, W, cap;
+  const int* count;      // [B]
+  const int4* pad;       // [B][cap]  (x, y, ex, ey)
+  const int* offs;       // [B+1] exclusive scan of min(count, cap)
+  const float* w;
+  float* prob;           // [B][cap]
+  float4* reg;           // [B][cap]
+  float* lmk;            // [B][cap][10] (O-Net)
+  float* crops_out;      // nullable, [flat][3][S][S]
+};
+
+// ------------------------------------------------------------------------------------------------------- R-Net
+constexpr int RG = 4;     // candidates per CTA pass
+constexpr int R_A = RG * 3 * 24 * 24;        // 6912   input / pool2 / fc4 out
+constexpr int R_B = RG * 28 * 11 * 11;       // 13552  pooled conv1 / conv3 out
+constexpr int R_C = RG * 48 * 9 * 9;         // 15552  conv1 channel-slab temp (8 ch: 15488) / conv2 out / fc scratch
+constexpr int R_SMEM = (R_A + R_B + R_C) * 4;
+
+__global__ void __launch_bounds__(NT, 1) rnet_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm; float* Bf = sm + R_A; float* Cf = Bf + R_B;
+  const int total = a.offs[a.B];
+  const float* w = a.w;
+  for (int base = blockIdx.x * RG; base < total; base += gridDim.x * RG) {
+    __shared__ int s_b[RG], s_slot[RG];
+    if (threadIdx.x < RG) {
+      int b = 0, slot = 0;
+      if (base + threadIdx.x < total) locate(a.offs, a.B, base + threadIdx.x, b, slot);
+      s_b[threadIdx.x] = (base + threadIdx.x < total) ? b : -1;
+      s_slot[threadIdx.x] = slot;
+    }
+    __syncthreads();
+    for (int g = 0; g < RG; ++g) {
+      if (s_b[g] >= 0) {
+        const int4 pd = a.pad[(size_t)s_b[g] * a.cap + s_slot[g]];
+        crop_resize_smem<24>(a.frames + (size_t)s_b[g] * a.H * a.W * 3, a.W, pd, A + g * 3 * 576);
+      } else {
+        for (int i = threadIdx.x; i < 3 * 576; i += NT) A[g * 3 * 576 + i] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (a.crops_out != nullptr)
+      for (int i = threadIdx.x; i < RG * 3 * 576; i += NT)
+        if (base + i / (3 * 576) < total) a.crops_out[(size_t)base * 3 * 576 + i] = A[i];
+    // conv1 3->28 (3x3) + PReLU in slabs of 8 channels -> maxpool 3/2 ceil -> Bf [RG][28][11][11]
+    for (int c0 = 0; c0 < 28; c0 += 8) {
+      const int c1 = min(28, c0 + 8), cn = c1 - c0;
+      conv_prelu_smem<3, 28, 3, 3, 24, 24, RG>(A, Cf, w + RW::W1, w + RW::B1, w + RW::A1, c0, c1);   // Cf [RG][cn][22][22]
+      __syncthreads();
+      for (int g = 0; g < RG; ++g) {
+        // pool channel slab of candidate g into its place in Bf
+        constexpr int OH = 11;
+        for (int i = threadIdx.x; i < cn * OH * OH; i += NT) {
+          const int c = i / (OH * OH), r = i - c * (OH * OH);
+          const int oy = r / OH, ox = r - oy * OH;
+          float m = -CUDART_INF_F;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int y = 2 * oy + ky, x = 2 * ox + kx;
+              if (y < 22 && x < 22) m = fmaxf(m, Cf[((g * cn + c) * 22 + y) * 22 + x]);
+            }
+          Bf[((g * 28 + c0 + c) * OH + oy) * OH + ox] = m;
+        }
+      }
+      __syncthreads();
+    }
+    conv_prelu_smem<28, 48, 3, 3, 11, 11, RG>(Bf, Cf, w + RW::W2, w + RW::B2, w + RW::A2, 0, 48);      // Cf [RG][48][9][9]
+    __syncthreads();
+    maxpool_smem<3, 9, 9>(Cf, A, RG * 48);                                                            // A  [RG][48][4][4]
+    __syncthreads();
+    conv_prelu_smem<48, 64, 2, 2, 4, 4, RG>(A, Bf, w + RW::W3, w + RW::B3, w + RW::A3, 0, 64);         // Bf [RG][64][3][3] = [RG][576]
+    __syncthreads();
+    fc_prelu_smem<576, 128, RG>(Bf, A, Cf, w + RW::W4, w + RW::B4, w + RW::A4);                        // A  [RG][128]
+    __syncthreads();
+    if (threadIdx.x < RG * 8) {
+      const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+      float s = __ldg(w + RW::B5 + j);
+      for (int k = 0; k < 128; ++k) s = fmaf(__ldg(w + RW::W5 + k * 8 + j), A[g * 128 + k], s);
+      Cf[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < RG && s_b[threadIdx.x] >= 0) {
+      const int g = threadIdx.x;
+      const float l0 = Cf[g * 8], l1 = Cf[g * 8 + 1];
+      const float mx = fmaxf(l0, l1);
+      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+      const size_t o = (size_t)s_b[g] * a.cap + s_slot[g];
+      const int4 pd = a.pad[o];
+      const bool empty = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);      // detect_face.py:110 would skip this crop
+      a.prob[o] = empty ? 0.f : e1 / (e0 + e1);
+      a.reg[o] = make_float4(Cf[g * 8 + 2], Cf[g * 8 + 3], Cf[g * 8 + 4], Cf[g * 8 + 5]);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------- O-Net
+constexpr int O_A = 3 * 48 * 48;             // 6912   input / pool2 out (6400) / pool3 out / fc5 out
+constexpr int O_B = 32 * 23 * 23;            // 16928  pooled conv1 / conv3 out (4096) / conv4 out (1152)
+constexpr int O_C = 64 * 21 * 21;            // 28224  conv1 slab temp (8 ch: 16928) / conv2 out / fc scratch (4096)
+constexpr int O_SMEM = (O_A + O_B + O_C) * 4;
+
+__global__ void __launch_bounds__(NT, 1) onet_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm; float* Bf = sm + O_A; float* Cf = Bf + O_B;
+  const int total = a.offs[a.B];
+  const float* w = a.w;
+  for (int flat = blockIdx.x; flat < total; flat += gridDim.x) {
+    __shared__ int s_b, s_slot;
+    if (threadIdx.x == 0) { int b, slot; locate(a.offs, a.B, flat, b, slot); s_b = b; s_slot = slot; }
+    __syncthreads();
+    const size_t o = (size_t)s_b * a.cap + s_slot;
+    const int4 pd = a.pad[o];
+    crop_resize_smem<48>(a.frames + (size_t)s_b * a.H * a.W * 3, a.W, pd, A);
+    __syncthreads();
+    if (a.crops_out != nullptr)
+      for (int i = threadIdx.x; i < O_A; i += NT) a.crops_out[(size_t)flat * O_A + i] = A[i];
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      conv_prelu_smem<3, 32, 3, 3, 48, 48, 1>(A, Cf, w + OW_::W1, w + OW_::B1, w + OW_::A1, c0, c0 + 8);   // Cf [8][46][46]
+      __syncthreads();
+      maxpool_smem<3, 46, 46>(Cf, Bf + c0 * 23 * 23, 8);                                                 // Bf [32][23][23]
+      __syncthreads();
+    }
+    conv_prelu_smem<32, 64, 3, 3, 23, 23, 1>(Bf, Cf, w + OW_::W2, w + OW_::B2, w + OW_::A2, 0, 64);       // Cf [64][21][21]
+    __syncthreads();
+    maxpool_smem<3, 21, 21>(Cf, A, 64);                                                                  // A  [64][10][10]
+    __syncthreads();
+    conv_prelu_smem<64, 64, 3, 3, 10, 10, 1>(A, Bf, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);        // Bf [64][8][8]
+    __syncthreads();
+    maxpool_smem<2, 8, 8>(Bf, A, 64);                                                                    // A  [64][4][4]
+    __syncthreads();
+    conv_prelu_smem<64, 128, 2, 2, 4, 4, 1>(A, Bf, w + OW_::W4, w + OW_::B4, w + OW_::A4, 0, 128);        // Bf [128][3][3] = [1152]
+    __syncthreads();
+    fc_prelu_smem<1152, 256, 1>(Bf, A, Cf, w + OW_::W5, w + OW_::B5, w + OW_::A5);                        // A  [256]
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      const int j = threadIdx.x;
+      float s = __ldg(w + OW_::B6 + j);
+      for (int k = 0; k < 256; ++k) s = fmaf(__ldg(w + OW_::W6 + k * 16 + j), A[k], s);
+      Cf[j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float l0 = Cf[0], l1 = Cf[1];
+      const float mx = fmaxf(l0, l1);
+      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+      const bool empty = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);
+      a.prob[o] = empty ? 0.f : e1 / (e0 + e1);
+      a.reg[o] = make_float4(Cf[2], Cf[3], Cf[4], Cf[5]);
+    }
+    if (threadIdx.x < 10) a.lmk[o * 10 + threadIdx.x] = Cf[6 + threadIdx.x];
+    __syncthreads();
+  }
+}
+
+__global__ void scan_counts_kernel(const int* __restrict__ count, int B, int cap, int* __restrict__ offs) {
+  // B is small (frames per batch): a single thread does the exclusive scan
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int s = 0;
+    for (int b = 0; b < B; ++b) { offs[b] = s; s += min(count[b], cap); }
+    offs[B] = s;
+  }
+}
+
+}  // namespace
+
+extern "C" int vnfr_rnet_weight_floats(void) { return RW::END; }
+extern "C" int vnfr_onet_weight_floats(void) { return OW_::END; }
+
+static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                    const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops_out, void* stream) {
+  VNFR_REQUIRE(frames && count && pad && weights && prob && reg && offs, "null pointer");
+  VNFR_REQUIRE(!onet || lmk != nullptr, "O-Net needs a landmark buffer");
+  if (B == 0) return VNFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_counts_kernel<<<1, 32, 0, st>>>(count, B, cap, offs);
+  ++g_vnfr_launches;
+  HeadArgs a;
+  a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
+  a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
+  a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops_out = crops_out;
+  static bool attr = false;
+  if (!attr) {
+    VNFR_CUDA(cudaFuncSetAttribute(rnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(onet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O_SMEM));
+    attr = true;
+  }
+  // persistent grid: one CTA per SM (shared memory bound), each loops over the flat candidate list
+  if (onet) onet_kernel<<<148 * 1, NT, O_SMEM, st>>>(a);
+  else rnet_kernel<<<148 * 1, NT, R_SMEM, st>>>(a);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_rnet_forward(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                                 const float* weights, float* prob, float* reg, int32_t* offs, float* crops_out, void* stream) {
+  return run_head(false, frames, B, H, W, cap, count, pad, weights, prob, reg, nullptr, offs, crops_out, stream);
+}
+
+extern "C" int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                                 const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops_out,
+                                 void* stream) {
+  return run_head(true, frames, B, H, W, cap, count, pad, weights, prob, reg, lmk, offs, crops_out, stream);
+}

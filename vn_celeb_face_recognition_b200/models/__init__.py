@@ -3,7 +3,4 @@
 conventions; every forward runs hand-written sm_100a kernels through the C-ABI of include/vnfr_b200.h."""
 from .inception_resnet_v1 import InceptionResnetV1
 from .mlp_model import MLPModel
-try:
-    from .mtcnn import MTCNN
-except ImportError:      # pragma: no cover  (during bring-up only)
-    pass
+from .mtcnn import MTCNN, fixed_image_standardization, prewhiten

@@ -1,0 +1,222 @@
+"""Host-side mirror of the reference's pipeline glue for the hot path, plus the fused device pipeline.
+
+Reference-facing functions (same names / arguments / returns as the reference):
+  * ``parallel_detect_and_align``  demo_image.py:273-306
+  * ``recognize_celeb``            demo_image.py:50-76
+  * ``find_embedding``             demo_image.py:30-34
+  * ``identify_person``            demo_image.py:113-147
+  * ``transforms_default``         data_loader/__init__.py:27-34, 52-56
+  * ``cal_embedding`` and helpers  find_embedding.py:11-59
+  * ``center_point_dict``          align_face.py:12-48
+``FacePipeline`` is the same path without the host round trips between stages: frames (u8, device) -> MTCNN cascade ->
+aligned crops -> InceptionResnetV1 -> MLP -> labels, one read-back at the end.
+"""
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _lib, encoder_plan
+
+center_point_dict = {
+    "(96, 112)": np.array([[30.2946, 51.6963], [65.5318, 51.5014], [48.0252, 71.7366], [33.5493, 92.3655],
+                           [62.7299, 92.2041]], dtype=np.float32),
+    "(112, 112)": np.array([[38.2946, 51.6963], [73.5318, 51.5014], [56.0252, 71.7366], [41.5493, 92.3655],
+                            [70.7299, 92.2041]], dtype=np.float32),
+    "(150, 150)": np.array([[51.287415, 69.23612], [98.48009, 68.97509], [75.03375, 96.075806], [55.646385, 123.7038],
+                            [94.72754, 123.48763]], dtype=np.float32),
+    "(160, 160)": np.array([[54.706573, 73.85186], [105.045425, 73.573425], [80.036, 102.48086], [59.356144, 131.95071],
+                            [101.04271, 131.72014]], dtype=np.float32),
+    "(224, 224)": np.array([[76.589195, 103.3926], [147.0636, 103.0028], [112.0504, 143.4732], [83.098595, 184.731],
+                            [141.4598, 184.4082]], dtype=np.float32),
+}
+
+
+def transforms_default(face):
+    """np.float32 -> (x - 127.5) / 128 -> HWC -> CHW tensor (data_loader/__init__.py:27-34, 52-56)."""
+    arr = (np.float32(face) - 127.5) / 128
+    return torch.from_numpy(np.ascontiguousarray(np.transpose(arr, (2, 0, 1))))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused device pipeline
+# ----------------------------------------------------------------------------------------------------------------
+class FacePipeline:
+    """detect -> align/crop -> embed -> classify on the device.
+
+    align="similarity": demo_video semantics (get_face_from_boxes + 5-point similarity + cv2.warpAffine);
+    align="extract":    MTCNN.extract semantics (box crop + area resize + fixed_image_standardization)."""
+
+    def __init__(self, detector, encoder, classifier=None, target_fs=(160, 160), align="similarity", center_point=None,
+                 threshold=0.0, max_faces_per_frame=32):
+        assert target_fs[0] == target_fs[1], "square targets only"
+        self.det, self.enc, self.cls = detector, encoder, classifier
+        self.S = int(target_fs[0])
+        self.mode = 1 if align == "similarity" else 0
+        self.template = center_point if center_point is not None else center_point_dict.get(str(tuple(target_fs)))
+        if self.mode == 1 and self.template is None:
+            raise ValueError("no landmark template for target size %s" % (target_fs,))
+        self.threshold = threshold
+        self.max_faces_per_frame = max_faces_per_frame
+
+    def run_device(self, frames_u8):
+        """frames_u8: CUDA uint8 (B,H,W,3).  Returns a dict of DEVICE tensors + the face count (one tiny sync to size
+        the encoder batch): count (B,), boxes (B,capf,5), points (B,capf,10), faces_u8 (F,S,S,3), emb (F,512),
+        label (F,), prob (F,), face_img (F,)."""
+        with torch.no_grad():
+            ws = self.det.detect_device(frames_u8)
+            dt = self.enc.half_dtype or encoder_plan.HALF
+            u8, half, fimg, cap = self.det.face_crops_device(ws, self.mode, self.S, self.det.margin, self.template, dt,
+                                                            ws.B * self.max_faces_per_frame)
+            host = ws.counters[-(ws.B + 1):].cpu().numpy()       # out_count (B) + status: the only mid-pipeline read-back
+            self.det.check_status(int(host[-1]))
+            F = int(host[:-1].sum())
+            out = {"count": ws.out_count, "boxes": ws.out_box, "points": ws.out_pts, "n_faces": F, "faces_u8": u8[:F],
+                   "face_img": fimg[:F], "count_host": host[:-1].copy()}
+            if F == 0:
+                dev = frames_u8.device
+                out.update(emb=torch.zeros(0, 512, device=dev), label=torch.zeros(0, dtype=torch.int64, device=dev),
+                           prob=torch.zeros(0, device=dev))
+                return out
+            emb, emb16 = self.enc.embed_nhwc8(half[:F])
+            out["emb"] = emb
+            if self.cls is not None:
+                label, prob = self.cls.classify_half(emb16)
+                # identify_person thresholding (demo_image.py:131-137): below threshold -> num_classes ("Unknown")
+                if self.threshold and self.threshold > 0:
+                    label = torch.where(prob >= self.threshold, label, torch.full_like(label, self.cls.num_classes))
+                out["label"], out["prob"] = label, prob
+        return out
+
+    def __call__(self, frames):
+        """frames: (B,H,W,3) uint8 numpy / torch (host or device).  Returns per-frame lists (boxes (n,4) numpy, labels,
+        probs) plus the (F,512) embeddings -- one H2D of the frames, one D2H of the results."""
+        dev = self.det._cuda_device()
+        t = torch.as_tensor(frames)
+        if not t.is_cuda:
+            t = t.to(dev, non_blocking=True)
+        out = self.run_device(t)
+        cnt = out["count_host"]
+        F = out["n_faces"]
+        nmax = int(cnt.max()) if len(cnt) else 0
+        boxes = out["boxes"][:, :max(nmax, 1)].cpu().numpy()
+        lab = out["label"].cpu().numpy() if "label" in out else np.zeros(F, np.int64)
+        prob = out["prob"].cpu().numpy() if "prob" in out else np.zeros(F, np.float32)
+        emb = out["emb"].cpu().numpy()
+        res, o = [], 0
+        for b in range(len(cnt)):
+            n = int(cnt[b])
+            res.append({"boxes": boxes[b, :n, :4].copy(), "det_prob": boxes[b, :n, 4].copy(), "labels": lab[o:o + n].copy(),
+                        "probs": prob[o:o + n].copy(), "emb": emb[o:o + n]})
+            o += n
+        return res
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference-facing glue
+# ----------------------------------------------------------------------------------------------------------------
+def parallel_detect_and_align(rgb_images, detection_md, center_point, target_fs, log=False):
+    """demo_image.py:273-306: returns (list[list[u8 (S,S,3) RGB]], list[list[box (4,)]]) on the host."""
+    dev = detection_md._cuda_device()
+    frames = torch.as_tensor(np.stack([np.asarray(im) for im in rgb_images])).to(dev)
+    with torch.no_grad():
+        ws = detection_md.detect_device(frames)
+        u8, _, _, _ = detection_md.face_crops_device(ws, 1, int(target_fs[0]), 0, center_point)
+        cnt = ws.out_count.cpu().numpy()
+        detection_md.check_status(int(ws.status.item()))
+        F = int(cnt.sum())
+        faces = u8[:F].cpu().numpy()
+        nmax = int(cnt.max()) if len(cnt) else 0
+        boxes = ws.out_box[:, :max(nmax, 1), :4].cpu().numpy()
+    bth_faces, bth_boxes, o = [], [], 0
+    for b in range(len(cnt)):
+        n = int(cnt[b])
+        bth_faces.append([faces[o + i] for i in range(n)])
+        bth_boxes.append([boxes[b, i].copy() for i in range(n)])
+        if n == 0 and log:
+            print("Face not found in this image !")
+        o += n
+    return bth_faces, bth_boxes
+
+
+def find_embedding(image_tensor, embedding_model):
+    """demo_image.py:30-34."""
+    embedding_model.eval()
+    with torch.no_grad():
+        embeddings = embedding_model(image_tensor)
+    return embeddings.detach()
+
+
+def identify_person(embeddings, classify_model, name_df, threshold):
+    """demo_image.py:113-147: argmax, exp(log-prob), (per-class) threshold -> label or num_classes, name lookup."""
+    classify_model.eval()
+    with torch.no_grad():
+        output = classify_model(embeddings)
+    n_classes = output.size(1)
+    predictions = torch.argmax(output, dim=1).detach().cpu().numpy()
+    probs = torch.exp(output).detach().cpu().numpy()
+    chosen_prob = probs[np.arange(len(predictions)), predictions]
+    if type(threshold) is float:
+        thr = np.full(len(predictions), threshold)
+    else:
+        thr = np.array([threshold[str(p)] for p in predictions])
+    filtered = np.where(chosen_prob >= thr, predictions, n_classes)
+    # vectorised replacement of the per-face pandas scan (demo_image.py:139-145): first name per label
+    lookup = {}
+    for lab, name in zip(name_df["label"].tolist(), name_df["name"].tolist()):
+        lookup.setdefault(lab, name)
+    return [lookup.get(int(p), "Unknown") for p in filtered]
+
+
+def recognize_celeb(bth_alg_face_list, device, emb_model, classify_model, transforms, label2name_df, threshold):
+    """demo_image.py:50-76."""
+    flat = [f for x in bth_alg_face_list for f in x]
+    if len(flat) == 0:
+        return [[] for _ in bth_alg_face_list]
+    tf = torch.stack([transforms(f) for f in flat], dim=0)
+    embeddings = find_embedding(tf.to(device), emb_model)
+    names = identify_person(embeddings, classify_model, label2name_df, threshold)
+    out, c = [], 0
+    for x in bth_alg_face_list:
+        out.append(names[c:c + len(x)])
+        c += len(x)
+    return out
+
+
+# find_embedding.py -------------------------------------------------------------------------------------------------
+def create_batch_images(list_files, batch_size):
+    """find_embedding.py:11-20 -- including the reference's trailing (possibly empty) batch."""
+    n_batchs = len(list_files) // batch_size
+    batches = [list_files[i * batch_size:(i + 1) * batch_size] for i in range(n_batchs)]
+    batches.append(list_files[n_batchs * batch_size:])
+    return batches, n_batchs
+
+
+def create_image_tensors(data_dir_path, list_files, transforms):
+    """find_embedding.py:23-32."""
+    from PIL import Image
+    return torch.stack([transforms(Image.open(str(Path(data_dir_path) / f))) for f in list_files], 0)
+
+
+def save_embeddings(embeddings, list_files, output_dir):
+    """find_embedding.py:34-42: one ``<stem>.npz`` per image, key ``arr_0``, (512,) fp32 -- the wire format
+    VNCelebEmbDataset reads (data_loader/vn_celeb_emb_dataset.py:14)."""
+    for i in range(embeddings.shape[0]):
+        np.savez_compressed(str(Path(output_dir) / "{}.npz".format(list_files[i].split(".")[0])), embeddings[i])
+
+
+def cal_embedding(data_dir, batch_size, model, transforms, output_dir, device):
+    """find_embedding.py:45-59.  Unlike the reference an EMPTY trailing batch is skipped instead of crashing in
+    torch.stack (the reference raises when len(files) % batch_size == 0)."""
+    os.makedirs(output_dir, exist_ok=True)
+    model.eval()
+    list_files = sorted(os.listdir(data_dir))
+    batches, n_batchs = create_batch_images(list_files, batch_size)
+    for batch_file in batches:
+        if not batch_file:
+            continue
+        tensors = create_image_tensors(Path(data_dir), batch_file, transforms).to(device)
+        with torch.no_grad():
+            embeddings = model(tensors).detach().cpu().numpy()
+        save_embeddings(embeddings, batch_file, output_dir)
