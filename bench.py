@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Benchmark of the detect -> align -> embed -> classify hot path (BASELINE.json metric: faces/sec on 1080p frames).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels through the C-ABI)
+    python bench.py --impl reference ...                     # the reference's CPU path (oracle port) on the host cores
+
+One step = one pass of the whole path over one batch of synthetic 1080p frames (BASELINE config 3: 64 frames per rank,
+12 bundled faces pasted per frame, MTCNN(**cfg/detection/mtcnn.json) i.e. min_face_size 50 + keep_all, demo_video
+alignment to 160x160, InceptionResnetV1 + MLPModel(512, 1001) with random-init weights).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "faces/sec detect+embed+classify (1080p)"
+UNIT = "faces/s"
+ENC_FLOP_PER_FACE = 2.8353e9          # 1 417.66 MMAC per 160x160 crop (conv + last_linear)
+MLP_FLOP_PER_FACE = 6.2e6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def make_frames(n, first_seed, kind="1080p"):
+    """Synthetic frames that contain faces (random noise yields zero detections): seeded, frame seed = global index."""
+    from oracle import synth                # data generator only (shared with the tests); not on the product path
+    return synth.frames(kind, n, first_seed=first_seed)
+
+
+def build_models(dev, seed=0):
+    import torch
+    from vn_celeb_face_recognition_b200.models import MTCNN, InceptionResnetV1, MLPModel
+    torch.manual_seed(seed)
+    det = MTCNN(image_size=160, keep_all=True, min_face_size=50, device=dev)       # cfg/detection/mtcnn.json
+    enc = InceptionResnetV1(pretrained=None, device=dev).eval()                    # random init (BASELINE config)
+    cls = MLPModel(512, 1001).to(dev).eval()
+    return det, enc, cls
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def cpu_reference_leg(frames, enc_sd, mlp_sd, repeats=1, threads=None):
+    """The reference's CPU path on the host cores: parallel_detect_and_align + recognize_celeb semantics (oracle port of
+    demo_image.py:273-306, :50-76).  Returns (faces/s, n_faces, seconds, threads)."""
+    import torch
+    from oracle import pipeline as opipe, synth, align
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sds = synth.mtcnn_state_dicts()
+    cp = align.CENTER_POINTS[(160, 160)]
+    best, nf = None, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        faces, _ = opipe.parallel_detect_and_align(list(frames), sds, cp, (160, 160), min_face_size=50)
+        labels, _ = opipe.recognize(faces, enc_sd, mlp_sd, 0.0)
+        dt = time.perf_counter() - t0
+        nf = sum(len(x) for x in faces)
+        best = dt if best is None else min(best, dt)
+    return nf / best, nf, best, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from vn_celeb_face_recognition_b200.models import InceptionResnetV1, MLPModel
+    torch.manual_seed(0)
+    enc_sd = {k: v.float() for k, v in InceptionResnetV1(pretrained=None).state_dict().items()}
+    mlp_sd = {k: v.float() for k, v in MLPModel(512, 1001).state_dict().items()}
+    n = args.cpu_frames
+    frames = make_frames(n, 0)
+    times, faces = [], 0
+    for i in range(args.warmup + args.steps):
+        fps, nf, dt, threads = cpu_reference_leg(frames, enc_sd, mlp_sd)
+        if i >= args.warmup:
+            times.append(dt)
+            faces += nf
+    total = sum(times)
+    val = faces / total
+    sample = "%d synthetic 1080p frames (seeds 0..%d, 12 faces each) per step, %d timed steps" % (n, n - 1, args.steps)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "pipeline_1080p (BASELINE config 3 on a bounded sample)", "frames_per_step": n,
+                       "faces_per_step": faces // max(1, args.steps), "min_face_size": 50, "align": "similarity 160x160",
+                       "num_classes": 1001},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vn_celeb_face_recognition_b200 import _lib, pipeline, dist as vdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    B = args.frames
+    det, enc, cls = build_models(dev)
+    enc.chunk = args.chunk
+    fp = pipeline.FacePipeline(det, enc, cls, (160, 160), "similarity")
+    frames_np = make_frames(B, rank * B)
+    frames_pinned = torch.from_numpy(frames_np).pin_memory()
+    frames_dev = frames_pinned.to(dev)
+
+    stage_ms = {}
+    ev_log = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        ev_log.append((name, e))
+
+    def step_device(timed):
+        out = fp.run_device(frames_dev, mark=mark if timed else None)
+        if world > 1:
+            vdist.all_gather_faces(out["emb"], out["label"], out["prob"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(args.warmup):
+        out = step_device(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    faces = 0
+    t0.record()
+    for _ in range(args.steps):
+        out = step_device(True)
+        faces += out["n_faces"]
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - l0
+    ms = t0.elapsed_time(t1)
+    # per-stage device time from the event marks (averaged over the timed steps)
+    for (n0, e0), (n1, e1) in zip(ev_log[:-1], ev_log[1:]):
+        if n1 != "start":
+            stage_ms[n1] = stage_ms.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
+
+    # ---- end to end through the public API: pinned host frames in, host results out (`e2e`)
+    e2e_steps = 1 if args.skip_e2e else args.steps
+    for _ in range(0 if args.skip_e2e else 2):
+        fp(frames_pinned)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    faces_e2e, d2h = 0, 0
+    e0.record()
+    for _ in range(e2e_steps):
+        res = fp(frames_pinned)
+        faces_e2e += sum(len(r["labels"]) for r in res)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    nf_step = faces_e2e // max(1, e2e_steps)
+    d2h = (B + 1) * 4 + B * max(1, max(len(r["labels"]) for r in res)) * 5 * 4 + nf_step * (8 + 4 + 512 * 4)
+
+    # ---- reductions over ranks
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        c = torch.tensor([faces, faces_e2e, launches], device=dev, dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        faces, faces_e2e, launches = [int(v) for v in c.tolist()]
+
+    if rank == 0:
+        ws = out["ws"]
+        cnts = ws.counters.cpu().numpy()
+        nseg = ws.B * ws.L
+        work = {"pnet_candidates_per_frame": float(np.minimum(cnts[:nseg], ws.caps[0]).sum()) / B,
+                "rnet_crops_per_frame": float(cnts[2 * nseg:2 * nseg + B].sum()) / B,
+                "onet_crops_per_frame": float(cnts[2 * nseg + B:2 * nseg + 2 * B].sum()) / B,
+                "faces_per_frame": float(cnts[2 * nseg + 2 * B:2 * nseg + 3 * B].sum()) / B}
+        faces_step_rank = out["n_faces"]
+        # roofline of the dominant kernel: the tcgen05 implicit-GEMM convolution (encoder stage)
+        enc_ms = stage_ms.get("encoder", 0.0)
+        conv_launches_per_step = None
+        roof = None
+        if enc_ms > 0:
+            flops = faces_step_rank * ENC_FLOP_PER_FACE
+            achieved = flops / (enc_ms * 1e-3) / 1e12
+            roof = {"kernel": "igemm_conv_kernel (InceptionResnetV1 stage: all conv launches of one step)", "bound": "tensor",
+                    "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                    "traffic": None, "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
+                    "stage_ms": enc_ms, "share_of_step": enc_ms / (ms / args.steps)}
+        line = {"metric": METRIC, "value": faces / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": _half_name(enc.half_dtype), "data": "synthetic",
+                "config": {"workload": "pipeline_1080p (BASELINE config 3)", "frames_per_rank": B, "frame": "1920x1080x3 u8",
+                           "faces_per_step": faces // max(1, args.steps), "min_face_size": 50, "align": "similarity 160x160",
+                           "encoder": "InceptionResnetV1 random-init", "classifier": "MLPModel(512,1001) random-init",
+                           "detector_weights": "bundled MTCNN", "detector_dtype": "f32", "encoder_chunk": enc.chunk,
+                           "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (frames_np.nbytes / 1e6),
+                           "work_per_frame": work, "collective": "all_gather(emb,label,prob)" if world > 1 else "none"},
+                "e2e": {"value": faces_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_np.nbytes),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps},
+                "gpu_launches": int(launches), "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+                "roofline": roof, "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            enc_sd = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
+            mlp_sd = {k: v.detach().float().cpu() for k, v in cls.state_dict().items()}
+            n = args.cpu_frames
+            fps, nf, dt, threads = cpu_reference_leg(frames_np[:n], enc_sd, mlp_sd, repeats=2)
+            line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "first %d of the step's 1080p frames (%d faces), best of 2, %.2f s" % (n, nf, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _half_name(dt=None):
+    """Arithmetic type of the dominant (tensor-core) part: 16-bit operands, fp32 accumulation.  The detector runs fp32."""
+    from vn_celeb_face_recognition_b200 import encoder_plan
+    import torch
+    return "f16" if (dt or encoder_plan.HALF) == torch.float16 else "bf16"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="1080p frames per rank per step (BASELINE config 3: 64)")
+    ap.add_argument("--chunk", type=int, default=256, help="encoder crops per internal chunk")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -116,7 +116,7 @@ int vnfr_stage3_faces(int B, int cap3, const int32_t* s3_count, const float* s3_
 /* Faces -> encoder inputs, one gather kernel.  mode 0: MTCNN.extract semantics for tensor frames (mtcnn.py:458-518,
  * detect_face.py:317-322, :342-378); mode 1: demo_video alignment (demo_image.py:174-199, :236-239;
  * align_face.py:51-57: 5-point similarity + cv2.warpAffine) with template_host[10] = center points (x,y)*5.
- * Faces are numbered image-major in detection order; offs [B+1] scratch.  face_u8 [max_faces][S][S][3],
+ * Faces are numbered image-major in detection order; offs [B+1] scratch.  face_u8 [max_faces][S][S][3] (nullable),
  * face_half [max_faces][S][S][8] (standardised, dtype 0 = bf16 / 1 = fp16), face_img [max_faces] (nullable).        */
 int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int capf, const int32_t* count, const float* box,
                     const float* pts, int mode, int image_size, int margin, const float* template_host, int dtype,

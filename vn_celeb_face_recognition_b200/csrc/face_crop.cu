@@ -19,7 +19,10 @@ namespace {
 
 // OpenCV initInterTab2D(INTER_LINEAR, fixpt): weights summing to 32768.  The (0,0) entry is 32768 itself, which does
 // not fit a signed short -- kept unsigned here (OpenCV's u8 path behaves as if it were +32768; pinned against cv2).
-__constant__ unsigned short c_bilin[32 * 32 * 4];
+// It lives in global memory and is staged into shared memory per CTA: every lane indexes it with its own (fy, fx), and
+// divergent __constant__ reads serialise (the first version spent 4.9 ms per 768 faces on exactly that).
+__device__ unsigned short g_bilin[32 * 32 * 4];
+constexpr int MAX_S = 256;                 // largest supported output edge
 
 struct FaceArgs {
   const uint8_t* frames;
@@ -36,8 +39,10 @@ struct FaceArgs {
 };
 
 __device__ __forceinline__ void store_px(const FaceArgs& a, size_t px, unsigned r, unsigned g, unsigned b) {
-  uint8_t* u = a.face_u8 + px * 3;
-  u[0] = (uint8_t)r; u[1] = (uint8_t)g; u[2] = (uint8_t)b;
+  if (a.face_u8 != nullptr) {
+    uint8_t* u = a.face_u8 + px * 3;
+    u[0] = (uint8_t)r; u[1] = (uint8_t)g; u[2] = (uint8_t)b;
+  }
   // (x - 127.5) / 128 : exact in fp32 (power-of-two divisor)
   const float fr = ((float)r - 127.5f) * 0.0078125f, fg = ((float)g - 127.5f) * 0.0078125f, fb = ((float)b - 127.5f) * 0.0078125f;
   uint32_t w0, w1;
@@ -58,6 +63,11 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
   const int S = a.S;
   __shared__ double s_m[6];     // inverse affine (mode 1)
   __shared__ int s_box[4];      // integer crop box x1,y1,x2,y2 (exclusive ends)
+  __shared__ unsigned short s_tab[32 * 32 * 4];
+  __shared__ int s_ad[MAX_S], s_bd[MAX_S], s_x0[MAX_S], s_y0[MAX_S];   // OpenCV's adelta / bdelta / per-row X0, Y0
+  if (a.mode == 1)
+    for (int i = threadIdx.x; i < 32 * 32 * 4 / 2; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(g_bilin)[i];
   for (int f = blockIdx.x; f < total; f += gridDim.x) {
     // locate (image, slot)
     int lo = 0, hi = a.B;
@@ -106,6 +116,16 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
       }
     }
     __syncthreads();
+    if (a.mode == 1) {
+      // per-column / per-row fixed-point terms (AB_BITS = 10), exactly OpenCV's adelta/bdelta and X0/Y0 incl. round_delta
+      for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        s_ad[i] = (int)llrint(s_m[0] * (double)i * 1024.0);
+        s_bd[i] = (int)llrint(s_m[3] * (double)i * 1024.0);
+        s_x0[i] = (int)llrint((s_m[1] * (double)i + s_m[2]) * 1024.0) + 16;
+        s_y0[i] = (int)llrint((s_m[4] * (double)i + s_m[5]) * 1024.0) + 16;
+      }
+      __syncthreads();
+    }
     const int x1 = s_box[0], y1 = s_box[1], cw = s_box[2] - s_box[0], ch = s_box[3] - s_box[1];
     const uint8_t* img = a.frames + (size_t)b * a.H * a.W * 3;
     if (a.mode == 0) {
@@ -129,17 +149,14 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
       }
     } else {
       // cv2.warpAffine, INTER_LINEAR fixed point: AB_BITS = 10, INTER_BITS = 5, weights 2^15
-      const double m00 = s_m[0], m01 = s_m[1], m02 = s_m[2], m10 = s_m[3], m11 = s_m[4], m12 = s_m[5];
       for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
         const int oy = i / S, ox = i - oy * S;
-        const long long ad = llrint(m00 * (double)ox * 1024.0), bd = llrint(m10 * (double)ox * 1024.0);
-        const long long X0 = llrint((m01 * (double)oy + m02) * 1024.0) + 16, Y0 = llrint((m11 * (double)oy + m12) * 1024.0) + 16;
-        const long long X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
-        long long sxl = X >> 5, syl = Y >> 5;
-        sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);
-        syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
-        const int sx = (int)sxl, sy = (int)syl, fx = (int)(X & 31), fy = (int)(Y & 31);
-        const unsigned short* wt = c_bilin + (fy * 32 + fx) * 4;
+        const int X = (s_x0[oy] + s_ad[ox]) >> 5, Y = (s_y0[oy] + s_bd[ox]) >> 5;
+        int sx = X >> 5, sy = Y >> 5;
+        sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);
+        sy = sy < -32768 ? -32768 : (sy > 32767 ? 32767 : sy);
+        const int fx = X & 31, fy = Y & 31;
+        const unsigned short* wt = s_tab + (fy * 32 + fx) * 4;
         int acc[3] = {0, 0, 0};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -210,7 +227,8 @@ extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int c
                                const float* pts, int mode, int image_size, int margin, const float* template_host, int dtype,
                                int max_faces, int32_t* offs, uint8_t* face_u8, void* face_half, int32_t* face_img, int32_t* status,
                                void* stream) {
-  VNFR_REQUIRE(frames && count && box && offs && face_u8 && face_half && status, "null pointer");
+  VNFR_REQUIRE(frames && count && box && offs && face_half && status, "null pointer");
+  VNFR_REQUIRE(image_size <= MAX_S, "image_size larger than 256 is not supported");
   VNFR_REQUIRE(mode == 0 || (mode == 1 && pts != nullptr && template_host != nullptr), "align mode needs landmarks and a template");
   VNFR_REQUIRE(image_size > 0 && margin >= 0 && margin < image_size, "bad image_size / margin");
   if (B == 0 || max_faces == 0) return VNFR_OK;
@@ -219,7 +237,7 @@ extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int c
   if (!tab_set) {
     static unsigned short tab[32 * 32 * 4];
     build_bilinear_table(tab);
-    VNFR_CUDA(cudaMemcpyToSymbolAsync(c_bilin, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
+    VNFR_CUDA(cudaMemcpyToSymbolAsync(g_bilin, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
     tab_set = true;
   }
   scan_counts_kernel2<<<1, 32, 0, st>>>(count, B, capf, offs);

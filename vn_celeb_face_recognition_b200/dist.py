@@ -1,0 +1,37 @@
+"""Multi-GPU plumbing: one process per GPU, frames / crops sharded by index, every rank runs the whole pipeline on its
+slice.  The only collective on the path is the ragged all-gather of the per-face results
+(embeddings + labels + probabilities) at the end of a step -- NCCL over NVLink on GPUs, gloo in the CPU tests."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block partition: item i belongs to rank i // ceil(n/world)."""
+    per = (n_items + world - 1) // world
+    lo = min(rank * per, n_items)
+    return lo, min(lo + per, n_items)
+
+
+def all_gather_faces(emb, label, prob, group=None):
+    """emb (n_i, D) float, label (n_i,) int64, prob (n_i,) float on this rank -> concatenation over ranks in rank
+    order (= single-GPU order for a contiguous shard), plus the per-rank counts.  Two collectives: counts, then ONE
+    padded payload (label and prob ride in two extra float columns... kept exact: labels < 2^24)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return emb, label, prob, torch.tensor([emb.shape[0]], device=emb.device)
+    dev = emb.device
+    n = torch.tensor([emb.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = torch.cat(counts)
+    nmax = int(counts.max().item())
+    D = emb.shape[1]
+    payload = torch.zeros(nmax, D + 2, dtype=torch.float32, device=dev)
+    payload[:emb.shape[0], :D] = emb.float()
+    payload[:emb.shape[0], D] = label.float()
+    payload[:emb.shape[0], D + 1] = prob.float()
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    parts = [g[:int(c)] for g, c in zip(gathered, counts.tolist())]
+    allp = torch.cat(parts, 0)
+    return allp[:, :D].contiguous(), allp[:, D].long(), allp[:, D + 1].contiguous(), counts

@@ -235,7 +235,7 @@ class MTCNN(nn.Module):
     _pnet_owner = None
 
     # ---- the device pipeline ------------------------------------------------------------------------------------
-    def detect_device(self, frames_u8, select_largest=None):
+    def detect_device(self, frames_u8, select_largest=None, mark=None):
         """frames_u8: CUDA uint8 (B,H,W,3) RGB.  Runs the whole three-stage cascade on the current stream and returns
         the DetectWorkspace holding out_count (B,), out_box (B,capf,5), out_pts (B,capf,10), status -- all on device,
         nothing synchronised."""
@@ -255,22 +255,31 @@ class MTCNN(nn.Module):
         P = _lib.ptr
         t0, t1, t2 = [float(t) for t in self.thresholds]
         sl = self.select_largest if select_largest is None else select_largest
+        mark = mark or (lambda name: None)        # optional stage markers (bench.py records CUDA events here)
         ws.counters.zero_()
+        mark("start")
         if ws.L > 0:
             _lib.call("vnfr_pyramid_resize_norm", C.byref(ws.pyr), P(frames_u8), P(ws.levels), st)
+            mark("pyramid")
             _lib.call("vnfr_pnet_sweep_compact", C.byref(ws.pyr), P(ws.levels), t0, cap1, P(ws.cand_count), P(ws.cand_cell),
                       P(ws.cand_score), P(ws.cand_reg), None, None, st)
+            mark("pnet")
         _lib.call("vnfr_stage1_boxes", C.byref(ws.pyr), cap1, P(ws.cand_count), P(ws.cand_cell), P(ws.cand_score),
                   P(ws.cand_reg), P(ws.keep1_count), P(ws.keep1), cap2, P(ws.s2_count), P(ws.s2_box), P(ws.s2_pad),
                   P(ws.status), st)
+        mark("stage1_nms")
         _lib.call("vnfr_rnet_forward", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
                   P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), None, st)
+        mark("rnet")
         _lib.call("vnfr_stage2_boxes", B, H, W, cap2, P(ws.s2_count), P(ws.s2_box), P(ws.s2_prob), P(ws.s2_reg), t1, cap3,
                   P(ws.s3_count), P(ws.s3_box), P(ws.s3_pad), P(ws.status), st)
+        mark("stage2_nms")
         _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
                   P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), None, st)
+        mark("onet")
         _lib.call("vnfr_stage3_faces", B, cap3, P(ws.s3_count), P(ws.s3_box), P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), t2,
                   1 if sl else 0, capf, P(ws.out_count), P(ws.out_box), P(ws.out_pts), P(ws.status), st)
+        mark("stage3_nms")
         ws.frames = frames_u8
         return ws
 
@@ -282,7 +291,8 @@ class MTCNN(nn.Module):
             over = [n for i, n in enumerate(names) if status & (1 << i)]
             raise _lib.VnfrError("detection capacity exceeded: %s -- raise MTCNN.caps" % ", ".join(over))
 
-    def face_crops_device(self, ws, mode, image_size, margin=0, template=None, half_dtype=None, max_faces=None):
+    def face_crops_device(self, ws, mode, image_size, margin=0, template=None, half_dtype=None, max_faces=None,
+                          want_u8=True):
         """Faces of the detections in ``ws`` as encoder inputs (see vnfr_face_crops).  Returns (face_u8 (F,S,S,3),
         face_half (F,S,S,8), face_img (F,), F_capacity) on device; the number of valid faces is ws.out_count.sum()."""
         from .. import encoder_plan
@@ -304,8 +314,8 @@ class MTCNN(nn.Module):
             tmpl = (C.c_float * 10)(*[float(v) for v in np.asarray(template, dtype=np.float32).reshape(-1)])
         _lib.call("vnfr_face_crops", _lib.ptr(ws.frames), ws.B, ws.H, ws.W, capf, _lib.ptr(ws.out_count), _lib.ptr(ws.out_box),
                   _lib.ptr(ws.out_pts), mode, S, margin, tmpl, encoder_plan.dtype_code(dt), max_faces, _lib.ptr(ws.offs),
-                  _lib.ptr(u8), _lib.ptr(half), _lib.ptr(fimg), _lib.ptr(ws.status), _lib.stream_ptr())
-        return u8, half, fimg, max_faces
+                  _lib.ptr(u8 if want_u8 else None), _lib.ptr(half), _lib.ptr(fimg), _lib.ptr(ws.status), _lib.stream_ptr())
+        return (u8 if want_u8 else None), half, fimg, max_faces
 
     # ---- reference API ------------------------------------------------------------------------------------------
     def _to_frames(self, img):

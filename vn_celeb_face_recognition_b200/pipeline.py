@@ -49,7 +49,7 @@ class FacePipeline:
     align="extract":    MTCNN.extract semantics (box crop + area resize + fixed_image_standardization)."""
 
     def __init__(self, detector, encoder, classifier=None, target_fs=(160, 160), align="similarity", center_point=None,
-                 threshold=0.0, max_faces_per_frame=32):
+                 threshold=0.0, max_faces_per_frame=32, return_faces_u8=False):
         assert target_fs[0] == target_fs[1], "square targets only"
         self.det, self.enc, self.cls = detector, encoder, classifier
         self.S = int(target_fs[0])
@@ -59,30 +59,35 @@ class FacePipeline:
             raise ValueError("no landmark template for target size %s" % (target_fs,))
         self.threshold = threshold
         self.max_faces_per_frame = max_faces_per_frame
+        self.return_faces_u8 = return_faces_u8
 
-    def run_device(self, frames_u8):
+    def run_device(self, frames_u8, mark=None):
         """frames_u8: CUDA uint8 (B,H,W,3).  Returns a dict of DEVICE tensors + the face count (one tiny sync to size
         the encoder batch): count (B,), boxes (B,capf,5), points (B,capf,10), faces_u8 (F,S,S,3), emb (F,512),
         label (F,), prob (F,), face_img (F,)."""
+        mark = mark or (lambda name: None)
         with torch.no_grad():
-            ws = self.det.detect_device(frames_u8)
+            ws = self.det.detect_device(frames_u8, mark=mark)
             dt = self.enc.half_dtype or encoder_plan.HALF
             u8, half, fimg, cap = self.det.face_crops_device(ws, self.mode, self.S, self.det.margin, self.template, dt,
-                                                            ws.B * self.max_faces_per_frame)
+                                                            ws.B * self.max_faces_per_frame, want_u8=self.return_faces_u8)
+            mark("face_crops")
             host = ws.counters[-(ws.B + 1):].cpu().numpy()       # out_count (B) + status: the only mid-pipeline read-back
             self.det.check_status(int(host[-1]))
             F = int(host[:-1].sum())
-            out = {"count": ws.out_count, "boxes": ws.out_box, "points": ws.out_pts, "n_faces": F, "faces_u8": u8[:F],
-                   "face_img": fimg[:F], "count_host": host[:-1].copy()}
+            out = {"count": ws.out_count, "boxes": ws.out_box, "points": ws.out_pts, "n_faces": F, "faces_u8": None if u8 is None else u8[:F],
+                   "face_img": fimg[:F], "count_host": host[:-1].copy(), "ws": ws}
             if F == 0:
                 dev = frames_u8.device
                 out.update(emb=torch.zeros(0, 512, device=dev), label=torch.zeros(0, dtype=torch.int64, device=dev),
                            prob=torch.zeros(0, device=dev))
                 return out
             emb, emb16 = self.enc.embed_nhwc8(half[:F])
+            mark("encoder")
             out["emb"] = emb
             if self.cls is not None:
                 label, prob = self.cls.classify_half(emb16)
+                mark("classifier")
                 # identify_person thresholding (demo_image.py:131-137): below threshold -> num_classes ("Unknown")
                 if self.threshold and self.threshold > 0:
                     label = torch.where(prob >= self.threshold, label, torch.full_like(label, self.cls.num_classes))
