@@ -290,7 +290,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=64, help="1080p frames per rank per step (BASELINE config 3: 64)")
-    ap.add_argument("--chunk", type=int, default=256, help="encoder crops per internal chunk")
+    ap.add_argument("--chunk", type=int, default=1024, help="encoder crops per internal chunk")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")

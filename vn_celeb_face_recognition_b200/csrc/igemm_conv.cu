@@ -21,9 +21,10 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements: 128 bytes = one swizzle-128B row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_PRODUCER_THREADS = 128;         // warps 0-3: A gather, then epilogue
-constexpr int NUM_THREADS = 192;                  // warp 4: TMA for W, warp 5: TMEM alloc + MMA issue
-constexpr int MAX_STAGES = 6;
+constexpr int NUM_PRODUCER_THREADS = 256;         // warps 0-7: A gather, two threads per GEMM row
+constexpr int NUM_EPILOGUE_THREADS = 128;         // warps 8-11
+constexpr int NUM_THREADS = 448;                  // warp 12: TMA for W, warp 13: TMEM alloc + MMA issue
+constexpr int MAX_STAGES = 8;
 
 struct ConvParams {
   const __nv_bfloat16* in;
@@ -35,7 +36,7 @@ struct ConvParams {
   int n_img, in_h, in_w, cin, in_pitch;
   int kh, kw, stride, pad_h, pad_w;
   int out_h, out_w;
-  int M, K, cout, k_blocks, block_n;
+  int M, K, cout, k_blocks, block_n, n_tiles_m, n_tiles_n;
   int n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
   int relu;
   int stages, tmem_cols;
@@ -83,6 +84,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// one (non-incrementing) arrival on `bar` once all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -145,6 +150,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// the "+r" ties make every later use of v[] depend on the wait
+__device__ __forceinline__ void tmem_ld_wait(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -158,9 +180,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------- kernel
-// Shared memory: [A stage 0..S) 16 KB each][W stage 0..S) block_n*128 B each][barriers], base aligned to 1024 B.
+// Persistent, warp-specialised: one CTA per SM walks over output tiles (tile = 128 rows x block_n channels).
+//   warps 0-7   A producers: two threads per GEMM row (= output pixel), 4 x 16-byte cp.async each per K block; the
+//               full barrier is armed by cp.async.mbarrier.arrive (no wait_group in the loop: fully asynchronous)
+//   warps 8-11  epilogue: TMEM lane quarter = warp & 3; drains accumulator buffer `ab` while the MMA fills the other
+//   warp  12    W producer: TMA (one elected lane)
+//   warp  13    TMEM alloc + tcgen05.mma issue (one elected lane)
+// Three barrier rings: smem full/empty per stage (global K-block counter runs across tiles, so the load pipeline never
+// drains at a tile boundary), TMEM full/empty per accumulator buffer.
+// Shared memory: [A stage 0..S) 16 KB each][W stage 0..S) block_n*128 B each][bias 2 x 256 fp32][barriers].
 template <bool F16>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -168,26 +198,33 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + (uint32_t)S * A_STAGE_BYTES;
-  const uint32_t bars = smem_b + (uint32_t)S * b_stage_bytes;   // full[S], empty[S], accum, tmem slot
-  const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_accum = bars + 16u * S, tmem_slot = bars + 16u * S + 8u;
+  const uint32_t smem_bias = smem_b + (uint32_t)S * b_stage_bytes;          // 2 x 256 floats
+  const uint32_t bars = smem_bias + 2048u;
+  const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bar_tfull + 16u,
+                 tmem_slot = bar_tempty + 16u;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * p.block_n;
   const int KB = p.k_blocks;
+  const int n_tiles_n = p.n_tiles_n;
+  const int total_tiles = p.n_tiles_m * n_tiles_n;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_full + 8u * s, NUM_PRODUCER_THREADS + 1);
       mbar_init(bar_empty + 8u * s, 1);
     }
-    mbar_init(bar_accum, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8u * i, 1);
+      mbar_init(bar_tempty + 8u * i, NUM_EPILOGUE_THREADS);
+    }
     fence_barrier_init();
   }
-  if (warp == 5) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols)
+  if (warp == 12 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+  if (warp == 13) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -197,157 +234,201 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp < 4) {
-    // ================================================= A producer: one GEMM row (= output pixel) per thread
-    const int r = tid;
-    const int m = m0 + r;
-    const bool row_ok = m < p.M;
-    int iy0 = 0, ix0 = 0;
-    const __nv_bfloat16* img_base = p.in;
-    if (row_ok) {
-      const int hw = p.out_h * p.out_w;
-      const int img = m / hw;
-      const int rem = m - img * hw;
-      const int oy = rem / p.out_w;
-      const int ox = rem - oy * p.out_w;
-      iy0 = oy * p.stride - p.pad_h;
-      ix0 = ox * p.stride - p.pad_w;
-      img_base = p.in + (size_t)img * p.in_h * p.in_w * p.in_pitch;
-    }
+  if (warp < 8) {
+    // ================================================= A producers
+    const int r = tid & 127;
+    const int half = tid >> 7;                 // which 4 of the 8 16-byte chunks of the row this thread copies
     const uint32_t row_smem = (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
-    int c = 0, ky = 0, kx = 0, k = 0;          // running decomposition of k = (ky*kw + kx)*cin + c
-    const int LA = S - 1;                      // cp.async groups kept in flight
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % S;
-      mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
-      const uint32_t dst_row = smem_a + (uint32_t)s * A_STAGE_BYTES + row_smem;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const void* src = p.in;
-        uint32_t nbytes = 0;
-        if (row_ok && k < p.K) {
-          const int iy = iy0 + ky, ix = ix0 + kx;
-          if ((unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w) {
-            src = img_base + ((size_t)iy * p.in_w + ix) * p.in_pitch + c;
-            nbytes = 16;
-          }
-        }
-        cp_async_16(dst_row + (((uint32_t)j ^ sw) << 4), src, nbytes);
-        k += 8;
-        c += 8;
-        if (c >= p.cin) {
-          c = 0;
-          if (++kx == p.kw) { kx = 0; ++ky; }
-        }
-      }
-      cp_async_commit();
-      if (kb >= LA) {
-        // group (kb - LA) has landed: make it visible to the tensor-core (async) proxy, then signal the MMA thread
-        switch (LA) {
-          case 1: cp_async_wait<1>(); break;
-          case 2: cp_async_wait<2>(); break;
-          case 3: cp_async_wait<3>(); break;
-          case 4: cp_async_wait<4>(); break;
-          default: cp_async_wait<5>(); break;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(bar_full + 8u * ((kb - LA) % S));
-      }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int kb = (KB > LA ? KB - LA : 0); kb < KB; ++kb) mbar_arrive(bar_full + 8u * (kb % S));
-
-    // ================================================= epilogue: TMEM -> registers -> bias/residual/ReLU -> global
-    mbar_wait(bar_accum, 0);
-    tc_fence_after();
-    const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int n_valid = min(p.block_n, p.cout - n0);
-    for (int c0 = 0; c0 < n_valid; c0 += 16) {
-      float v[16];
-      __syncwarp();
-      tmem_ld16(t_row + (uint32_t)c0, v);      // warp-collective: executed by all lanes, also for rows >= M
+    const int hw = p.out_h * p.out_w;
+    const bool tap_aligned = (p.cin & 63) == 0;   // a 64-element K block never straddles a filter tap
+    int it = 0;                                // K blocks issued so far (all tiles)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m = (tile / n_tiles_n) * BLOCK_M + r;
+      const bool row_ok = m < p.M;
+      int iy0 = 0, ix0 = 0;
+      const __nv_bfloat16* img_base = p.in;
       if (row_ok) {
-      const int n = n0 + c0;
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 bb = __ldg(b4 + q);
-        v[4 * q + 0] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        const int img = m / hw;
+        const int rem = m - img * hw;
+        const int oy = rem / p.out_w;
+        const int ox = rem - oy * p.out_w;
+        iy0 = oy * p.stride - p.pad_h;
+        ix0 = ox * p.stride - p.pad_w;
+        img_base = p.in + (size_t)img * p.in_h * p.in_w * p.in_pitch;
       }
-      if (p.residual != nullptr) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)m * p.res_pitch + n);
+      if (tap_aligned) {
+        int c = 0, ky = 0, kx = 0;             // tap of the current K block, first channel of the block
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          const int iy = iy0 + ky, ix = ix0 + kx;
+          const bool ok = row_ok && (unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w;
+          const __nv_bfloat16* src = ok ? img_base + ((size_t)iy * p.in_w + ix) * p.in_pitch + c + half * 32 : p.in;
+          const uint32_t nbytes = ok ? 16u : 0u;
+          mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+          const uint32_t dst_row = smem_a + (uint32_t)s * A_STAGE_BYTES + row_smem;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint4 rr = __ldg(r4 + q);
-          const uint32_t w[4] = {rr.x, rr.y, rr.z, rr.w};
+          for (int j = 0; j < 4; ++j)
+            cp_async_16(dst_row + (((uint32_t)(half * 4 + j) ^ sw) << 4), ok ? src + j * 8 : src, nbytes);
+          cp_async_arrive_noinc(bar_full + 8u * s);
+          c += 64;
+          if (c >= p.cin) {
+            c = 0;
+            if (++kx == p.kw) { kx = 0; ++ky; }
+          }
+        }
+      } else {
+        // generic path (cin = 8, 32, 80, 96): each 16-byte chunk carries its own tap
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          // k index of this thread's first chunk -> (tap, channel); one division per K block
+          int ck = kb * BLOCK_K + half * 32;
+          const int tap = ck / p.cin;
+          int cc = ck - tap * p.cin;
+          int cky = tap / p.kw;
+          int ckx = tap - cky * p.kw;
+          mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+          const uint32_t dst_row = smem_a + (uint32_t)s * A_STAGE_BYTES + row_smem;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float lo, hi;
-            unpack2<F16>(w[e], lo, hi);
-            v[8 * q + 2 * e + 0] += lo;
-            v[8 * q + 2 * e + 1] += hi;
+          for (int j = 0; j < 4; ++j) {
+            const void* src = p.in;
+            uint32_t nbytes = 0;
+            if (row_ok && ck < p.K) {
+              const int iy = iy0 + cky, ix = ix0 + ckx;
+              if ((unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w) {
+                src = img_base + ((size_t)iy * p.in_w + ix) * p.in_pitch + cc;
+                nbytes = 16;
+              }
+            }
+            cp_async_16(dst_row + (((uint32_t)(half * 4 + j) ^ sw) << 4), src, nbytes);
+            ck += 8; cc += 8;
+            if (cc >= p.cin) { cc = 0; if (++ckx == p.kw) { ckx = 0; ++cky; } }
+          }
+          cp_async_arrive_noinc(bar_full + 8u * s);
+        }
+      }
+    }
+    cp_async_wait<0>();                        // nothing may be in flight when the CTA retires
+  } else if (warp < 12) {
+    // ================================================= epilogue: TMEM -> registers -> bias/residual/ReLU -> global
+    const int q = warp & 3;                    // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;               // row inside the tile
+    const int et = tid - NUM_PRODUCER_THREADS; // 0..127
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      const int m = (tile / n_tiles_n) * BLOCK_M + r;
+      const int n0 = (tile % n_tiles_n) * p.block_n;
+      const bool row_ok = m < p.M;
+      const int n_valid = min(p.block_n, p.cout - n0);
+      // stage this tile's bias while the MMAs are still running
+      float* sb = s_bias + ab * 256;
+      for (int i = et; i < n_valid; i += NUM_EPILOGUE_THREADS) sb[i] = __ldg(p.bias + n0 + i);
+      const __nv_bfloat16* res_row = p.residual != nullptr && row_ok ? p.residual + (size_t)m * p.res_pitch + n0 : nullptr;
+      uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
+      if (res_row != nullptr) {
+        rn0 = __ldg(reinterpret_cast<const uint4*>(res_row));
+        rn1 = __ldg(reinterpret_cast<const uint4*>(res_row) + 1);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");      // bias visible to the 4 epilogue warps
+      mbar_wait(bar_tfull + 8u * ab, (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tmem_cols);
+      for (int c0 = 0; c0 < n_valid; c0 += 16) {
+        float v[16];
+        __syncwarp();
+        tmem_ld16_issue(t_row + (uint32_t)c0, v);        // warp-collective, also for rows >= M
+        const uint4 rc0 = rn0, rc1 = rn1;
+        if (res_row != nullptr && c0 + 16 < n_valid) {   // prefetch the next chunk's residual under this chunk's math
+          rn0 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 16));
+          rn1 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 16) + 1);
+        }
+        tmem_ld_wait(v);
+        if (row_ok) {
+          const int n = n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += sb[c0 + i];
+          if (res_row != nullptr) {
+            const uint32_t w[8] = {rc0.x, rc0.y, rc0.z, rc0.w, rc1.x, rc1.y, rc1.z, rc1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float lo, hi;
+              unpack2<F16>(w[e], lo, hi);
+              v[2 * e + 0] += lo;
+              v[2 * e + 1] += hi;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+          }
+          if (p.out_f32 != nullptr) {
+            float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.out_f32_pitch + n);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) o[qq] = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+          } else {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
+            __nv_bfloat16* dst = (n < p.n_split) ? p.out0 + (size_t)m * p.out0_pitch + n
+                                                 : p.out1 + (size_t)m * p.out1_pitch + (n - p.n_split);
+            uint4* o = reinterpret_cast<uint4*>(dst);
+            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
         }
       }
-      if (p.relu) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-      }
-      if (p.out_f32 != nullptr) {
-        float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.out_f32_pitch + n);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      } else {
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pk[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
-        __nv_bfloat16* dst = (n < p.n_split) ? p.out0 + (size_t)m * p.out0_pitch + n
-                                             : p.out1 + (size_t)m * p.out1_pitch + (n - p.n_split);
-        uint4* o = reinterpret_cast<uint4*>(dst);
-        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      }  // row_ok
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8u * ab);       // accumulator buffer `ab` may be overwritten
     }
-    tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == 12) {
     // ================================================= W producer: TMA, one elected lane
     if (lane == 0) {
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % S;
-        mbar_wait(bar_empty + 8u * s, ((kb / S) & 1) ^ 1);
-        mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
-        tma_load_2d(smem_b + (uint32_t)s * b_stage_bytes, &tmap_w, bar_full + 8u * s, kb * BLOCK_K, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * p.block_n;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
+          tma_load_2d(smem_b + (uint32_t)s * b_stage_bytes, &tmap_w, bar_full + 8u * s, kb * BLOCK_K, n0);
+        }
       }
     }
   } else {
     // ================================================= MMA issuer: one elected lane
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(p.block_n, F16 ? 1 : 0);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % S;
-        mbar_wait(bar_full + 8u * s, (kb / S) & 1);
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int ab = tcount & 1;
+        mbar_wait(bar_tempty + 8u * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t a_desc = make_sw128_desc(smem_a + (uint32_t)s * A_STAGE_BYTES);
-        const uint64_t b_desc = make_sw128_desc(smem_b + (uint32_t)s * b_stage_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.tmem_cols);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(bar_full + 8u * s, (it / S) & 1);
+          fence_proxy_async_smem();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_a + (uint32_t)s * A_STAGE_BYTES);
+          const uint64_t b_desc = make_sw128_desc(smem_b + (uint32_t)s * b_stage_bytes);
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) start-address field
-          umma_bf16(tmem_base, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0);
+          for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
+            // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (>>4) start-address field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0);
+          }
+          umma_commit(bar_empty + 8u * s);     // smem stage reusable once these MMAs have read it
         }
-        umma_commit(bar_empty + 8u * s);       // smem stage reusable once these MMAs have read it
+        umma_commit(bar_tfull + 8u * ab);      // accumulator complete
       }
-      umma_commit(bar_accum);                  // accumulator complete
     }
     __syncwarp();
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 13) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
   }
 }
 
@@ -368,16 +449,18 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+int g_num_sms = 148;
+
 int pick_stages(int block_n) {
   const int stage_bytes = A_STAGE_BYTES + block_n * 128;
-  int s = (96 * 1024) / stage_bytes;           // ~96 KB per CTA -> two CTAs per SM
+  int s = (220 * 1024) / stage_bytes;          // one persistent CTA per SM owns (almost) all of its shared memory
   if (s < 2) s = 2;
   if (s > MAX_STAGES) s = MAX_STAGES;
   return s;
 }
 
 size_t smem_bytes_for(int block_n, int stages) {
-  return 1024 /*alignment slack*/ + (size_t)stages * (A_STAGE_BYTES + block_n * 128) + 16 * stages + 64;
+  return 1024 /*alignment slack*/ + (size_t)stages * (A_STAGE_BYTES + block_n * 128) + 2048 /*bias*/ + 16 * stages + 64;
 }
 
 }  // namespace
@@ -424,8 +507,8 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   VNFR_REQUIRE(op != nullptr, "op is null");
   static bool attr_set = false;
   if (!attr_set) {
-    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   ConvParams p;
@@ -454,7 +537,10 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   if (p.M <= 0) return VNFR_OK;
   CUtensorMap tm;
   memcpy(&tm, op->tmap_w, sizeof(tm));
-  dim3 grid(ceil_div(p.M, BLOCK_M), ceil_div(op->cout, op->block_n));
+  p.n_tiles_m = ceil_div(p.M, BLOCK_M);
+  p.n_tiles_n = ceil_div(op->cout, op->block_n);
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n;
+  dim3 grid(total_tiles < g_num_sms ? total_tiles : g_num_sms);
   if (op->dtype == 1)
     igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, p);
   else
