@@ -130,6 +130,7 @@ int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int capf, const 
  * last_linear + last_bn (:296-297) and both MLP layers (mlp_model.py:10-15).                                        */
 typedef struct {
   unsigned char tmap_w[128];      /* CUtensorMap of the packed weights, filled by vnfr_conv_prepare                */
+  unsigned char tmap_a[128];      /* CUtensorMap of the activations (a_mode 1 / 2), filled by vnfr_conv_prepare   */
   const void* in;                 /* bf16 NHWC; pixel pitch in_pitch elements; already offset to first channel     */
   const void* weights;            /* bf16 [cout_pad][k_pad], k = (ky*KW + kx)*cin + c, zero padded                 */
   const float* bias;              /* fp32 [cout_pad]                                                               */
@@ -144,7 +145,8 @@ typedef struct {
   int32_t n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
   int32_t relu;
   int32_t dtype;                  /* storage type of in/weights/residual/out0/out1: 0 = bf16, 1 = fp16             */
-  int32_t reserved[2];
+  int32_t a_mode;                 /* set by vnfr_conv_prepare: 0 = cp.async gather, 1 = TMA tiled (1x1), 2 = TMA im2col */
+  int32_t reserved[1];
 } VnfrConvOp;
 
 /* Fills op->tmap_w (cuTensorMapEncodeTiled on op->weights, box {64, block_n}, 128B swizzle) and validates the op. */

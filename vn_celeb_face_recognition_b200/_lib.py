@@ -27,7 +27,7 @@ class Pyramid(C.Structure):
 
 class ConvOp(C.Structure):
     _fields_ = [
-        ("tmap_w", C.c_ubyte * 128),
+        ("tmap_w", C.c_ubyte * 128), ("tmap_a", C.c_ubyte * 128),
         ("inp", C.c_void_p), ("weights", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
         ("out0", C.c_void_p), ("out1", C.c_void_p), ("out_f32", C.c_void_p),
         ("n_img", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("cin", C.c_int32), ("in_pitch", C.c_int32),
@@ -35,7 +35,7 @@ class ConvOp(C.Structure):
         ("out_h", C.c_int32), ("out_w", C.c_int32),
         ("cout", C.c_int32), ("cout_pad", C.c_int32), ("k_pad", C.c_int32), ("block_n", C.c_int32),
         ("n_split", C.c_int32), ("out0_pitch", C.c_int32), ("out1_pitch", C.c_int32), ("res_pitch", C.c_int32),
-        ("out_f32_pitch", C.c_int32), ("relu", C.c_int32), ("dtype", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("out_f32_pitch", C.c_int32), ("relu", C.c_int32), ("dtype", C.c_int32), ("a_mode", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

@@ -14,6 +14,7 @@
 // <= 256 TMEM columns per CTA so that two CTAs share an SM and one's epilogue overlaps the other's main loop.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 namespace {
@@ -22,8 +23,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // bf16 elements: 128 bytes = one swizzle-128B row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_PRODUCER_THREADS = 256;         // warps 0-7: A gather, two threads per GEMM row
-constexpr int NUM_EPILOGUE_THREADS = 128;         // warps 8-11
-constexpr int NUM_THREADS = 448;                  // warp 12: TMA for W, warp 13: TMEM alloc + MMA issue
+constexpr int NUM_EPILOGUE_THREADS = 256;         // warps 8-15: two warps per TMEM lane quarter, alternating 16-column chunks
+constexpr int NUM_THREADS = 576;                  // warp 16: TMA producer, warp 17: TMEM alloc + MMA issue
 constexpr int MAX_STAGES = 8;
 
 struct ConvParams {
@@ -40,6 +41,7 @@ struct ConvParams {
   int n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
   int relu;
   int stages, tmem_cols;
+  int a_mode;  // 0: cp.async gather by warps 0-7, 1: TMA tiled 2-D (1x1 convs), 2: TMA im2col
   int dtype;   // 0 = bf16, 1 = fp16 (both: fp32 accumulation in TMEM)
 };
 
@@ -183,15 +185,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // Persistent, warp-specialised: one CTA per SM walks over output tiles (tile = 128 rows x block_n channels).
 //   warps 0-7   A producers: two threads per GEMM row (= output pixel), 4 x 16-byte cp.async each per K block; the
 //               full barrier is armed by cp.async.mbarrier.arrive (no wait_group in the loop: fully asynchronous)
-//   warps 8-11  epilogue: TMEM lane quarter = warp & 3; drains accumulator buffer `ab` while the MMA fills the other
-//   warp  12    W producer: TMA (one elected lane)
-//   warp  13    TMEM alloc + tcgen05.mma issue (one elected lane)
+//   warps 8-15  epilogue: TMEM lane quarter = warp & 3, two warps per quarter take alternate 16-column chunks; they
+//               drain accumulator buffer `ab` while the MMA fills the other one
+//   warp  16    TMA producer: W always, A too when the convolution is 1x1 (plain 2-D box) (one elected lane)
+//   warp  17    TMEM alloc + tcgen05.mma issue (one elected lane)
 // Three barrier rings: smem full/empty per stage (global K-block counter runs across tiles, so the load pipeline never
 // drains at a tile boundary), TMEM full/empty per accumulator buffer.
 // Shared memory: [A stage 0..S) 16 KB each][W stage 0..S) block_n*128 B each][bias 2 x 256 fp32][barriers].
 template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
@@ -213,7 +216,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8u * s, NUM_PRODUCER_THREADS + 1);
+      mbar_init(bar_full + 8u * s, p.a_mode == 0 ? NUM_PRODUCER_THREADS + 1 : 1);
       mbar_init(bar_empty + 8u * s, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -222,8 +225,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
     }
     fence_barrier_init();
   }
-  if (warp == 12 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-  if (warp == 13) {
+  if (warp == 16 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    if (p.a_mode != 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+  }
+  if (warp == 17) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -235,6 +241,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp < 8) {
+    if (p.a_mode == 0) {
     // ================================================= A producers
     const int r = tid & 127;
     const int half = tid >> 7;                 // which 4 of the 8 16-byte chunks of the row this thread copies
@@ -309,11 +316,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
       }
     }
     cp_async_wait<0>();                        // nothing may be in flight when the CTA retires
-  } else if (warp < 12) {
+    }  // a_mode == 0 (with TMA-fed A these warps are idle)
+  } else if (warp < 16) {
     // ================================================= epilogue: TMEM -> registers -> bias/residual/ReLU -> global
     const int q = warp & 3;                    // TMEM lane quarter of this warp
     const int r = q * 32 + lane;               // row inside the tile
-    const int et = tid - NUM_PRODUCER_THREADS; // 0..127
+    const int et = tid - NUM_PRODUCER_THREADS; // 0..255
+    const int chalf = (warp - 8) >> 2;         // this warp handles 16-column chunks with (chunk & 1) == chalf
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int ab = tcount & 1;
@@ -326,28 +335,31 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
       for (int i = et; i < n_valid; i += NUM_EPILOGUE_THREADS) sb[i] = __ldg(p.bias + n0 + i);
       const __nv_bfloat16* res_row = p.residual != nullptr && row_ok ? p.residual + (size_t)m * p.res_pitch + n0 : nullptr;
       uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
-      if (res_row != nullptr) {
-        rn0 = __ldg(reinterpret_cast<const uint4*>(res_row));
-        rn1 = __ldg(reinterpret_cast<const uint4*>(res_row) + 1);
+      if (res_row != nullptr && chalf * 16 < n_valid) {
+        rn0 = __ldg(reinterpret_cast<const uint4*>(res_row + chalf * 16));
+        rn1 = __ldg(reinterpret_cast<const uint4*>(res_row + chalf * 16) + 1);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");      // bias visible to the 4 epilogue warps
       mbar_wait(bar_tfull + 8u * ab, (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tmem_cols);
-      for (int c0 = 0; c0 < n_valid; c0 += 16) {
+      for (int c0 = chalf * 16; c0 < n_valid; c0 += 32) {
         float v[16];
         __syncwarp();
         tmem_ld16_issue(t_row + (uint32_t)c0, v);        // warp-collective, also for rows >= M
         const uint4 rc0 = rn0, rc1 = rn1;
-        if (res_row != nullptr && c0 + 16 < n_valid) {   // prefetch the next chunk's residual under this chunk's math
-          rn0 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 16));
-          rn1 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 16) + 1);
+        if (res_row != nullptr && c0 + 32 < n_valid) {   // prefetch the next chunk's residual under this chunk's math
+          rn0 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32));
+          rn1 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32) + 1);
         }
         tmem_ld_wait(v);
         if (row_ok) {
           const int n = n0 + c0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += sb[c0 + i];
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * i);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
           if (res_row != nullptr) {
             const uint32_t w[8] = {rc0.x, rc0.y, rc0.z, rc0.w, rc1.x, rc1.y, rc1.z, rc1.w};
 #pragma unroll
@@ -381,16 +393,23 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
       tc_fence_before();
       mbar_arrive(bar_tempty + 8u * ab);       // accumulator buffer `ab` may be overwritten
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ================================================= W producer: TMA, one elected lane
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % n_tiles_n) * p.block_n;
+        const int m0 = (tile / n_tiles_n) * BLOCK_M;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % S;
           mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
+          if (p.a_mode == 1) {
+            // 1x1 convolution: the A tile is a plain 2-D box of the [M][pitch] activation matrix
+            mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes + A_STAGE_BYTES);
+            tma_load_2d(smem_a + (uint32_t)s * A_STAGE_BYTES, &tmap_a, bar_full + 8u * s, kb * BLOCK_K, m0);
+          } else {
+            mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
+          }
           tma_load_2d(smem_b + (uint32_t)s * b_stage_bytes, &tmap_w, bar_full + 8u * s, kb * BLOCK_K, n0);
         }
       }
@@ -408,7 +427,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % S;
           mbar_wait(bar_full + 8u * s, (it / S) & 1);
-          fence_proxy_async_smem();            // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          if (p.a_mode == 0) fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
           const uint64_t a_desc = make_sw128_desc(smem_a + (uint32_t)s * A_STAGE_BYTES);
           const uint64_t b_desc = make_sw128_desc(smem_b + (uint32_t)s * b_stage_bytes);
@@ -426,7 +445,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const ConvParams p
   }
 
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 17) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
   }
@@ -500,6 +519,23 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
     return VNFR_ERR_CUDA;
   }
   memcpy(op->tmap_w, &tm, sizeof(tm));
+  // A operand: 1x1 / stride 1 / no padding convolutions read a plain [M][in_pitch] matrix -> 2-D tiled TMA
+  op->a_mode = 0;
+  const long long M = (long long)op->n_img * op->out_h * op->out_w;
+  if (op->kh == 1 && op->kw == 1 && op->stride == 1 && op->pad_h == 0 && op->pad_w == 0 && M > 0 &&
+      ((uintptr_t)op->in % 16 == 0) && getenv("VNFR_NO_TMA_A") == nullptr) {
+    CUtensorMap ta;
+    const cuuint64_t adims[2] = {(cuuint64_t)op->cin, (cuuint64_t)M};
+    const cuuint64_t astrides[1] = {(cuuint64_t)op->in_pitch * 2};
+    const cuuint32_t abox[2] = {BLOCK_K, BLOCK_M};
+    CUresult ra = enc(&ta, op->dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                      const_cast<void*>(op->in), adims, astrides, abox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ra == CUDA_SUCCESS) {
+      memcpy(op->tmap_a, &ta, sizeof(ta));
+      op->a_mode = 1;
+    }
+  }
   return VNFR_OK;
 }
 
@@ -530,21 +566,23 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   p.res_pitch = op->res_pitch; p.out_f32_pitch = op->out_f32_pitch;
   p.relu = op->relu;
   p.dtype = op->dtype;
+  p.a_mode = op->a_mode;
   p.stages = pick_stages(op->block_n);
   int cols = 32;
   while (cols < op->block_n) cols <<= 1;
   p.tmem_cols = cols;
   if (p.M <= 0) return VNFR_OK;
-  CUtensorMap tm;
+  CUtensorMap tm, ta;
   memcpy(&tm, op->tmap_w, sizeof(tm));
+  memcpy(&ta, op->a_mode != 0 ? op->tmap_a : op->tmap_w, sizeof(ta));
   p.n_tiles_m = ceil_div(p.M, BLOCK_M);
   p.n_tiles_n = ceil_div(op->cout, op->block_n);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   dim3 grid(total_tiles < g_num_sms ? total_tiles : g_num_sms);
   if (op->dtype == 1)
-    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, p);
+    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, ta, p);
   else
-    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, p);
+    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, ta, p);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
