@@ -243,76 +243,57 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   if (warp < 8) {
     if (p.a_mode == 0) {
     // ================================================= A producers
-    const int r = tid & 127;
-    const int half = tid >> 7;                 // which 4 of the 8 16-byte chunks of the row this thread copies
-    const uint32_t row_smem = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
+    // 8 consecutive lanes copy the 8 16-byte chunks (one 128-byte K-block row) of one GEMM row, so every warp-level
+    // cp.async touches whole 128-byte lines; each thread serves 4 rows (rg, rg+32, rg+64, rg+96) with the same chunk j,
+    // hence the (tap, channel) decode of chunk j is done once per K block per thread.
+    const int j = tid & 7;                     // chunk inside the 128-byte row
+    const int rg = tid >> 3;                   // 0..31
     const int hw = p.out_h * p.out_w;
-    const bool tap_aligned = (p.cin & 63) == 0;   // a 64-element K block never straddles a filter tap
     int it = 0;                                // K blocks issued so far (all tiles)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m = (tile / n_tiles_n) * BLOCK_M + r;
-      const bool row_ok = m < p.M;
-      int iy0 = 0, ix0 = 0;
-      const __nv_bfloat16* img_base = p.in;
-      if (row_ok) {
-        const int img = m / hw;
-        const int rem = m - img * hw;
-        const int oy = rem / p.out_w;
-        const int ox = rem - oy * p.out_w;
-        iy0 = oy * p.stride - p.pad_h;
-        ix0 = ox * p.stride - p.pad_w;
-        img_base = p.in + (size_t)img * p.in_h * p.in_w * p.in_pitch;
+      const int m_base = (tile / n_tiles_n) * BLOCK_M;
+      int iy0[4], ix0[4];
+      const __nv_bfloat16* img_base[4];
+      uint32_t dst_off[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rg + 32 * q;
+        const int m = m_base + r;
+        dst_off[q] = (uint32_t)r * 128u + (((uint32_t)j ^ (uint32_t)(r & 7)) << 4);
+        if (m < p.M) {
+          const int img = m / hw;
+          const int rem = m - img * hw;
+          const int oy = rem / p.out_w;
+          const int ox = rem - oy * p.out_w;
+          iy0[q] = oy * p.stride - p.pad_h;
+          ix0[q] = ox * p.stride - p.pad_w;
+          img_base[q] = p.in + (size_t)img * p.in_h * p.in_w * p.in_pitch;
+        } else {
+          iy0[q] = -(1 << 28);                 // fails every bounds check -> zero fill
+          ix0[q] = 0;
+          img_base[q] = p.in;
+        }
       }
-      if (tap_aligned) {
-        int c = 0, ky = 0, kx = 0;             // tap of the current K block, first channel of the block
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % S;
-          const int iy = iy0 + ky, ix = ix0 + kx;
-          const bool ok = row_ok && (unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w;
-          const __nv_bfloat16* src = ok ? img_base + ((size_t)iy * p.in_w + ix) * p.in_pitch + c + half * 32 : p.in;
-          const uint32_t nbytes = ok ? 16u : 0u;
-          mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
-          const uint32_t dst_row = smem_a + (uint32_t)s * A_STAGE_BYTES + row_smem;
+      // (tap, channel) of chunk j in K block 0, then advanced by 64 elements per block
+      int kf = j * 8;
+      int c = kf, ky = 0, kx = 0;
+      while (c >= p.cin) { c -= p.cin; if (++kx == p.kw) { kx = 0; ++ky; } }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % S;
+        const bool k_ok = kf < p.K;
+        mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+        const uint32_t stage = smem_a + (uint32_t)s * A_STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            cp_async_16(dst_row + (((uint32_t)(half * 4 + j) ^ sw) << 4), ok ? src + j * 8 : src, nbytes);
-          cp_async_arrive_noinc(bar_full + 8u * s);
-          c += 64;
-          if (c >= p.cin) {
-            c = 0;
-            if (++kx == p.kw) { kx = 0; ++ky; }
-          }
+        for (int q = 0; q < 4; ++q) {
+          const int iy = iy0[q] + ky, ix = ix0[q] + kx;
+          const bool ok = k_ok && (unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w;
+          const void* src = ok ? (const void*)(img_base[q] + ((size_t)iy * p.in_w + ix) * p.in_pitch + c) : (const void*)p.in;
+          cp_async_16(stage + dst_off[q], src, ok ? 16u : 0u);
         }
-      } else {
-        // generic path (cin = 8, 32, 80, 96): each 16-byte chunk carries its own tap
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % S;
-          // k index of this thread's first chunk -> (tap, channel); one division per K block
-          int ck = kb * BLOCK_K + half * 32;
-          const int tap = ck / p.cin;
-          int cc = ck - tap * p.cin;
-          int cky = tap / p.kw;
-          int ckx = tap - cky * p.kw;
-          mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
-          const uint32_t dst_row = smem_a + (uint32_t)s * A_STAGE_BYTES + row_smem;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const void* src = p.in;
-            uint32_t nbytes = 0;
-            if (row_ok && ck < p.K) {
-              const int iy = iy0 + cky, ix = ix0 + ckx;
-              if ((unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w) {
-                src = img_base + ((size_t)iy * p.in_w + ix) * p.in_pitch + cc;
-                nbytes = 16;
-              }
-            }
-            cp_async_16(dst_row + (((uint32_t)(half * 4 + j) ^ sw) << 4), src, nbytes);
-            ck += 8; cc += 8;
-            if (cc >= p.cin) { cc = 0; if (++ckx == p.kw) { ckx = 0; ++cky; } }
-          }
-          cp_async_arrive_noinc(bar_full + 8u * s);
-        }
+        cp_async_arrive_noinc(bar_full + 8u * s);
+        kf += 64;
+        c += 64;
+        while (c >= p.cin) { c -= p.cin; if (++kx == p.kw) { kx = 0; ++ky; } }
       }
     }
     cp_async_wait<0>();                        // nothing may be in flight when the CTA retires
