@@ -1,0 +1,114 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/vnfr_b200.h declares, the
+host-side entry points behave (pyramid plan = reference's scale list, argument validation), the drop-in classes keep
+the reference's state_dict surface, and the product refuses to run without CUDA instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from vn_celeb_face_recognition_b200 import _lib, build
+    build.build()           # no-op when up to date; compiles with nvcc otherwise
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "vnfr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(vnfr_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    l = lib.lib()
+    for sym in sorted(declared):
+        assert hasattr(l, sym), "libvnfr_b200.so does not export %s" % sym
+    assert set(lib.exported_symbols()) <= declared | {"vnfr_last_error"}
+    assert l.vnfr_version() >= 100
+
+
+@pytest.mark.parametrize("H,W,minsize,n_levels,cells", [(1080, 1920, 50, 9, 54797), (1080, 1920, 20, 12, 362055),
+                                                        (2160, 3840, 20, 14, 1474378), (181, 181, 50, 4, 455)])
+def test_pyramid_plan_matches_reference_scale_list(lib, H, W, minsize, n_levels, cells):
+    """vnfr_pyramid_plan is host code: identical fp64 scale list / level sizes to detect_face.py:48-60, :71, and the
+    P-Net map geometry of SURVEY.md Appendix C."""
+    from oracle import detect
+    p = lib.Pyramid()
+    lib.call("vnfr_pyramid_plan", 3, H, W, minsize, 0.709, C.byref(p))
+    scales = detect.scale_pyramid(H, W, minsize, 0.709)
+    assert p.n_levels == n_levels == len(scales)
+    assert [p.scale_d[i] for i in range(n_levels)] == scales
+    assert [(p.lh[i], p.lw[i]) for i in range(n_levels)] == [detect.level_size(H, W, s) for s in scales]
+    assert sum(p.oh[i] * p.ow[i] for i in range(n_levels)) == cells
+    assert p.map_off[n_levels] == 3 * cells and p.level_off[n_levels] == 3 * 3 * sum(p.lh[i] * p.lw[i] for i in range(n_levels))
+
+
+def test_argument_validation_reports_errors(lib):
+    p = lib.Pyramid()
+    with pytest.raises(lib.VnfrError, match="bad arguments"):
+        lib.call("vnfr_pyramid_plan", 1, 0, 100, 20, 0.709, C.byref(p))
+    with pytest.raises(lib.VnfrError, match="cap"):
+        lib.call("vnfr_nms_segments", 1, 100000, None, None, None, 0.5, 0, None, None, None)
+    op = lib.ConvOp()
+    op.cin = 3                                           # not a multiple of 8
+    with pytest.raises(lib.VnfrError, match="multiples of 8"):
+        lib.call("vnfr_conv_prepare", C.byref(op))
+
+
+def test_dropin_state_dict_surface():
+    from oracle import nets, synth
+    from vn_celeb_face_recognition_b200.models import MTCNN, InceptionResnetV1, MLPModel
+    enc = InceptionResnetV1(pretrained=None)
+    sd = nets.make_encoder_state_dict(seed=0, calibrate=False)
+    assert set(enc.state_dict().keys()) == set(sd.keys()) and len(sd) == 714
+    enc.load_state_dict(sd)
+    enc_c = InceptionResnetV1(pretrained=None, classify=True, num_classes=10)
+    assert enc_c.state_dict()["logits.weight"].shape == (10, 512)
+    mlp = MLPModel(512, 1001)
+    mlp.load_state_dict(nets.make_mlp_state_dict(1001))
+    det = MTCNN(image_size=160, keep_all=True, min_face_size=50)             # cfg/detection/mtcnn.json minus device
+    ref = synth.mtcnn_state_dicts()
+    for name in ("pnet", "rnet", "onet"):
+        got = getattr(det, name).state_dict()
+        assert set(got.keys()) == set(ref[name].keys())
+        for k in got:
+            assert torch.equal(got[k], ref[name][k]), "bundled %s weights not auto-loaded" % name
+    with pytest.raises(Exception, match="num_classes"):
+        InceptionResnetV1(pretrained=None, classify=True)
+    with pytest.raises(Exception, match="network"):
+        InceptionResnetV1(pretrained="vggface2")
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA -- never compute on the CPU."""
+    from vn_celeb_face_recognition_b200 import _lib
+    from vn_celeb_face_recognition_b200.models import MTCNN, InceptionResnetV1, MLPModel
+    with pytest.raises(_lib.VnfrError):
+        InceptionResnetV1(pretrained=None).eval()(torch.zeros(1, 3, 160, 160))
+    with pytest.raises(_lib.VnfrError):
+        MLPModel(512, 10).eval()(torch.zeros(1, 512))
+    with pytest.raises(_lib.VnfrError):
+        MTCNN(min_face_size=50).detect(np.zeros((64, 64, 3), np.uint8))
+    src = ""
+    pkg = os.path.join(ROOT, "vn_celeb_face_recognition_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src += open(os.path.join(dp, f)).read()
+    assert "import oracle" not in src and "from oracle" not in src, "the product must never import the oracle"
+
+
+def test_pack_layouts_are_permutations():
+    """The R/O-Net FC repack maps the reference's (W,H,C) flatten (mtcnn.py:93-94) onto the kernels' (C,H,W) order."""
+    from vn_celeb_face_recognition_b200.models import mtcnn as M
+    w = torch.arange(128 * 576, dtype=torch.float32).reshape(128, 576)
+    packed = M._fc_whc_to_chw(w, 64, 3, 3).reshape(576, 128)
+    x = torch.randn(2, 64, 3, 3)                                  # conv output (N,C,H,W)
+    ref = torch.nn.functional.linear(x.permute(0, 3, 2, 1).contiguous().view(2, -1), w)
+    got = x.reshape(2, -1) @ packed
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-2)
+    assert M._pack_pnet({k: v for k, v in __import__("oracle.synth", fromlist=["x"]).mtcnn_state_dicts()["pnet"].items()}).numel() == 6632

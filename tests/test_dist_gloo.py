@@ -1,0 +1,65 @@
+"""world_size-2 gloo test of the only collective on the path: the ragged all-gather of per-face results, and of the
+frame sharding.  CPU only."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vn_celeb_face_recognition_b200 import dist as vdist
+    n_frames = 7
+    lo, hi = vdist.shard_range(n_frames, rank, world)
+    # per-frame face counts are ragged; embeddings are a deterministic function of the global face index
+    counts = [3, 0, 2, 5, 1, 0, 4]
+    start = sum(counts[:lo])
+    n = sum(counts[lo:hi])
+    idx = torch.arange(start, start + n)
+    emb = torch.stack([torch.full((8,), float(i)) for i in idx]) if n else torch.zeros(0, 8)
+    label = idx * 3
+    prob = idx.float() / 100
+    e, l, p, c = vdist.all_gather_faces(emb, label, prob)
+    if rank == 0:
+        out.put((e.numpy(), l.numpy(), p.numpy(), c.numpy(), (lo, hi)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_all_gather_reproduces_single_process_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    e, l, p, c, rng = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    total = 15
+    assert e.shape == (total, 8) and c.tolist() == [10, 5] and rng == (0, 4)
+    np.testing.assert_array_equal(e[:, 0], np.arange(total, dtype=np.float32))      # rank-order concat = global order
+    np.testing.assert_array_equal(l, np.arange(total) * 3)
+    np.testing.assert_allclose(p, np.arange(total) / 100, atol=1e-7)
+
+
+def test_shard_range_partitions_all_items():
+    from vn_celeb_face_recognition_b200 import dist as vdist
+    for n in (0, 1, 7, 64, 65):
+        for w in (1, 2, 4, 8):
+            spans = [vdist.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
