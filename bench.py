@@ -38,8 +38,8 @@ def load_peaks():
 
 def make_frames(n, first_seed, kind="1080p"):
     """Synthetic frames that contain faces (random noise yields zero detections): seeded, frame seed = global index."""
-    from oracle import synth                # data generator only (shared with the tests); not on the product path
-    return synth.frames(kind, n, first_seed=first_seed)
+    from vn_celeb_face_recognition_b200 import synthetic
+    return synthetic.frames(kind, n, first_seed=first_seed)
 
 
 def build_models(dev, seed=0):
@@ -90,7 +90,8 @@ def cpu_reference_leg(frames, enc_sd, mlp_sd, repeats=1, threads=None):
     """The reference's CPU path on the host cores: parallel_detect_and_align + recognize_celeb semantics (oracle port of
     demo_image.py:273-306, :50-76).  Returns (faces/s, n_faces, seconds, threads)."""
     import torch
-    from oracle import pipeline as opipe, synth, align
+    from oracle import pipeline as opipe, align
+    from vn_celeb_face_recognition_b200 import synthetic as synth
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     sds = synth.mtcnn_state_dicts()

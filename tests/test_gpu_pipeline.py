@@ -249,3 +249,24 @@ def test_cal_embedding_matches_reference_golden(dev, models, tmp_path):
     # batch size dividing the file count: the reference crashes on the empty trailing batch, we skip it
     pipeline.cal_embedding(os.path.join(synth.ASSETS, "faces"), 10, models["enc"], tr, str(tmp_path / "b10"), dev)
     assert len(os.listdir(tmp_path / "b10")) == 20
+
+
+def test_host_frame_path_overlapped_copy_equals_device_path(dev, models):
+    """FacePipeline.__call__ on PINNED host frames (sub-batched H2D on a copy stream overlapping the cascade) must give
+    exactly what the device-resident single pass gives, including ragged sub-batches and repeated calls."""
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import pipeline
+    fr = np.concatenate([synth.frames("small", 3, first_seed=0), synth.frames("small", 2, first_seed=7)])
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    fp = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity")
+    fp.sub_batch = 2                                                    # 5 frames -> sub-batches 2 + 2 + 1
+    ref = fp(torch.from_numpy(fr).to(dev))
+    pinned = torch.from_numpy(fr).pin_memory()
+    for _ in range(2):
+        got = fp(pinned)
+        assert len(got) == len(ref) == 5
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a["boxes"], b["boxes"])
+            np.testing.assert_array_equal(a["labels"], b["labels"])
+            np.testing.assert_array_equal(a["emb"], b["emb"])
+    assert sum(len(r["labels"]) for r in ref) > 0

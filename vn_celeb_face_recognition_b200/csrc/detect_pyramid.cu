@@ -4,7 +4,8 @@
 // list), :71-72 + :304-306 (imresample(area) per scale + (x-127.5)*0.0078125).  The u8 frame is the only input: every
 // level pixel is the mean of its adaptive-average-pooling window [floor(i*H/oh), ceil((i+1)*H/oh)) computed as an exact
 // integer sum followed by sum/kh/kw in fp32 -- bit-identical to torch's CPU adaptive_avg_pool2d on integer pixels.
-// Work is ordered frame-major so that the 9-14 passes over one frame hit L2, and HBM sees each frame once.
+// One task per output row (see pyramid_rows_kernel); tasks are ordered frame-major so that the 9-14 passes over one
+// frame hit L2 and HBM sees each frame once.
 #include "common.cuh"
 #include <math.h>
 
@@ -49,43 +50,98 @@ extern "C" int vnfr_pyramid_plan(int B, int H, int W, int min_face_size, double 
 
 namespace {
 
+constexpr int PYR_THREADS = 256;
+
 struct PyrResizeParams {
   int B, H, W, n_levels;
   int lh[VNFR_MAX_LEVELS], lw[VNFR_MAX_LEVELS];
   long long level_off[VNFR_MAX_LEVELS];
-  long long px_off[VNFR_MAX_LEVELS + 1];
+  int row_off[VNFR_MAX_LEVELS + 1];     // prefix sum of lh: task r of a frame is output row r - row_off[l] of level l
 };
 
-__global__ void __launch_bounds__(256) pyramid_resize_kernel(const __grid_constant__ PyrResizeParams p,
-                                                             const uint8_t* __restrict__ frames, float* __restrict__ levels) {
-  const long long per_img = p.px_off[p.n_levels];
-  const long long total = per_img * p.B;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(idx / per_img);
-    const long long q = idx - (long long)b * per_img;
+// Packed accumulation of 4 source bytes: two u32 each holding two u16 lanes (bytes 0,2 and bytes 1,3).
+__device__ __forceinline__ void acc_word(uint32_t w, uint32_t& even, uint32_t& odd) {
+  even += w & 0x00FF00FFu;
+  odd += (w >> 8) & 0x00FF00FFu;
+}
+
+// One task = one output row (frame b, level l, row oy).  Its adaptive-average-pooling windows all share the source rows
+// [y0, y1), which are ONE contiguous span of the u8 frame: the CTA streams that span with V-byte loads (V = 16 when the
+// row pitch and base allow it), each thread keeping exact integer sums of its byte columns (u16 lanes, flushed to u32
+// shared memory every 256 rows), then every output pixel adds up its kw column sums.  Arithmetic of the final
+// conversion is the reference's: sum / kh / kw in fp32, then (x - 127.5) * 0.0078125 (detect_face.py:72, :305).
+template <int V>
+__global__ void __launch_bounds__(PYR_THREADS) pyramid_rows_kernel(const __grid_constant__ PyrResizeParams p,
+                                                                   const uint8_t* __restrict__ frames, float* __restrict__ levels) {
+  extern __shared__ uint32_t colsum[];          // [W*3] exact column sums of the current task
+  const int rows_per_frame = p.row_off[p.n_levels];
+  const long long n_tasks = (long long)rows_per_frame * p.B;
+  const int rowbytes = p.W * 3;
+  const int n_chunks = rowbytes / V;
+  for (long long task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    const int b = (int)(task / rows_per_frame);
+    const int r = (int)(task - (long long)b * rows_per_frame);
     int l = 0;
-    while (l + 1 < p.n_levels && q >= p.px_off[l + 1]) ++l;
+    while (l + 1 < p.n_levels && r >= p.row_off[l + 1]) ++l;
     const int lw = p.lw[l], lh = p.lh[l];
-    const int r = (int)(q - p.px_off[l]);
-    const int oy = r / lw, ox = r - oy * lw;
+    const int oy = r - p.row_off[l];
     const int y0 = (int)(((long long)oy * p.H) / lh), y1 = (int)((((long long)oy + 1) * p.H + lh - 1) / lh);
-    const int x0 = (int)(((long long)ox * p.W) / lw), x1 = (int)((((long long)ox + 1) * p.W + lw - 1) / lw);
-    unsigned s0 = 0, s1 = 0, s2 = 0;
-    const uint8_t* img = frames + (size_t)b * p.H * p.W * 3;
-    for (int y = y0; y < y1; ++y) {
-      const uint8_t* row = img + ((size_t)y * p.W + x0) * 3;
-      for (int x = 0; x < (x1 - x0); ++x) {
-        s0 += __ldg(row + 3 * x);
-        s1 += __ldg(row + 3 * x + 1);
-        s2 += __ldg(row + 3 * x + 2);
+    const uint8_t* src = frames + ((size_t)b * p.H + y0) * rowbytes;
+    for (int c = threadIdx.x; c < n_chunks; c += PYR_THREADS) {
+      uint32_t tot[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) tot[j] = 0;
+      for (int yb = y0; yb < y1; yb += 256) {
+        const int ye = min(y1, yb + 256);
+        const uint8_t* q = src + (size_t)(yb - y0) * rowbytes + (size_t)c * V;
+        if (V == 16) {
+          uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
+          int y = yb;
+          for (; y + 4 <= ye; y += 4) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint4*>(q + (size_t)u * rowbytes));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc_word(w[u].x, ev[0], od[0]); acc_word(w[u].y, ev[1], od[1]);
+              acc_word(w[u].z, ev[2], od[2]); acc_word(w[u].w, ev[3], od[3]);
+            }
+            q += (size_t)4 * rowbytes;
+          }
+          for (; y < ye; ++y) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(q));
+            acc_word(w.x, ev[0], od[0]); acc_word(w.y, ev[1], od[1]);
+            acc_word(w.z, ev[2], od[2]); acc_word(w.w, ev[3], od[3]);
+            q += rowbytes;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tot[4 * k + 0] += ev[k] & 0xFFFFu; tot[4 * k + 1] += od[k] & 0xFFFFu;
+            tot[4 * k + 2] += ev[k] >> 16;     tot[4 * k + 3] += od[k] >> 16;
+          }
+        } else {
+          for (int y = yb; y < ye; ++y) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) tot[j] += __ldg(q + j);
+            q += rowbytes;
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < V; ++j) colsum[c * V + j] = tot[j];
     }
-    const float kh = (float)(y1 - y0), kw = (float)(x1 - x0);
+    __syncthreads();
+    const float kh = (float)(y1 - y0);
     const size_t plane = (size_t)lh * lw;
-    float* o = levels + p.level_off[l] + (size_t)b * 3 * plane + (size_t)oy * lw + ox;
-    o[0] = mul_rn(sub_rn(div_rn(div_rn((float)s0, kh), kw), 127.5f), 0.0078125f);
-    o[plane] = mul_rn(sub_rn(div_rn(div_rn((float)s1, kh), kw), 127.5f), 0.0078125f);
-    o[2 * plane] = mul_rn(sub_rn(div_rn(div_rn((float)s2, kh), kw), 127.5f), 0.0078125f);
+    float* orow = levels + p.level_off[l] + (size_t)b * 3 * plane + (size_t)oy * lw;
+    for (int i = threadIdx.x; i < 3 * lw; i += PYR_THREADS) {
+      const int ch = i / lw, ox = i - ch * lw;
+      const int x0 = (int)(((long long)ox * p.W) / lw), x1 = (int)((((long long)ox + 1) * p.W + lw - 1) / lw);
+      uint32_t s = 0;
+      for (int x = x0; x < x1; ++x) s += colsum[3 * x + ch];
+      orow[ch * plane + ox] = mul_rn(sub_rn(div_rn(div_rn((float)s, kh), (float)(x1 - x0)), 127.5f), 0.0078125f);
+    }
+    __syncthreads();
   }
 }
 
@@ -96,14 +152,27 @@ extern "C" int vnfr_pyramid_resize_norm(const VnfrPyramid* pyr, const uint8_t* f
   if (pyr->B == 0 || pyr->n_levels == 0) return VNFR_OK;
   PyrResizeParams p;
   p.B = pyr->B; p.H = pyr->H; p.W = pyr->W; p.n_levels = pyr->n_levels;
+  int roff = 0;
   for (int l = 0; l < pyr->n_levels; ++l) {
-    p.lh[l] = pyr->lh[l]; p.lw[l] = pyr->lw[l]; p.level_off[l] = pyr->level_off[l]; p.px_off[l] = pyr->px_off[l];
+    p.lh[l] = pyr->lh[l]; p.lw[l] = pyr->lw[l]; p.level_off[l] = pyr->level_off[l];
+    p.row_off[l] = roff; roff += pyr->lh[l];
   }
-  p.px_off[pyr->n_levels] = pyr->px_off[pyr->n_levels];
-  const long long total = p.px_off[p.n_levels] * p.B;
-  long long grid = (total + 255) / 256;
-  if (grid > 148LL * 64) grid = 148LL * 64;
-  pyramid_resize_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(p, frames, levels);
+  p.row_off[pyr->n_levels] = roff;
+  const long long n_tasks = (long long)roff * p.B;
+  const size_t smem = (size_t)p.W * 3 * sizeof(uint32_t);
+  VNFR_REQUIRE(smem <= 200 * 1024, "frame too wide for the pyramid kernel (W*3*4 bytes of shared memory needed)");
+  const bool vec = ((size_t)p.W * 3) % 16 == 0 && ((uintptr_t)frames % 16) == 0;
+  const int per_sm = smem > 0 ? (int)((220 * 1024) / (smem + 1024)) : 8;
+  long long grid = 148LL * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+  if (grid > n_tasks) grid = n_tasks;
+  static bool attr = false;
+  if (!attr) {
+    VNFR_CUDA(cudaFuncSetAttribute(pyramid_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VNFR_CUDA(cudaFuncSetAttribute(pyramid_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  if (vec) pyramid_rows_kernel<16><<<(int)grid, PYR_THREADS, smem, (cudaStream_t)stream>>>(p, frames, levels);
+  else pyramid_rows_kernel<1><<<(int)grid, PYR_THREADS, smem, (cudaStream_t)stream>>>(p, frames, levels);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

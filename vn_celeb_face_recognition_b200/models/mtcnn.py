@@ -164,6 +164,22 @@ class DetectWorkspace:
         self.out_pts = torch.zeros(B, capf, 10, **f32)
 
 
+class ResultWorkspace:
+    """Detections of a whole batch assembled from sub-batch passes (the host-frame path overlaps the H2D copy of
+    sub-batch i+1 with the cascade of sub-batch i): just the tensors the face-crop stage and the read-back need."""
+
+    def __init__(self, B, H, W, caps, dev):
+        self.B, self.H, self.W, self.caps = B, H, W, caps
+        capf = caps[3]
+        self.counters = torch.zeros(B + 1, dtype=torch.int32, device=dev)      # out_count (B) + status
+        self.out_count = self.counters[:B]
+        self.status = self.counters[B:]
+        self.out_box = torch.zeros(B, capf, 5, dtype=torch.float32, device=dev)
+        self.out_pts = torch.zeros(B, capf, 10, dtype=torch.float32, device=dev)
+        self.offs = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.frames = None
+
+
 class MTCNN(nn.Module):
     """MTCNN face detection module -- see the module docstring; keyword arguments as in mtcnn.py:200-204."""
 
@@ -247,7 +263,7 @@ class MTCNN(nn.Module):
         key = (B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev)
         ws = self._ws.get(key)
         if ws is None:
-            if len(self._ws) > 4:
+            if len(self._ws) > 8:
                 self._ws.clear()
             ws = self._ws[key] = DetectWorkspace(B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev)
         cap1, cap2, cap3, capf = ws.caps
@@ -282,6 +298,30 @@ class MTCNN(nn.Module):
         mark("stage3_nms")
         ws.frames = frames_u8
         return ws
+
+    def detect_device_chunked(self, frames_dev, ready_events, sub):
+        """The cascade over sub-batches of ``sub`` frames of ``frames_dev`` (CUDA u8 (B,H,W,3)); sub-batch i starts as
+        soon as ``ready_events[i]`` (recorded on the copy stream after its H2D) has fired.  Returns a ResultWorkspace
+        with the detections of the whole batch."""
+        B, H, W, _ = frames_dev.shape
+        dev = frames_dev.device
+        key = ("result", B, H, W, tuple(self.caps), dev)
+        full = self._ws.get(key)
+        if full is None:
+            full = self._ws[key] = ResultWorkspace(B, H, W, tuple(self.caps), dev)
+        full.status.zero_()
+        cur = torch.cuda.current_stream(dev)
+        for i, b0 in enumerate(range(0, B, sub)):
+            b1 = min(B, b0 + sub)
+            if ready_events is not None:
+                cur.wait_event(ready_events[i])
+            ws = self.detect_device(frames_dev[b0:b1])
+            full.out_count[b0:b1].copy_(ws.out_count)
+            full.out_box[b0:b1].copy_(ws.out_box)
+            full.out_pts[b0:b1].copy_(ws.out_pts)
+            full.status.bitwise_or_(ws.status)
+        full.frames = frames_dev
+        return full
 
     @staticmethod
     def check_status(status):

@@ -68,6 +68,11 @@ class FacePipeline:
         mark = mark or (lambda name: None)
         with torch.no_grad():
             ws = self.det.detect_device(frames_u8, mark=mark)
+            return self._embed_classify(ws, mark)
+
+    def _embed_classify(self, ws, mark):
+        """detections (DetectWorkspace / ResultWorkspace) -> aligned crops -> encoder -> classifier, on the device."""
+        with torch.no_grad():
             dt = self.enc.half_dtype or encoder_plan.HALF
             u8, half, fimg, cap = self.det.face_crops_device(ws, self.mode, self.S, self.det.margin, self.template, dt,
                                                             ws.B * self.max_faces_per_frame, want_u8=self.return_faces_u8)
@@ -78,7 +83,7 @@ class FacePipeline:
             out = {"count": ws.out_count, "boxes": ws.out_box, "points": ws.out_pts, "n_faces": F, "faces_u8": None if u8 is None else u8[:F],
                    "face_img": fimg[:F], "count_host": host[:-1].copy(), "ws": ws}
             if F == 0:
-                dev = frames_u8.device
+                dev = ws.out_box.device
                 out.update(emb=torch.zeros(0, 512, device=dev), label=torch.zeros(0, dtype=torch.int64, device=dev),
                            prob=torch.zeros(0, device=dev))
                 return out
@@ -94,14 +99,45 @@ class FacePipeline:
                 out["label"], out["prob"] = label, prob
         return out
 
+    #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i)
+    sub_batch = 16
+
+    def _run_host_frames(self, t, dev):
+        """Pinned host frames -> device in sub-batches on a copy stream, the detection cascade of each sub-batch
+        starting as soon as its frames have landed; crops / encoder / classifier then run once over all faces."""
+        B, H, W, _ = t.shape
+        key = (B, H, W, dev)
+        if getattr(self, "_fbuf_key", None) != key:
+            self._fbuf = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
+            self._fbuf_key = key
+            self._copy_stream = torch.cuda.Stream(dev)
+        buf, cs = self._fbuf, self._copy_stream
+        cur = torch.cuda.current_stream(dev)
+        cs.wait_stream(cur)                                  # the previous call's kernels are done reading the buffer
+        events = []
+        with torch.cuda.stream(cs):
+            for b0 in range(0, B, self.sub_batch):
+                b1 = min(B, b0 + self.sub_batch)
+                buf[b0:b1].copy_(t[b0:b1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                events.append(ev)
+        with torch.no_grad():
+            ws = self.det.detect_device_chunked(buf, events, self.sub_batch)
+        return self._embed_classify(ws, lambda name: None)
+
     def __call__(self, frames):
         """frames: (B,H,W,3) uint8 numpy / torch (host or device).  Returns per-frame lists (boxes (n,4) numpy, labels,
-        probs) plus the (F,512) embeddings -- one H2D of the frames, one D2H of the results."""
+        probs) plus the (F,512) embeddings -- the H2D of the frames (overlapped with compute when the host tensor is
+        pinned), one D2H of the results."""
         dev = self.det._cuda_device()
         t = torch.as_tensor(frames)
-        if not t.is_cuda:
-            t = t.to(dev, non_blocking=True)
-        out = self.run_device(t)
+        if t.is_cuda:
+            out = self.run_device(t)
+        elif t.is_pinned() and t.dim() == 4 and t.shape[0] > self.sub_batch and t.dtype == torch.uint8:
+            out = self._run_host_frames(t, dev)
+        else:
+            out = self.run_device(t.to(dev, non_blocking=True))
         cnt = out["count_host"]
         F = out["n_faces"]
         nmax = int(cnt.max()) if len(cnt) else 0
