@@ -117,11 +117,13 @@ int vnfr_stage3_faces(int B, int cap3, const int32_t* s3_count, const float* s3_
  * detect_face.py:317-322, :342-378); mode 1: demo_video alignment (demo_image.py:174-199, :236-239;
  * align_face.py:51-57: 5-point similarity + cv2.warpAffine) with template_host[10] = center points (x,y)*5.
  * Faces are numbered image-major in detection order; offs [B+1] scratch.  face_u8 [max_faces][S][S][3] (nullable),
- * face_half [max_faces][S][S][8] (standardised, dtype 0 = bf16 / 1 = fp16), face_img [max_faces] (nullable).        */
+ * face_half (standardised, dtype 0 = bf16 / 1 = fp16): half_layout 0 = [max_faces][S][S][8] (3 real + 5 zero channels),
+ * 1 = space-to-depth [max_faces][ceil(S/2)][ceil(S/2)][16], channel ((y&1)*2 + (x&1))*4 + c (the buffer must be zeroed
+ * once by the caller when S is odd: pad sub-pixels are never written); face_img [max_faces] (nullable).            */
 int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int capf, const int32_t* count, const float* box,
                     const float* pts, int mode, int image_size, int margin, const float* template_host, int dtype,
                     int max_faces, int32_t* offs, uint8_t* face_u8, void* face_half, int32_t* face_img, int32_t* status,
-                    void* stream);
+                    int half_layout, void* stream);
 
 /* ---- encoder: implicit-GEMM convolution on tcgen05 / TMEM ---------------------------------------------------------
  * One fused op = conv (no bias) + folded-BN bias + optional residual add + optional ReLU, NHWC bf16 (or fp16, see `dtype`) in/out, writing
@@ -145,8 +147,13 @@ typedef struct {
   int32_t n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
   int32_t relu;
   int32_t dtype;                  /* storage type of in/weights/residual/out0/out1: 0 = bf16, 1 = fp16             */
-  int32_t a_mode;                 /* set by vnfr_conv_prepare: 0 = cp.async gather, 1 = TMA tiled (1x1), 2 = TMA im2col */
-  int32_t reserved[1];
+  int32_t a_mode;                 /* set by vnfr_conv_prepare: 0 = cp.async gather, 1 = TMA tiled (1x1), 3 = shifted view */
+  int32_t epi_mode;               /* set by vnfr_conv_prepare: 0 = per-row register epilogue, 1 = shared-memory staged tile with
+                                     TMA residual load + TMA store (single 16-bit destination)                          */
+  unsigned char tmap_c[128];      /* CUtensorMap of the destination (epi_mode 1)                                       */
+  unsigned char tmap_r[128];      /* CUtensorMap of the residual (epi_mode 1, residual != NULL)                        */
+  int32_t reserved[1];            /* [0] = sv_ck: 0, or 32 / 64 = request the shifted-view kernel (stride-1 k x k convs, cout <=
+                                     256) with weights packed k = (tap*ceil(cin/sv_ck) + chunk)*sv_ck + c               */
 } VnfrConvOp;
 
 /* Fills op->tmap_w (cuTensorMapEncodeTiled on op->weights, box {64, block_n}, 128B swizzle) and validates the op. */
@@ -170,6 +177,8 @@ int vnfr_maxpool3s2_nhwc(const void* in, int n_img, int in_h, int in_w, int c, i
 int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, void* out, int dtype, void* stream);
 /* fp32 NCHW (3 channels) -> bf16 NHWC with 8 channels (3 real + 5 zero): input adapter of InceptionResnetV1.forward. */
 int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream);
+/* Same input -> the space-to-depth layout [n][ceil(h/2)][ceil(w/2)][16] (see vnfr_face_crops half_layout 1). */
+int vnfr_nchw3_to_s2d16(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream);
 /* F.normalize(p=2, dim=1) (inception_resnet_v1.py:302): x fp32 [n][d] -> emb fp32 [n][d] and bf16 copy (nullable). */
 int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_half, int dtype, void* stream);
 /* F.log_softmax(dim=1) + argmax + exp(max log-prob) (mlp_model.py:14; demo_image.py:126-130).

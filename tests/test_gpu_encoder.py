@@ -15,7 +15,7 @@ def dev():
 
 
 def _conv_case(dev, n, h, w, cin, cout, k, stride, pad, cin_real=None, residual=False, relu=True, split=None, f32=False,
-               block_n=None, seed=0, dt=torch.bfloat16):
+               block_n=None, seed=0, dt=torch.bfloat16, sv=None, expect_mode=None):
     from vn_celeb_face_recognition_b200 import encoder_plan as ep
     g = torch.Generator(device="cpu").manual_seed(seed)
     kh, kw = (k, k) if isinstance(k, int) else k
@@ -26,7 +26,7 @@ def _conv_case(dev, n, h, w, cin, cout, k, stride, pad, cin_real=None, residual=
     wt = torch.randn(cout, cin_real, kh, kw, generator=g) / (cin_real * kh * kw) ** 0.5
     bias = torch.randn(cout, generator=g)
     xb = x.to(dev).to(dt)
-    pc = ep.pack_conv(wt, None, bias, dev, cin_pad=cin, block_n=block_n, dtype=dt)
+    pc = ep.pack_conv(wt, None, bias, dev, cin_pad=max(cin, sv or 0), block_n=block_n, dtype=dt)
     oh, ow = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
     ref = torch.nn.functional.conv2d(xb.float().permute(0, 3, 1, 2)[:, :cin_real], wt.to(dev).to(dt).float(),
                                      bias.to(dev), stride=stride, padding=(ph, pw))
@@ -58,11 +58,13 @@ def _conv_case(dev, n, h, w, cin, cout, k, stride, pad, cin_real=None, residual=
     else:
         out = torch.full((n, oh, ow, cout), float("nan"), dtype=dt, device=dev)
         ol.conv(pc, ep.View(xb), ep.View(out), stride=stride, pad=(ph, pw), relu=relu,
-                residual=None if res is None else ep.View(res))
+                residual=None if res is None else ep.View(res), sv=sv)
         ol.run()
         torch.cuda.synchronize()
         got = out.float()
         tol = 2e-2
+    if expect_mode is not None:
+        assert ol.ops[-1].conv.a_mode == expect_mode, "kernel variant %d ran, expected %d" % (ol.ops[-1].conv.a_mode, expect_mode)
     assert torch.isfinite(got).all(), "non-finite / unwritten outputs"
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
@@ -90,6 +92,27 @@ def test_igemm_conv_matches_torch(dev, case, dt):
     _conv_case(dev, dt=dt, **case)
 
 
+@pytest.mark.parametrize("case", [
+    # shifted-view kernel (csrc/sv_conv.cu, a_mode 3): resident weights, 64-byte swizzle rows (32 channels per plane)
+    dict(n=3, h=40, w=40, cin=32, cout=32, k=3, stride=1, pad=0, sv=32),              # conv2d_2a-like: several bands per image
+    dict(n=2, h=37, w=37, cin=32, cout=64, k=3, stride=1, pad=1, sv=32),              # conv2d_2b-like: TMA zero-fill = padding
+    dict(n=9, h=17, w=17, cin=32, cout=32, k=3, stride=1, pad=1, sv=32),              # Block35 3x3: several images per band
+    dict(n=2, h=17, w=17, cin=32, cout=32, k=3, stride=1, pad=1, sv=32, residual=True),
+    # 128-byte swizzle rows; 32 real channels zero-extended to a 64-channel plane by the TMA unit
+    dict(n=3, h=40, w=40, cin=32, cout=32, k=3, stride=1, pad=0, sv=64),
+    dict(n=9, h=17, w=17, cin=32, cout=32, k=3, stride=1, pad=1, sv=64),
+    dict(n=2, h=21, w=21, cin=64, cout=64, k=3, stride=1, pad=1, sv=64),
+    dict(n=3, h=40, w=40, cin=16, cout=32, k=2, stride=1, pad=0, sv=16),              # s2d stem: 32-byte swizzle rows
+    # streamed weights, two accumulator tiles per weight stage
+    dict(n=7, h=8, w=8, cin=128, cout=128, k=(1, 7), stride=1, pad=(0, 3), sv=64),
+    dict(n=7, h=8, w=8, cin=128, cout=128, k=(7, 1), stride=1, pad=(3, 0), sv=64),
+    dict(n=150, h=8, w=8, cin=128, cout=128, k=(1, 7), stride=1, pad=(0, 3), sv=64),    # more bands than SMs
+])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_shifted_view_conv_matches_torch(dev, case, dt):
+    _conv_case(dev, dt=dt, expect_mode=3, **case)
+
+
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 def test_pool_norm_softmax_kernels(dev, dt):
     from vn_celeb_face_recognition_b200 import _lib
@@ -111,6 +134,14 @@ def test_pool_norm_softmax_kernels(dev, dt):
     nhwc = torch.empty(7, 20, 24, 8, dtype=dt, device=dev)
     _lib.call("vnfr_nchw3_to_nhwc8", _lib.ptr(z), 7, 20, 24, _lib.ptr(nhwc), code, _lib.stream_ptr())
     assert torch.equal(nhwc[..., :3], z.permute(0, 2, 3, 1).to(dt)) and (nhwc[..., 3:] == 0).all()
+    for hh, ww in ((20, 24), (19, 23)):                    # even and odd sizes (odd: zero pad row / column)
+        z2 = torch.randn(7, 3, hh, ww, generator=g).to(dev)
+        s2d = torch.full((7, (hh + 1) // 2, (ww + 1) // 2, 16), float("nan"), dtype=dt, device=dev)
+        _lib.call("vnfr_nchw3_to_s2d16", _lib.ptr(z2), 7, hh, ww, _lib.ptr(s2d), code, _lib.stream_ptr())
+        zp = torch.zeros(7, 4, 2 * ((hh + 1) // 2), 2 * ((ww + 1) // 2), device=dev)
+        zp[:, :3, :hh, :ww] = z2
+        exp = zp.view(7, 4, (hh + 1) // 2, 2, (ww + 1) // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(7, (hh + 1) // 2, (ww + 1) // 2, 16)
+        assert torch.equal(s2d, exp.to(dt))
 
     e = torch.randn(9, 512, generator=g).to(dev)
     emb = torch.empty_like(e)

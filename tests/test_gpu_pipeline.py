@@ -176,14 +176,20 @@ def test_alignment_kernel_matches_cv2_path(dev, models):
         F = int(cnt.sum())
         u8 = torch.zeros(F, S, S, 3, dtype=torch.uint8, device=dev)
         half = torch.zeros(F, S, S, 8, dtype=torch.float16, device=dev)
+        half_s2d = torch.zeros(F, S // 2, S // 2, 16, dtype=torch.float16, device=dev)
         offs = torch.zeros(B + 1, dtype=torch.int32, device=dev); status = torch.zeros(1, dtype=torch.int32, device=dev)
         fimg = torch.zeros(F, dtype=torch.int32, device=dev)
         t = (C.c_float * 10)(*tmpl.reshape(-1).tolist())
         P = _lib.ptr
         d_fr, d_cnt, d_box, d_pts = torch.from_numpy(fr).to(dev), cnt.to(dev), box.to(dev), pts.to(dev)
         _lib.call("vnfr_face_crops", P(d_fr), B, H, W, capf, P(d_cnt), P(d_box), P(d_pts),
-                  1, S, 0, t, 1, F, P(offs), P(u8), P(half), P(fimg), P(status), _lib.stream_ptr())
+                  1, S, 0, t, 1, F, P(offs), P(u8), P(half), P(fimg), P(status), 0, _lib.stream_ptr())
+        _lib.call("vnfr_face_crops", P(d_fr), B, H, W, capf, P(d_cnt), P(d_box), P(d_pts),
+                  1, S, 0, t, 1, F, P(offs), None, P(half_s2d), None, P(status), 1, _lib.stream_ptr())
         torch.cuda.synchronize()
+        # space-to-depth layout = the same pixels regrouped: channel ((y&1)*2 + (x&1))*4 + c
+        regroup = half.view(F, S // 2, 2, S // 2, 2, 8)[..., :4].permute(0, 1, 3, 2, 4, 5).reshape(F, S // 2, S // 2, 16)
+        assert torch.equal(half_s2d, regroup)
         got = u8.cpu().numpy()
         k = 0
         for i in range(B):

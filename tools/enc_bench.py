@@ -12,16 +12,16 @@ mlp = MLPModel(512, 1001).to(dev).eval()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 768
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 enc.chunk = n
-x = torch.randn(n, 160, 160, 8, device=dev).to(encoder_plan.HALF)
+x = torch.randn(n, 80, 80, 16, device=dev).to(encoder_plan.HALF)
 for _ in range(2):
-    e, e16 = enc.embed_nhwc8(x)
+    e, e16 = enc.embed_s2d(x, 160)
     lab, pr = mlp.classify_half(e16)
 torch.cuda.synchronize()
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 l0 = _lib.launch_count()
 t0.record()
 for _ in range(iters):
-    e, e16 = enc.embed_nhwc8(x)
+    e, e16 = enc.embed_s2d(x, 160)
     lab, pr = mlp.classify_half(e16)
 t1.record()
 torch.cuda.synchronize()

@@ -35,7 +35,8 @@ class ConvOp(C.Structure):
         ("out_h", C.c_int32), ("out_w", C.c_int32),
         ("cout", C.c_int32), ("cout_pad", C.c_int32), ("k_pad", C.c_int32), ("block_n", C.c_int32),
         ("n_split", C.c_int32), ("out0_pitch", C.c_int32), ("out1_pitch", C.c_int32), ("res_pitch", C.c_int32),
-        ("out_f32_pitch", C.c_int32), ("relu", C.c_int32), ("dtype", C.c_int32), ("a_mode", C.c_int32), ("reserved", C.c_int32 * 1),
+        ("out_f32_pitch", C.c_int32), ("relu", C.c_int32), ("dtype", C.c_int32), ("a_mode", C.c_int32), ("epi_mode", C.c_int32),
+        ("tmap_c", C.c_ubyte * 128), ("tmap_r", C.c_ubyte * 128), ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -58,13 +59,14 @@ _SIGS = {
     "vnfr_onet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "vnfr_stage2_boxes": [_I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P],
     "vnfr_stage3_faces": [_I, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P],
-    "vnfr_face_crops": [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P],
+    "vnfr_face_crops": [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "vnfr_conv_prepare": [C.POINTER(ConvOp)],
     "vnfr_conv_run": [C.POINTER(ConvOp), _P],
     "vnfr_run_ops": [C.POINTER(Op), _I, _P],
     "vnfr_maxpool3s2_nhwc": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "vnfr_avgpool_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "vnfr_nchw3_to_nhwc8": [_P, _I, _I, _I, _P, _I, _P],
+    "vnfr_nchw3_to_s2d16": [_P, _I, _I, _I, _P, _I, _P],
     "vnfr_l2norm_rows": [_P, _I, _I, _I, _P, _P, _I, _P],
     "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
 }

@@ -99,6 +99,34 @@ __global__ void nchw3_to_nhwc8_kernel(const float* __restrict__ in, int n_img, i
   }
 }
 
+// fp32 NCHW (3 planes) -> 16-bit space-to-depth [n][h2][w2][16]: one thread per 2x2 cell = two 16-byte stores.
+template <bool F16>
+__global__ void nchw3_to_s2d16_kernel(const float* __restrict__ in, int n_img, int h, int w, __nv_bfloat16* __restrict__ out) {
+  const int h2 = (h + 1) >> 1, w2 = (w + 1) >> 1;
+  const long long total = (long long)n_img * h2 * w2;
+  const long long hw = (long long)h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / (h2 * w2);
+    const int rem = (int)(i - img * (h2 * w2));
+    const int cy = rem / w2, cx = rem - cy * w2;
+    uint32_t wds[8];
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int y = 2 * cy + (sub >> 1), x = 2 * cx + (sub & 1);
+      float r = 0.f, g = 0.f, bl = 0.f;
+      if (y < h && x < w) {
+        const float* b = in + img * 3 * hw + (long long)y * w + x;
+        r = __ldg(b); g = __ldg(b + hw); bl = __ldg(b + 2 * hw);
+      }
+      wds[2 * sub] = pack_h2<F16>(r, g);
+      wds[2 * sub + 1] = pack_h2<F16>(bl, 0.f);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    o[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -198,6 +226,16 @@ extern "C" int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, voi
   if (n_img == 0) return VNFR_OK;
   auto kern = dtype == 1 ? nchw3_to_nhwc8_kernel<true> : nchw3_to_nhwc8_kernel<false>;
   kern<<<grid_for((long long)n_img * h * w, 256), 256, 0, (cudaStream_t)stream>>>(in, n_img, h * w, (__nv_bfloat16*)out);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_nchw3_to_s2d16(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream) {
+  if (n_img == 0) return VNFR_OK;
+  auto kern = dtype == 1 ? nchw3_to_s2d16_kernel<true> : nchw3_to_s2d16_kernel<false>;
+  kern<<<grid_for((long long)n_img * ((h + 1) / 2) * ((w + 1) / 2), 256), 256, 0, (cudaStream_t)stream>>>(in, n_img, h, w,
+                                                                                                    (__nv_bfloat16*)out);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

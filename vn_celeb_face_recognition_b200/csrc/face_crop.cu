@@ -26,7 +26,7 @@ constexpr int MAX_S = 256;                 // largest supported output edge
 
 struct FaceArgs {
   const uint8_t* frames;
-  int B, H, W, capf, S, mode, margin, max_faces, f16;
+  int B, H, W, capf, S, mode, margin, max_faces, f16, s2d;
   const int* count;        // [B]
   const float* box;        // [B][capf][5]
   const float* pts;        // [B][capf][10]  (x0,y0,...,x4,y4)
@@ -53,7 +53,18 @@ __device__ __forceinline__ void store_px(const FaceArgs& a, size_t px, unsigned 
     const __nv_bfloat162 h0 = __floats2bfloat162_rn(fr, fg), h1 = __floats2bfloat162_rn(fb, 0.f);
     w0 = *reinterpret_cast<const uint32_t*>(&h0); w1 = *reinterpret_cast<const uint32_t*>(&h1);
   }
-  *reinterpret_cast<uint4*>(a.face_h + px * 8) = make_uint4(w0, w1, 0u, 0u);
+  if (a.s2d) {
+    // space-to-depth layout [f][ceil(S/2)][ceil(S/2)][16]: channel = ((y&1)*2 + (x&1))*4 + c -- the stride-2 3x3 stem
+    // convolution becomes a stride-1 2x2 convolution over 16 channels (see encoder_plan.pack_stem_s2d)
+    const int S = a.S, S2 = (S + 1) >> 1;
+    const size_t f = px / ((size_t)S * S);
+    const int rem = (int)(px - f * (size_t)S * S);
+    const int y = rem / S, x = rem - y * S;
+    unsigned short* dst = a.face_h + ((f * S2 + (y >> 1)) * S2 + (x >> 1)) * 16 + (((y & 1) << 1) | (x & 1)) * 4;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(w0, w1);
+  } else {
+    *reinterpret_cast<uint4*>(a.face_h + px * 8) = make_uint4(w0, w1, 0u, 0u);
+  }
 }
 
 __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
@@ -226,7 +237,7 @@ void build_bilinear_table(unsigned short* tab) {
 extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int capf, const int32_t* count, const float* box,
                                const float* pts, int mode, int image_size, int margin, const float* template_host, int dtype,
                                int max_faces, int32_t* offs, uint8_t* face_u8, void* face_half, int32_t* face_img, int32_t* status,
-                               void* stream) {
+                               int half_layout, void* stream) {
   VNFR_REQUIRE(frames && count && box && offs && face_half && status, "null pointer");
   VNFR_REQUIRE(image_size <= MAX_S, "image_size larger than 256 is not supported");
   VNFR_REQUIRE(mode == 0 || (mode == 1 && pts != nullptr && template_host != nullptr), "align mode needs landmarks and a template");
@@ -244,7 +255,7 @@ extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int c
   ++g_vnfr_launches;
   FaceArgs a;
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.capf = capf; a.S = image_size; a.mode = mode; a.margin = margin;
-  a.max_faces = max_faces; a.f16 = dtype == 1;
+  a.max_faces = max_faces; a.f16 = dtype == 1; a.s2d = half_layout == 1;
   a.count = count; a.box = box; a.pts = pts; a.offs = offs;
   for (int i = 0; i < 10; ++i) a.tmpl[i] = template_host ? template_host[i] : 0.f;
   a.face_u8 = face_u8; a.face_h = (unsigned short*)face_half; a.face_img = face_img; a.status = status;

@@ -12,174 +12,11 @@
 // Replaces the cuDNN / cuBLAS call sites of inception_resnet_v1.py:12-33, :56-67, :85-95, :114-126, :296-297 and
 // mlp_model.py:10-15.  One CTA = one 128 x block_n output tile; ~96 KB of shared memory and
 // <= 256 TMEM columns per CTA so that two CTAs share an SM and one's epilogue overlaps the other's main loop.
-#include "common.cuh"
-#include <string.h>
-#include <stdlib.h>
-#include <cuda_fp16.h>
+#include "tc_common.cuh"
+
+using namespace tc;
 
 namespace {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                       // bf16 elements: 128 bytes = one swizzle-128B row
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_PRODUCER_THREADS = 256;         // warps 0-7: A gather, two threads per GEMM row
-constexpr int NUM_EPILOGUE_THREADS = 256;         // warps 8-15: two warps per TMEM lane quarter, alternating 16-column chunks
-constexpr int NUM_THREADS = 576;                  // warp 16: TMA producer, warp 17: TMEM alloc + MMA issue
-constexpr int MAX_STAGES = 8;
-
-struct ConvParams {
-  const __nv_bfloat16* in;
-  const float* bias;
-  const __nv_bfloat16* residual;
-  __nv_bfloat16* out0;
-  __nv_bfloat16* out1;
-  float* out_f32;
-  int n_img, in_h, in_w, cin, in_pitch;
-  int kh, kw, stride, pad_h, pad_w;
-  int out_h, out_w;
-  int M, K, cout, k_blocks, block_n, n_tiles_m, n_tiles_n;
-  int n_split, out0_pitch, out1_pitch, res_pitch, out_f32_pitch;
-  int relu;
-  int stages, tmem_cols;
-  int a_mode;  // 0: cp.async gather by warps 0-7, 1: TMA tiled 2-D (1x1 convs), 2: TMA im2col
-  int dtype;   // 0 = bf16, 1 = fp16 (both: fp32 accumulation in TMEM)
-};
-
-// ------------------------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ uint64_t globaltimer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a protocol bug must trap (launch error), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 2000000000ull) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// one (non-incrementing) arrival on `bar` once all cp.async issued so far by this thread have landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// K-major, 128B-swizzled shared-memory matrix descriptor (rows of 128 B, 8-row groups 1024 B apart).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address  [0,14)
-  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major) [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows * 128 B  [32,46)
-  d |= (uint64_t)1 << 46;                             // descriptor version 1 (sm_100)
-  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: D fp32, A/B bf16 (format 1) or fp16 (format 0), both K-major, M = 128, N = n.
-__device__ __forceinline__ uint32_t make_idesc_f16(int n, int is_fp16) {
-  const uint32_t fmt = is_fp16 ? 0u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-// 16-bit float helpers parameterised on the storage type (F16 = true: IEEE half, false: bfloat16)
-template <bool F16>
-__device__ __forceinline__ void unpack2(uint32_t w, float& lo, float& hi) {
-  if (F16) {
-    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
-    lo = f.x; hi = f.y;
-  } else {
-    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xFFFF0000u);
-  }
-}
-template <bool F16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (F16) {
-    // saturate instead of overflowing to inf (fp16 range 65504)
-    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
-    const __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-  } else {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t*>(&h);
-  }
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-// the "+r" ties make every later use of v[] depend on the wait
-__device__ __forceinline__ void tmem_ld_wait(float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 // ---------------------------------------------------------------------------------------------------------- kernel
 // Persistent, warp-specialised: one CTA per SM walks over output tiles (tile = 128 rows x block_n channels).
@@ -194,17 +31,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 // Shared memory: [A stage 0..S) 16 KB each][W stage 0..S) block_n*128 B each][bias 2 x 256 fp32][barriers].
 template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const ConvParams p) {
+igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + (uint32_t)S * A_STAGE_BYTES;
-  const uint32_t smem_bias = smem_b + (uint32_t)S * b_stage_bytes;          // 2 x 256 floats
+  const uint32_t smem_c = smem_b + (uint32_t)S * b_stage_bytes;             // staged C tile: 64-channel panels of 16 KB
+  const uint32_t n_panels = p.epi_mode ? (uint32_t)((p.block_n + 63) >> 6) : 0u;
+  const uint32_t smem_bias = smem_c + n_panels * 16384u;                    // 2 x 256 floats
   const uint32_t bars = smem_bias + 2048u;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bar_tfull + 16u,
-                 tmem_slot = bar_tempty + 16u;
+                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 8u, tmem_slot = bar_cfree + 8u;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x;
@@ -223,11 +63,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_init(bar_tfull + 8u * i, 1);
       mbar_init(bar_tempty + 8u * i, NUM_EPILOGUE_THREADS);
     }
+    mbar_init(bar_res, 1);
+    mbar_init(bar_cfree, 1);
     fence_barrier_init();
   }
   if (warp == 16 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     if (p.a_mode != 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    if (p.epi_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_c) : "memory");
+    if (p.epi_mode && p.residual != nullptr) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_r) : "memory");
   }
   if (warp == 17) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)(2 * p.tmem_cols))
@@ -249,7 +93,8 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int j = tid & 7;                     // chunk inside the 128-byte row
     const int rg = tid >> 3;                   // 0..31
     const int hw = p.out_h * p.out_w;
-    int it = 0;                                // K blocks issued so far (all tiles)
+    int s = 0;                                 // ring stage / phase parity: wrapping counters, no division in the loop
+    uint32_t ph = 1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_base = (tile / n_tiles_n) * BLOCK_M;
       int iy0[4], ix0[4];
@@ -278,10 +123,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       int kf = j * 8;
       int c = kf, ky = 0, kx = 0;
       while (c >= p.cin) { c -= p.cin; if (++kx == p.kw) { kx = 0; ++ky; } }
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % S;
+      for (int kb = 0; kb < KB; ++kb) {
         const bool k_ok = kf < p.K;
-        mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+        mbar_wait(bar_empty + 8u * s, ph);
         const uint32_t stage = smem_a + (uint32_t)s * A_STAGE_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -291,6 +135,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           cp_async_16(stage + dst_off[q], src, ok ? 16u : 0u);
         }
         cp_async_arrive_noinc(bar_full + 8u * s);
+        if (++s == S) { s = 0; ph ^= 1u; }
         kf += 64;
         c += 64;
         while (c >= p.cin) { c -= p.cin; if (++kx == p.kw) { kx = 0; ++ky; } }
@@ -314,76 +159,41 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       // stage this tile's bias while the MMAs are still running
       float* sb = s_bias + ab * 256;
       for (int i = et; i < n_valid; i += NUM_EPILOGUE_THREADS) sb[i] = __ldg(p.bias + n0 + i);
-      const __nv_bfloat16* res_row = p.residual != nullptr && row_ok ? p.residual + (size_t)m * p.res_pitch + n0 : nullptr;
-      uint4 rn0 = make_uint4(0, 0, 0, 0), rn1 = rn0;
-      if (res_row != nullptr && chalf * 16 < n_valid) {
-        rn0 = __ldg(reinterpret_cast<const uint4*>(res_row + chalf * 16));
-        rn1 = __ldg(reinterpret_cast<const uint4*>(res_row + chalf * 16) + 1);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");      // bias visible to the 4 epilogue warps
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");      // bias visible to the 8 epilogue warps
       mbar_wait(bar_tfull + 8u * ab, (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tmem_cols);
-      for (int c0 = chalf * 16; c0 < n_valid; c0 += 32) {
-        float v[16];
-        __syncwarp();
-        tmem_ld16_issue(t_row + (uint32_t)c0, v);        // warp-collective, also for rows >= M
-        const uint4 rc0 = rn0, rc1 = rn1;
-        if (res_row != nullptr && c0 + 32 < n_valid) {   // prefetch the next chunk's residual under this chunk's math
-          rn0 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32));
-          rn1 = __ldg(reinterpret_cast<const uint4*>(res_row + c0 + 32) + 1);
+      if (p.epi_mode) {
+        // staged: the C panels are free (and hold the residual, if any) once bar_res completes for this tile
+        mbar_wait(bar_res, tcount & 1);
+        epilogue_row_staged<F16>(p, sb, t_row, smem_c, r, n_valid, chalf, p.residual != nullptr);
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8u * ab);     // accumulator drained: the MMA warp may reuse it
+        fence_proxy_async_smem();              // generic-proxy writes of the tile -> visible to the TMA store
+        asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");
+        if (et == 0) {
+          const int m0 = (tile / n_tiles_n) * BLOCK_M;
+          for (int j = 0; j * 64 < n_valid; ++j) tma_store_2d(&tmap_c, smem_c + (uint32_t)j * 16384u, n0 + j * 64, m0);
+          tma_store_commit();
+          tma_store_wait_read();               // the panels have been read: they may be refilled
+          mbar_arrive(bar_cfree);
         }
-        tmem_ld_wait(v);
-        if (row_ok) {
-          const int n = n0 + c0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + 4 * i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-          }
-          if (res_row != nullptr) {
-            const uint32_t w[8] = {rc0.x, rc0.y, rc0.z, rc0.w, rc1.x, rc1.y, rc1.z, rc1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float lo, hi;
-              unpack2<F16>(w[e], lo, hi);
-              v[2 * e + 0] += lo;
-              v[2 * e + 1] += hi;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-          }
-          if (p.out_f32 != nullptr) {
-            float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.out_f32_pitch + n);
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) o[qq] = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
-          } else {
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack2<F16>(v[2 * i], v[2 * i + 1]);
-            __nv_bfloat16* dst = (n < p.n_split) ? p.out0 + (size_t)m * p.out0_pitch + n
-                                                 : p.out1 + (size_t)m * p.out1_pitch + (n - p.n_split);
-            uint4* o = reinterpret_cast<uint4*>(dst);
-            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-        }
+        continue;
       }
+      epilogue_row<F16>(p, sb, t_row, m, row_ok, n0, n_valid, chalf);
       tc_fence_before();
       mbar_arrive(bar_tempty + 8u * ab);       // accumulator buffer `ab` may be overwritten
     }
   } else if (warp == 16) {
     // ================================================= W producer: TMA, one elected lane
     if (lane == 0) {
-      int it = 0;
+      int s = 0, tn = 0;
+      uint32_t ph = 1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % n_tiles_n) * p.block_n;
         const int m0 = (tile / n_tiles_n) * BLOCK_M;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(bar_empty + 8u * s, ((it / S) & 1) ^ 1);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_empty + 8u * s, ph);
           if (p.a_mode == 1) {
             // 1x1 convolution: the A tile is a plain 2-D box of the [M][pitch] activation matrix
             mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes + A_STAGE_BYTES);
@@ -392,26 +202,47 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
           }
           tma_load_2d(smem_b + (uint32_t)s * b_stage_bytes, &tmap_w, bar_full + 8u * s, kb * BLOCK_K, n0);
+          if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        if (p.epi_mode) {
+          // C panels: wait until the previous tile's TMA store has read them, then (re)fill them with this tile's
+          // residual.  Issued AFTER the tile's K-block loads so that it never holds up the MMA pipeline; the ring depth
+          // gives the load its lead time over the epilogue.
+          mbar_wait(bar_cfree, (uint32_t)((tn & 1) ^ 1));
+          if (p.residual != nullptr) {
+            const int n_valid = min(p.block_n, p.cout - n0);
+            const int np = (n_valid + 63) >> 6;
+            mbar_arrive_expect_tx(bar_res, (uint32_t)np * 16384u);
+            for (int j = 0; j < np; ++j) tma_load_2d(smem_c + (uint32_t)j * 16384u, &tmap_r, bar_res, n0 + j * 64, m0);
+          } else {
+            mbar_arrive(bar_res);
+          }
+          ++tn;
         }
       }
     }
   } else {
-    // ================================================= MMA issuer: one elected lane
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(p.block_n, F16 ? 1 : 0);
-      int it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const int ab = tcount & 1;
-        mbar_wait(bar_tempty + 8u * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+    // ================================================= MMA issuer.  The whole warp runs the loop convergently so that
+    // stage / phase counters and descriptors live in uniform registers (a lane-0-only loop costs ~25 scalar
+    // instructions + a register->uniform waterfall per tcgen05.mma, measured ~300 cycles per instruction); only the
+    // tcgen05 instructions themselves are predicated on one elected lane.
+    const uint32_t idesc = make_idesc_f16(p.block_n, F16 ? 1 : 0);
+    int s = 0, tcount = 0;
+    uint32_t ph = 0;
+    const uint64_t a_desc0 = make_sw128_desc(smem_a), b_desc0 = make_sw128_desc(smem_b);
+    const uint32_t b_stage16 = b_stage_bytes >> 4;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int ab = tcount & 1;
+      mbar_wait(bar_tempty + 8u * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.tmem_cols);
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(bar_full + 8u * s, ph);
+        if (p.a_mode == 0) fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.tmem_cols);
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % S;
-          mbar_wait(bar_full + 8u * s, (it / S) & 1);
-          if (p.a_mode == 0) fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
-          tc_fence_after();
-          const uint64_t a_desc = make_sw128_desc(smem_a + (uint32_t)s * A_STAGE_BYTES);
-          const uint64_t b_desc = make_sw128_desc(smem_b + (uint32_t)s * b_stage_bytes);
+        const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)s * (A_STAGE_BYTES >> 4));
+        const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)s * b_stage16);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
             // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (>>4) start-address field
@@ -419,12 +250,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           }
           umma_commit(bar_empty + 8u * s);     // smem stage reusable once these MMAs have read it
         }
-        umma_commit(bar_tfull + 8u * ab);      // accumulator complete
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1u; }
       }
+      if (elect_one()) umma_commit(bar_tfull + 8u * ab);      // accumulator complete
+      __syncwarp();
     }
-    __syncwarp();
   }
 
+  if (p.epi_mode && tid == NUM_PRODUCER_THREADS) tma_store_wait_all();     // the storing thread: writes have landed
   __syncthreads();
   if (warp == 17) {
     tc_fence_after();
@@ -433,34 +267,21 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 int g_num_sms = 148;
 
-int pick_stages(int block_n) {
+int staging_bytes(int block_n, int epi_mode) { return epi_mode ? ((block_n + 63) / 64) * 16384 : 0; }
+
+int pick_stages(int block_n, int epi_mode) {
   const int stage_bytes = A_STAGE_BYTES + block_n * 128;
-  int s = (220 * 1024) / stage_bytes;          // one persistent CTA per SM owns (almost) all of its shared memory
+  int s = (220 * 1024 - staging_bytes(block_n, epi_mode)) / stage_bytes;   // one persistent CTA per SM owns (almost) all of its shared memory
   if (s < 2) s = 2;
   if (s > MAX_STAGES) s = MAX_STAGES;
   return s;
 }
 
-size_t smem_bytes_for(int block_n, int stages) {
-  return 1024 /*alignment slack*/ + (size_t)stages * (A_STAGE_BYTES + block_n * 128) + 2048 /*bias*/ + 16 * stages + 64;
+size_t smem_bytes_for(int block_n, int stages, int epi_mode) {
+  return 1024 /*alignment slack*/ + (size_t)stages * (A_STAGE_BYTES + block_n * 128) + staging_bytes(block_n, epi_mode) +
+         2048 /*bias*/ + 16 * stages + 96;
 }
 
 }  // namespace
@@ -487,6 +308,12 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
     vnfr_set_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return VNFR_ERR_CUDA;
   }
+  op->a_mode = 0;
+  if (op->reserved[0] != 0 && getenv("VNFR_NO_SV") == nullptr) {
+    // shifted-view kernel requested (reserved[0] = channels per plane); falls back to the generic path when the
+    // geometry does not qualify (the caller checks a_mode when its weight packing is not generic-compatible)
+    if (vnfr_sv_prepare(op) == VNFR_OK) return VNFR_OK;
+  }
   CUtensorMap tm;
   const cuuint64_t dims[2] = {(cuuint64_t)op->k_pad, (cuuint64_t)op->cout_pad};
   const cuuint64_t strides[1] = {(cuuint64_t)op->k_pad * 2};
@@ -500,8 +327,36 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
     return VNFR_ERR_CUDA;
   }
   memcpy(op->tmap_w, &tm, sizeof(tm));
+  // staged epilogue (TMA residual load + TMA store): single 16-bit destination whose rows are 16-byte aligned
+  op->epi_mode = 0;
+  {
+    const long long Mo = (long long)op->n_img * op->out_h * op->out_w;
+    // every stored 64-channel panel must lie inside its own N tile: block_n a multiple of 64, or a single N tile
+    const bool single = op->out_f32 == nullptr && op->n_split >= op->cout && op->out0 != nullptr &&
+                        (op->block_n % 64 == 0 || op->cout <= op->block_n);
+    if (single && Mo > 0 && ((uintptr_t)op->out0 % 16 == 0) && op->out0_pitch % 8 == 0 &&
+        (op->residual == nullptr || (((uintptr_t)op->residual % 16 == 0) && op->res_pitch % 8 == 0)) &&
+        getenv("VNFR_NO_TMA_EPILOGUE") == nullptr) {
+      const CUtensorMapDataType dt = op->dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      const cuuint64_t cdims[2] = {(cuuint64_t)op->cout, (cuuint64_t)Mo};
+      const cuuint32_t cbox[2] = {64, BLOCK_M};
+      CUtensorMap tcm, trm;
+      const cuuint64_t cstr[1] = {(cuuint64_t)op->out0_pitch * 2};
+      bool ok = enc(&tcm, dt, 2, op->out0, cdims, cstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      if (ok && op->residual != nullptr) {
+        const cuuint64_t rstr[1] = {(cuuint64_t)op->res_pitch * 2};
+        ok = enc(&trm, dt, 2, const_cast<void*>(op->residual), cdims, rstr, cbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        if (ok) memcpy(op->tmap_r, &trm, sizeof(trm));
+      }
+      if (ok) {
+        memcpy(op->tmap_c, &tcm, sizeof(tcm));
+        op->epi_mode = 1;
+      }
+    }
+  }
   // A operand: 1x1 / stride 1 / no padding convolutions read a plain [M][in_pitch] matrix -> 2-D tiled TMA
-  op->a_mode = 0;
   const long long M = (long long)op->n_img * op->out_h * op->out_w;
   if (op->kh == 1 && op->kw == 1 && op->stride == 1 && op->pad_h == 0 && op->pad_w == 0 && M > 0 &&
       ((uintptr_t)op->in % 16 == 0) && getenv("VNFR_NO_TMA_A") == nullptr) {
@@ -522,6 +377,7 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
 
 extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   VNFR_REQUIRE(op != nullptr, "op is null");
+  if (op->a_mode == 3) return vnfr_sv_run(op, stream);
   static bool attr_set = false;
   if (!attr_set) {
     VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -548,22 +404,25 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   p.relu = op->relu;
   p.dtype = op->dtype;
   p.a_mode = op->a_mode;
-  p.stages = pick_stages(op->block_n);
+  p.epi_mode = op->epi_mode;
+  p.stages = pick_stages(op->block_n, op->epi_mode);
   int cols = 32;
   while (cols < op->block_n) cols <<= 1;
   p.tmem_cols = cols;
   if (p.M <= 0) return VNFR_OK;
-  CUtensorMap tm, ta;
+  CUtensorMap tm, ta, tc_, tr;
   memcpy(&tm, op->tmap_w, sizeof(tm));
   memcpy(&ta, op->a_mode != 0 ? op->tmap_a : op->tmap_w, sizeof(ta));
+  memcpy(&tc_, op->epi_mode ? op->tmap_c : op->tmap_w, sizeof(tc_));
+  memcpy(&tr, (op->epi_mode && op->residual != nullptr) ? op->tmap_r : op->tmap_w, sizeof(tr));
   p.n_tiles_m = ceil_div(p.M, BLOCK_M);
   p.n_tiles_n = ceil_div(op->cout, op->block_n);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   dim3 grid(total_tiles < g_num_sms ? total_tiles : g_num_sms);
   if (op->dtype == 1)
-    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, ta, p);
+    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
   else
-    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages), (cudaStream_t)stream>>>(tm, ta, p);
+    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

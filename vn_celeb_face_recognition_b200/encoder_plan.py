@@ -24,6 +24,13 @@ BN_EPS = 1e-3
 HALF = torch.bfloat16 if os.environ.get("VNFR_HALF_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
 
 
+# channels-per-plane of the shifted-view kernel by input channel count (0 / missing = generic gather kernel).
+# 32-channel inputs use 64-byte swizzle rows; everything else 128-byte rows.
+SV_DEFAULT = {16: 16, 32: 32, 64: 64, 128: 64, 192: 64, 256: 64}
+if os.environ.get("VNFR_NO_SV"):
+    SV_DEFAULT = {}
+
+
 def dtype_code(dt):
     return 1 if dt == torch.float16 else 0
 
@@ -41,12 +48,14 @@ class PackedConv:
 
 
 def pick_block_n(cout):
+    """N tile: one tcgen05.mma costs the same for any N <= 256 (the shared-memory read of the 128-row A operand is the
+    floor), so tiles are as wide as possible; multiples of 64 keep the TMA-store panels inside their tile."""
     if cout <= 256:
         return cout
-    for bn in (256, 224, 192, 160, 144, 128, 112, 96, 80, 64):
+    for bn in (256, 192):
         if cout % bn == 0:
             return bn
-    return 64
+    return 256            # zero-padded last tile (cout_pad), e.g. 896 -> 4 x 256
 
 
 def pack_conv(w, scale, bias, device, cin_pad=None, block_n=None, dtype=None):
@@ -90,6 +99,24 @@ def pack_basic(sd, prefixes, device, cin_pad=None, block_n=None, dtype=None):
     return pack_conv(torch.cat(ws, 0), None, torch.cat(bs, 0), device, cin_pad, block_n, dtype)
 
 
+def pack_stem_s2d(sd, prefix, device, dtype=None):
+    """conv2d_1a (3x3, stride 2, 3 -> 32; inception_resnet_v1.py:219) re-expressed on the space-to-depth input
+    [n][H/2][W/2][16] (channel = ((y&1)*2 + (x&1))*4 + c): a stride-1 2x2 convolution over 16 channels whose tap (ty,tx)
+    / sub-pixel (sy,sx) weight is the original tap (ky,kx) = (2ty+sy, 2tx+sx) (zero where ky or kx would be 3)."""
+    w, s, b = fold_bn(sd, prefix)
+    w = (w * s.view(-1, 1, 1, 1)).float()                       # (32, 3, 3, 3) [co][ci][ky][kx]
+    co = w.shape[0]
+    w2 = torch.zeros(co, 16, 2, 2, dtype=torch.float32, device=w.device)
+    for ty in range(2):
+        for tx in range(2):
+            for sy in range(2):
+                for sx in range(2):
+                    ky, kx = 2 * ty + sy, 2 * tx + sx
+                    if ky < 3 and kx < 3:
+                        w2[:, (sy * 2 + sx) * 4:(sy * 2 + sx) * 4 + 3, ty, tx] = w[:, :, ky, kx]
+    return pack_conv(w2, None, b, device, cin_pad=16, dtype=dtype)
+
+
 def pack_projection(sd, p, scale, device, block_n=None, dtype=None):
     """Block projection conv2d (with bias), residual scale folded in."""
     return pack_conv(sd[p + ".weight"].float() * scale, None, sd[p + ".bias"].float() * scale, device, None, block_n, dtype)
@@ -131,8 +158,16 @@ class OpList:
         self.keep = []
         self._arr = None
 
-    def conv(self, pc, src, dst0, stride=1, pad=(0, 0), relu=True, dst1=None, n_split=None, residual=None, out_f32=None):
-        assert src.c == pc.cin, (src.c, pc.cin)
+    def conv(self, pc, src, dst0, stride=1, pad=(0, 0), relu=True, dst1=None, n_split=None, residual=None, out_f32=None,
+             sv=None):
+        """``sv`` = 32 / 64 requests the shifted-view kernel (csrc/sv_conv.cu) with that many channels per plane; the
+        packed weights must then be laid out with cin padded to a multiple of ``sv`` (pc.cin)."""
+        if sv is None:
+            sv = SV_DEFAULT.get(src.c) if (stride == 1 and pc.kh * pc.kw > 1 and pc.cout <= 256 and out_f32 is None
+                                            and pc.block_n == pc.cout == pc.cout_pad) else 0
+            if sv and pc.cin != _ceil(src.c, sv):
+                sv = 0
+        assert (src.c == pc.cin) or (sv and pc.cin == _ceil(src.c, sv)), (src.c, pc.cin, sv)
         op = _lib.Op()
         op.kind = 0
         c = op.conv
@@ -160,7 +195,10 @@ class OpList:
                 assert dst0.c == pc.cout, (dst0.c, pc.cout)
         if residual is not None:
             c.residual, c.res_pitch = residual.ptr, residual.pitch
+        c.reserved[0] = int(sv or 0)
         _lib.call("vnfr_conv_prepare", C.byref(c))
+        if pc.cin != src.c and c.a_mode != 3:
+            raise _lib.VnfrError("weights were packed for the shifted-view kernel but the geometry does not qualify")
         self.ops.append(op)
         self.keep += [pc, src, dst0, dst1, residual]
         self._arr = None
@@ -207,7 +245,7 @@ class EncoderWeights:
         pack_projection = functools.partial(globals()["pack_projection"], dtype=self.dtype)
         pack_conv = functools.partial(globals()["pack_conv"], dtype=self.dtype)
         P = {}
-        P["conv2d_1a"] = pack_basic(sd, ["conv2d_1a"], d, cin_pad=8)
+        P["conv2d_1a"] = pack_stem_s2d(sd, "conv2d_1a", d, dtype=self.dtype)
         for n in ["conv2d_2a", "conv2d_2b", "conv2d_3b", "conv2d_4a", "conv2d_4b"]:
             P[n] = pack_basic(sd, [n], d)
         for i in range(5):
@@ -223,7 +261,7 @@ class EncoderWeights:
         P["m6a.b1c"] = pack_basic(sd, ["mixed_6a.branch1.2"], d)
         for i in range(10):
             p = "repeat_2.%d" % i
-            P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0"], d, block_n=128)            # N = 256
+            P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0"], d, block_n=256)            # N = 256
             P[p + ".b1a"] = pack_basic(sd, [p + ".branch1.1"], d)
             P[p + ".b1b"] = pack_basic(sd, [p + ".branch1.2"], d)
             P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.10, d)
@@ -253,8 +291,9 @@ def _out_hw(h, k, s, p=0):
 
 
 class EncoderPlan:
-    """Op list + activation buffers of one forward for a fixed (batch, H, W).  Input: ``self.x0`` NHWC8 bf16; output:
-    ``self.emb_raw`` fp32 (n, 512) = last_bn(last_linear(avgpool)), before L2 normalisation."""
+    """Op list + activation buffers of one forward for a fixed (batch, H, W).  Input: ``self.x0``, the 16-bit
+    space-to-depth crop tensor (n, ceil(H/2), ceil(W/2), 16) (see pack_stem_s2d); output: ``self.emb_raw`` fp32 (n, 512)
+    = last_bn(last_linear(avgpool)), before L2 normalisation."""
 
     def __init__(self, weights, n, h, w, device):
         P = weights.P
@@ -264,8 +303,9 @@ class EncoderPlan:
         ol = OpList()
         self.ol = ol
         self.n = n
-        self.x0 = torch.zeros(n, h, w, 8, **bf)
+        self.x0 = torch.zeros(n, (h + 1) // 2, (w + 1) // 2, 16, **bf)
         h1, w1 = _out_hw(h, 3, 2), _out_hw(w, 3, 2)
+        assert h1 == (h + 1) // 2 - 1 and w1 == (w + 1) // 2 - 1
         c1a = buf(h1, w1, 32)
         h2, w2 = h1 - 2, w1 - 2
         c2a, c2b = buf(h2, w2, 32), buf(h2, w2, 64)
@@ -275,7 +315,7 @@ class EncoderPlan:
         c4a = buf(h4, w4, 192)
         h5, w5 = _out_hw(h4, 3, 2), _out_hw(w4, 3, 2)
         x35 = buf(h5, w5, 256)
-        ol.conv(P["conv2d_1a"], View(self.x0), View(c1a), stride=2)
+        ol.conv(P["conv2d_1a"], View(self.x0), View(c1a), sv=16)
         ol.conv(P["conv2d_2a"], View(c1a), View(c2a))
         ol.conv(P["conv2d_2b"], View(c2a), View(c2b), pad=(1, 1))
         ol.maxpool(View(c2b), View(mp))

@@ -127,17 +127,19 @@ class InceptionResnetV1(nn.Module):
             self._plans[key] = encoder_plan.EncoderPlan(self._ensure(dev), n, h, w, dev)
         return self._plans[key]
 
-    def embed_nhwc8(self, x_nhwc8):
-        """Device-resident fast path used by the fused pipeline: x 16-bit (n,H,W,8) NHWC -> (emb fp32 (n,512),
-        emb 16-bit (n,512)), both L2-normalised.  Chunked by ``self.chunk``."""
-        n, h, w, _ = x_nhwc8.shape
-        dev = x_nhwc8.device
+    def embed_s2d(self, x_s2d, size):
+        """Device-resident fast path used by the fused pipeline: x 16-bit space-to-depth crops (n, ceil(S/2), ceil(S/2),
+        16) of S x S faces (vnfr_face_crops half_layout 1) -> (emb fp32 (n,512), emb 16-bit (n,512)), both
+        L2-normalised.  Chunked by ``self.chunk``."""
+        n = x_s2d.shape[0]
+        h = w = int(size)
+        dev = x_s2d.device
         emb = torch.empty(n, 512, dtype=torch.float32, device=dev)
-        emb16 = torch.empty(n, 512, dtype=x_nhwc8.dtype, device=dev)
+        emb16 = torch.empty(n, 512, dtype=x_s2d.dtype, device=dev)
         for s in range(0, n, self.chunk):
             m = min(self.chunk, n - s)
             plan = self._plan(m, h, w, dev)
-            plan.x0.copy_(x_nhwc8[s:s + m])
+            plan.x0.copy_(x_s2d[s:s + m])
             plan.run()
             _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(emb[s:s + m]),
                       _lib.ptr(emb16[s:s + m]), encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())
@@ -158,7 +160,7 @@ class InceptionResnetV1(nn.Module):
             for s in range(0, n, self.chunk):
                 m = min(self.chunk, n - s)
                 plan = self._plan(m, h, w, dev)
-                _lib.call("vnfr_nchw3_to_nhwc8", _lib.ptr(x[s:s + m]), m, h, w, _lib.ptr(plan.x0),
+                _lib.call("vnfr_nchw3_to_s2d16", _lib.ptr(x[s:s + m]), m, h, w, _lib.ptr(plan.x0),
                           encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())
                 plan.run()
                 if self.classify:

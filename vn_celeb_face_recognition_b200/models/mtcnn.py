@@ -334,7 +334,8 @@ class MTCNN(nn.Module):
     def face_crops_device(self, ws, mode, image_size, margin=0, template=None, half_dtype=None, max_faces=None,
                           want_u8=True):
         """Faces of the detections in ``ws`` as encoder inputs (see vnfr_face_crops).  Returns (face_u8 (F,S,S,3),
-        face_half (F,S,S,8), face_img (F,), F_capacity) on device; the number of valid faces is ws.out_count.sum()."""
+        face_half (F,ceil(S/2),ceil(S/2),16) -- the space-to-depth layout the encoder's first convolution reads --,
+        face_img (F,), F_capacity) on device; the number of valid faces is ws.out_count.sum()."""
         from .. import encoder_plan
         dt = half_dtype or encoder_plan.HALF
         dev = ws.frames.device
@@ -345,7 +346,7 @@ class MTCNN(nn.Module):
         bufs = getattr(ws, "_face_bufs", {})
         if key not in bufs:
             bufs[key] = (torch.empty(max_faces, S, S, 3, dtype=torch.uint8, device=dev),
-                         torch.empty(max_faces, S, S, 8, dtype=dt, device=dev),
+                         torch.zeros(max_faces, (S + 1) // 2, (S + 1) // 2, 16, dtype=dt, device=dev),
                          torch.empty(max_faces, dtype=torch.int32, device=dev))
             ws._face_bufs = bufs
         u8, half, fimg = bufs[key]
@@ -354,7 +355,7 @@ class MTCNN(nn.Module):
             tmpl = (C.c_float * 10)(*[float(v) for v in np.asarray(template, dtype=np.float32).reshape(-1)])
         _lib.call("vnfr_face_crops", _lib.ptr(ws.frames), ws.B, ws.H, ws.W, capf, _lib.ptr(ws.out_count), _lib.ptr(ws.out_box),
                   _lib.ptr(ws.out_pts), mode, S, margin, tmpl, encoder_plan.dtype_code(dt), max_faces, _lib.ptr(ws.offs),
-                  _lib.ptr(u8 if want_u8 else None), _lib.ptr(half), _lib.ptr(fimg), _lib.ptr(ws.status), _lib.stream_ptr())
+                  _lib.ptr(u8 if want_u8 else None), _lib.ptr(half), _lib.ptr(fimg), _lib.ptr(ws.status), 1, _lib.stream_ptr())
         return (u8 if want_u8 else None), half, fimg, max_faces
 
     # ---- reference API ------------------------------------------------------------------------------------------
@@ -487,7 +488,7 @@ class MTCNN(nn.Module):
             d_cnt, d_box = cnt.to(dev), box.to(dev)        # keep the device copies alive across the launch
             _lib.call("vnfr_face_crops", _lib.ptr(frames), B, H, W, capf, _lib.ptr(d_cnt), _lib.ptr(d_box), None, 0,
                       self.image_size, self.margin, None, encoder_plan.dtype_code(encoder_plan.HALF), total, _lib.ptr(offs),
-                      _lib.ptr(u8), _lib.ptr(half), None, _lib.ptr(status), _lib.stream_ptr())
+                      _lib.ptr(u8), _lib.ptr(half), None, _lib.ptr(status), 0, _lib.stream_ptr())
             faces_f = u8.permute(0, 3, 1, 2).float()                       # F.to_tensor(np.float32(face)), detect_face.py:376
             if self.post_process:
                 faces_f = fixed_image_standardization(faces_f)

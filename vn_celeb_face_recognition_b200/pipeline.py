@@ -87,7 +87,7 @@ class FacePipeline:
                 out.update(emb=torch.zeros(0, 512, device=dev), label=torch.zeros(0, dtype=torch.int64, device=dev),
                            prob=torch.zeros(0, device=dev))
                 return out
-            emb, emb16 = self.enc.embed_nhwc8(half[:F])
+            emb, emb16 = self.enc.embed_s2d(half[:F], self.S)
             mark("encoder")
             out["emb"] = emb
             if self.cls is not None:
