@@ -53,26 +53,71 @@ def build_models(dev, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md recipe): NVML polled every 10 ms from
+    a thread (nvidia-smi -lms cannot deliver a first sample inside a ~100 ms region); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.nvml, self._stop = gpu_index, [], None, None, False
+        self.sm, self.reasons, self.max_sm = [], set(), None
+
+    def _phys_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._phys_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._phys_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        names = [("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(self.h))
+                for name, bit in names:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -82,7 +127,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -223,6 +268,26 @@ def run_ours(args):
     nf_step = faces_e2e // max(1, e2e_steps)
     d2h = (B + 1) * 4 + B * max(1, max(len(r["labels"]) for r in res)) * 5 * 4 + nf_step * (8 + 4 + 512 * 4)
 
+    # ---- second headline figure of BASELINE.json ("embeds/sec"): InceptionResnetV1 + L2-norm + MLP classify on
+    # batch-1024 synthetic 160x160 crops (config 2) through the public forward() API, crops resident on the device
+    embed = None
+    if not args.skip_e2e:
+        torch.manual_seed(1)
+        crops = torch.randn(args.embed_batch, 3, 160, 160, device=dev).clamp_(-1, 1)
+        for _ in range(3):
+            lp = cls(enc(crops))
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            lp = cls(enc(crops))
+        g1.record()
+        torch.cuda.synchronize()
+        ms_emb = g0.elapsed_time(g1) / 5
+        embed = {"value": args.embed_batch / (ms_emb * 1e-3) * world, "unit": "embeds/s", "batch_per_rank": args.embed_batch,
+                 "ms_per_batch": ms_emb, "tflops": args.embed_batch * (ENC_FLOP_PER_FACE + MLP_FLOP_PER_FACE) / (ms_emb * 1e-3) / 1e12,
+                 "note": "InceptionResnetV1.forward + MLPModel.forward on (B,3,160,160) fp32 device tensors"}
+
     # ---- reductions over ranks
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -248,7 +313,8 @@ def run_ours(args):
         if enc_ms > 0:
             flops = faces_step_rank * ENC_FLOP_PER_FACE
             achieved = flops / (enc_ms * 1e-3) / 1e12
-            roof = {"kernel": "igemm_conv_kernel (InceptionResnetV1 stage: all conv launches of one step)", "bound": "tensor",
+            roof = {"kernel": "tcgen05 convolutions (sv_conv_kernel + igemm_conv_kernel): all 106 conv launches of the "
+                              "InceptionResnetV1 stage of one step", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                     "traffic": None, "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
                     "stage_ms": enc_ms, "share_of_step": enc_ms / (ms / args.steps)}
@@ -264,7 +330,7 @@ def run_ours(args):
                 "e2e": {"value": faces_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_np.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps},
                 "gpu_launches": int(launches), "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-                "roofline": roof, "clocks": clocks}
+                "roofline": roof, "clocks": clocks, "embed": embed}
         if world == 1 and not args.no_cpu_baseline:
             enc_sd = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
             mlp_sd = {k: v.detach().float().cpu() for k, v in cls.state_dict().items()}
@@ -293,6 +359,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="1080p frames per rank per step (BASELINE config 3: 64)")
     ap.add_argument("--chunk", type=int, default=1024, help="encoder crops per internal chunk")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded CPU sample")
+    ap.add_argument("--embed-batch", type=int, default=1024, help="crops per rank of the embeds/s measurement (config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")
     args = ap.parse_args()

@@ -113,3 +113,27 @@ def test_pack_layouts_are_permutations():
     got = x.reshape(2, -1) @ packed.double()
     torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-4)
     assert M._pack_pnet({k: v for k, v in __import__("oracle.synth", fromlist=["x"]).mtcnn_state_dicts()["pnet"].items()}).numel() == 6632
+
+
+def test_stem_space_to_depth_repack_is_the_same_convolution():
+    """encoder_plan.pack_stem_s2d: the stride-2 3x3 stem convolution (inception_resnet_v1.py:219) equals a stride-1 2x2
+    convolution over the 16-channel space-to-depth image with the re-indexed weights (host-side packing logic, checked
+    on the CPU for even and odd input sizes)."""
+    from vn_celeb_face_recognition_b200 import encoder_plan as ep
+    torch.manual_seed(0)
+    sd = {"c.conv.weight": torch.randn(32, 3, 3, 3), "c.bn.weight": torch.rand(32) + 0.5, "c.bn.bias": torch.randn(32),
+          "c.bn.running_mean": torch.randn(32), "c.bn.running_var": torch.rand(32) + 0.5}
+    pc = ep.pack_stem_s2d(sd, "c", torch.device("cpu"), dtype=torch.float32)
+    assert (pc.kh, pc.kw, pc.cin, pc.cout) == (2, 2, 16, 32) and tuple(pc.w.shape) == (32, 64)
+    w2 = pc.w.view(32, 2, 2, 16).permute(0, 3, 1, 2)                       # [co][ch][ty][tx]
+    w, s, b = ep.fold_bn(sd, "c")
+    for h, wd in ((20, 24), (19, 23)):
+        x = torch.randn(2, 3, h, wd)
+        ref = torch.nn.functional.conv2d(x, w * s.view(-1, 1, 1, 1), b, stride=2)
+        h2, w2d = (h + 1) // 2, (wd + 1) // 2
+        xp = torch.zeros(2, 4, 2 * h2, 2 * w2d)
+        xp[:, :3, :h, :wd] = x
+        s2d = xp.view(2, 4, h2, 2, w2d, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 16, h2, w2d)   # ch = (sy*2+sx)*4 + c
+        got = torch.nn.functional.conv2d(s2d, w2, pc.bias[:32])
+        assert got.shape == ref.shape
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)

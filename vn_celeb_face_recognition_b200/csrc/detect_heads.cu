@@ -21,20 +21,29 @@ __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : 
 // conv (valid, stride 1) + bias + PReLU on shared-memory activations for output channels [c_begin, c_end).
 //   in  [G][CIN][IH][IW]   out [G][c_end - c_begin][OH][OW] (channel c stored at index c - c_begin)
 //   w   [CIN*KH*KW][COUT] global, k = (ci*KH + ky)*KW + kx
-// Thread item = (4 output channels) x (4 positions p, p+NQ, p+2NQ, p+3NQ): 16 FMA per 4 LDS + one 16-byte weight load.
-template <int CIN, int COUT, int KH, int KW, int IH, int IW, int G>
-__device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
-                                                const float* __restrict__ bias, const float* __restrict__ alpha, int c_begin,
-                                                int c_end) {
-  constexpr int OH = IH - KH + 1, OW = IW - KW + 1, NPOS = G * OH * OW, NQ = (NPOS + 3) / 4;
-  const int ngroups = (c_end - c_begin) >> 2;
-  for (int item = threadIdx.x; item < ngroups * NQ; item += NT) {
-    const int cg = item / NQ, q = item - cg * NQ;
-    const int c0 = c_begin + 4 * cg;
-    int off[4];
-    bool ok[4];
+// Thread item = (CH output channels) x (POS positions p, p+NQ, ..., p+(POS-1)NQ) x (one of KS slices of the input
+// channels): CH*POS FMAs per POS shared-memory loads + CH/4 warp-uniform 16-byte weight loads.  The first version
+// (4 x 4 tiles) was bound by the load/store unit (ncu: LSU wavefronts 82 % of peak, FMA pipe 28 %); 8-channel tiles
+// halve the loads per FMA.  KS > 1 splits the reduction over thread groups for the small late layers (partial sums
+// through `scratch` [KS][out size]), which otherwise leave most of the CTA idle.
+template <int CIN, int COUT, int KH, int KW, int IH, int IW, int G, int CH, int POS, int KS>
+__device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ scratch,
+                                                const float* __restrict__ w, const float* __restrict__ bias,
+                                                const float* __restrict__ alpha, int c_begin, int c_end) {
+  constexpr int OH = IH - KH + 1, OW = IW - KW + 1, NPOS = G * OH * OW, NQ = (NPOS + POS - 1) / POS;
+  constexpr int CI_PER = CIN / KS;
+  static_assert(CIN % KS == 0 && CH % 4 == 0, "bad tiling");
+  const int ngroups = (c_end - c_begin) / CH;
+  const int cn = c_end - c_begin;
+  const int per_slice = ngroups * NQ;
+  for (int item = threadIdx.x; item < KS * per_slice; item += NT) {
+    const int ks = item / per_slice, it2 = item - ks * per_slice;
+    const int cg = it2 / NQ, q = it2 - cg * NQ;
+    const int c0 = c_begin + CH * cg;
+    int off[POS];
+    bool ok[POS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < POS; ++j) {
       const int p = q + j * NQ;
       ok[j] = p < NPOS;
       const int pp = ok[j] ? p : 0;
@@ -42,39 +51,59 @@ __device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, fl
       const int oy = r / OW, ox = r - oy * OW;
       off[j] = (g * CIN * IH + oy) * IW + ox;
     }
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
-    float acc[4][4];
+    float acc[POS][CH];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w; }
+    for (int c4 = 0; c4 < CH / 4; ++c4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ks == 0) b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c4));
+#pragma unroll
+      for (int j = 0; j < POS; ++j) { acc[j][4 * c4] = b4.x; acc[j][4 * c4 + 1] = b4.y; acc[j][4 * c4 + 2] = b4.z; acc[j][4 * c4 + 3] = b4.w; }
+    }
     const float* wp = w + c0;
-#pragma unroll 2
-    for (int ci = 0; ci < CIN; ++ci) {
+    const int ci0 = ks * CI_PER;
+#pragma unroll 1
+    for (int ci = ci0; ci < ci0 + CI_PER; ++ci) {
 #pragma unroll
       for (int ky = 0; ky < KH; ++ky)
 #pragma unroll
         for (int kx = 0; kx < KW; ++kx) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + ((ci * KH + ky) * KW + kx) * COUT));
+          float wv[CH];
+#pragma unroll
+          for (int c4 = 0; c4 < CH / 4; ++c4) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + ((ci * KH + ky) * KW + kx) * COUT) + c4);
+            wv[4 * c4] = w4.x; wv[4 * c4 + 1] = w4.y; wv[4 * c4 + 2] = w4.z; wv[4 * c4 + 3] = w4.w;
+          }
           const int o = (ci * IH + ky) * IW + kx;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < POS; ++j) {
             const float v = in[off[j] + o];
-            acc[j][0] = fmaf(w4.x, v, acc[j][0]);
-            acc[j][1] = fmaf(w4.y, v, acc[j][1]);
-            acc[j][2] = fmaf(w4.z, v, acc[j][2]);
-            acc[j][3] = fmaf(w4.w, v, acc[j][3]);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) acc[j][c] = fmaf(wv[c], v, acc[j][c]);
           }
         }
     }
-    const float4 a4 = __ldg(reinterpret_cast<const float4*>(alpha + c0));
-    const float al[4] = {a4.x, a4.y, a4.z, a4.w};
-    const int cn = c_end - c_begin;
+    float* dst = KS == 1 ? out : scratch + ks * (G * cn * OH * OW);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < POS; ++j) {
       if (!ok[j]) continue;
       const int p = q + j * NQ;
       const int g = p / (OH * OW), r = p - g * (OH * OW);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) out[(g * cn + 4 * cg + c) * (OH * OW) + r] = prelu(acc[j][c], al[c]);
+      for (int c = 0; c < CH; ++c) {
+        const float v = acc[j][c];
+        dst[(g * cn + CH * cg + c) * (OH * OW) + r] = KS == 1 ? prelu(v, __ldg(alpha + c0 + c)) : v;
+      }
+    }
+  }
+  if (KS > 1) {
+    __syncthreads();
+    const int total = G * cn * OH * OW;
+    for (int i = threadIdx.x; i < total; i += NT) {
+      float sum = scratch[i];
+#pragma unroll
+      for (int k = 1; k < KS; ++k) sum += scratch[k * total + i];
+      const int c = (i / (OH * OW)) % cn;
+      out[i] = prelu(sum, __ldg(alpha + c_begin + c));
     }
   }
 }
@@ -248,7 +277,7 @@ __global__ void __launch_bounds__(NT, 1) rnet_kernel(const HeadArgs a) {
     // conv1 3->28 (3x3) + PReLU in slabs of 8 channels -> maxpool 3/2 ceil -> Bf [RG][28][11][11]
     for (int c0 = 0; c0 < 28; c0 += 8) {
       const int c1 = min(28, c0 + 8), cn = c1 - c0;
-      conv_prelu_smem<3, 28, 3, 3, 24, 24, RG>(A, Cf, w + RW::W1, w + RW::B1, w + RW::A1, c0, c1);   // Cf [RG][cn][22][22]
+      conv_prelu_smem<3, 28, 3, 3, 24, 24, RG, 4, 8, 1>(A, Cf, nullptr, w + RW::W1, w + RW::B1, w + RW::A1, c0, c1);   // Cf [RG][cn][22][22]
       __syncthreads();
       for (int g = 0; g < RG; ++g) {
         // pool channel slab of candidate g into its place in Bf
@@ -269,11 +298,11 @@ __global__ void __launch_bounds__(NT, 1) rnet_kernel(const HeadArgs a) {
       }
       __syncthreads();
     }
-    conv_prelu_smem<28, 48, 3, 3, 11, 11, RG>(Bf, Cf, w + RW::W2, w + RW::B2, w + RW::A2, 0, 48);      // Cf [RG][48][9][9]
+    conv_prelu_smem<28, 48, 3, 3, 11, 11, RG, 8, 4, 1>(Bf, Cf, nullptr, w + RW::W2, w + RW::B2, w + RW::A2, 0, 48);      // Cf [RG][48][9][9]
     __syncthreads();
     maxpool_smem<3, 9, 9>(Cf, A, RG * 48);                                                            // A  [RG][48][4][4]
     __syncthreads();
-    conv_prelu_smem<48, 64, 2, 2, 4, 4, RG>(A, Bf, w + RW::W3, w + RW::B3, w + RW::A3, 0, 64);         // Bf [RG][64][3][3] = [RG][576]
+    conv_prelu_smem<48, 64, 2, 2, 4, 4, RG, 4, 3, 2>(A, Bf, Cf, w + RW::W3, w + RW::B3, w + RW::A3, 0, 64);   // Bf [RG][64][3][3] = [RG][576]
     __syncthreads();
     fc_prelu_smem<576, 128, RG>(Bf, A, Cf, w + RW::W4, w + RW::B4, w + RW::A4);                        // A  [RG][128]
     __syncthreads();
@@ -300,60 +329,96 @@ __global__ void __launch_bounds__(NT, 1) rnet_kernel(const HeadArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------- O-Net
-constexpr int O_A = 3 * 48 * 48;             // 6912   input / pool2 out (6400) / pool3 out / fc5 out
-constexpr int O_B = 32 * 23 * 23;            // 16928  pooled conv1 / conv3 out (4096) / conv4 out (1152)
-constexpr int O_C = 64 * 21 * 21;            // 28224  conv1 slab temp (8 ch: 16928) / conv2 out / fc scratch (4096)
-constexpr int O_SMEM = (O_A + O_B + O_C) * 4;
+constexpr int OG = 4;                        // crops whose dense5 + heads run together (dense5's 1.18 MB of weights are
+                                             // then read from L2 once per 4 crops instead of once per crop)
+constexpr int O_A = 3 * 48 * 48;             // 6912   input / pool2 out (6400) / pool3 out / fc5 out [OG][256]
+constexpr int O_B = 32 * 23 * 23;            // 16928  pooled conv1 / conv3 out (4096)
+constexpr int O_C = 64 * 21 * 21;            // 28224  conv1 slab temp (8 ch: 16928) / conv2 out / split-K + fc scratch
+constexpr int O_F = OG * 1152;               // 4608   conv4 outputs of the group = dense5 inputs
+constexpr int O_SMEM = (O_A + O_B + O_C + O_F) * 4;
+
+// optional per-phase cycle counters of CTA 0 (tools/heads_probe.py); null = off
+__device__ long long* g_heads_dbg = nullptr;
+#define HD_MARK(i) do { if (dbg) { const long long t__ = clock64(); dbg[i] += t__ - tlast; tlast = t__; } } while (0)
 
 __global__ void __launch_bounds__(NT, 1) onet_kernel(const HeadArgs a) {
   extern __shared__ __align__(16) float sm[];
-  float* A = sm; float* Bf = sm + O_A; float* Cf = Bf + O_B;
+  long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? g_heads_dbg : nullptr;
+  long long tlast = dbg ? clock64() : 0;
+  float* A = sm; float* Bf = sm + O_A; float* Cf = Bf + O_B; float* F = Cf + O_C;
+  __shared__ int s_b[OG], s_slot[OG], s_empty[OG];
   const int total = a.offs[a.B];
   const float* w = a.w;
-  for (int flat = blockIdx.x; flat < total; flat += gridDim.x) {
-    __shared__ int s_b, s_slot;
-    if (threadIdx.x == 0) { int b, slot; locate(a.offs, a.B, flat, b, slot); s_b = b; s_slot = slot; }
-    __syncthreads();
-    const size_t o = (size_t)s_b * a.cap + s_slot;
-    const int4 pd = a.pad[o];
-    crop_resize_smem<48>(a.frames + (size_t)s_b * a.H * a.W * 3, a.W, pd, A);
-    __syncthreads();
-    if (a.crops_out != nullptr)
-      for (int i = threadIdx.x; i < O_A; i += NT) a.crops_out[(size_t)flat * O_A + i] = A[i];
-    for (int c0 = 0; c0 < 32; c0 += 8) {
-      conv_prelu_smem<3, 32, 3, 3, 48, 48, 1>(A, Cf, w + OW_::W1, w + OW_::B1, w + OW_::A1, c0, c0 + 8);   // Cf [8][46][46]
+  // crop k of this CTA is flat index blockIdx.x + k*gridDim.x (balanced to +-1 crop per CTA)
+  for (int k0 = 0; blockIdx.x + k0 * gridDim.x < total; k0 += OG) {
+    for (int g = 0; g < OG; ++g) {
+      const int flat = blockIdx.x + (k0 + g) * gridDim.x;
+      if (flat >= total) {
+        if (threadIdx.x == 0) s_b[g] = -1;
+        for (int i = threadIdx.x; i < 1152; i += NT) F[g * 1152 + i] = 0.f;
+        continue;                              // uniform across the CTA
+      }
+      if (threadIdx.x == 0) { int b, slot; locate(a.offs, a.B, flat, b, slot); s_b[g] = b; s_slot[g] = slot; }
       __syncthreads();
-      maxpool_smem<3, 46, 46>(Cf, Bf + c0 * 23 * 23, 8);                                                 // Bf [32][23][23]
+      const size_t o = (size_t)s_b[g] * a.cap + s_slot[g];
+      const int4 pd = a.pad[o];
+      if (threadIdx.x == 0) s_empty[g] = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);
+      HD_MARK(0);
+      crop_resize_smem<48>(a.frames + (size_t)s_b[g] * a.H * a.W * 3, a.W, pd, A);
       __syncthreads();
+      HD_MARK(1);
+      if (a.crops_out != nullptr)
+        for (int i = threadIdx.x; i < O_A; i += NT) a.crops_out[(size_t)flat * O_A + i] = A[i];
+      for (int c0 = 0; c0 < 32; c0 += 8) {
+        conv_prelu_smem<3, 32, 3, 3, 48, 48, 1, 8, 5, 1>(A, Cf, nullptr, w + OW_::W1, w + OW_::B1, w + OW_::A1, c0, c0 + 8);   // Cf [8][46][46]
+        __syncthreads();
+        HD_MARK(2);
+        maxpool_smem<3, 46, 46>(Cf, Bf + c0 * 23 * 23, 8);                                               // Bf [32][23][23]
+        __syncthreads();
+        HD_MARK(3);
+      }
+      conv_prelu_smem<32, 64, 3, 3, 23, 23, 1, 8, 7, 1>(Bf, Cf, nullptr, w + OW_::W2, w + OW_::B2, w + OW_::A2, 0, 64);    // Cf [64][21][21]
+      __syncthreads();
+      HD_MARK(4);
+      maxpool_smem<3, 21, 21>(Cf, A, 64);                                                                // A  [64][10][10]
+      __syncthreads();
+      HD_MARK(5);
+      conv_prelu_smem<64, 64, 3, 3, 10, 10, 1, 4, 4, 2>(A, Bf, Cf, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);          // Bf [64][8][8]
+      __syncthreads();
+      HD_MARK(6);
+      maxpool_smem<2, 8, 8>(Bf, A, 64);                                                                  // A  [64][4][4]
+      __syncthreads();
+      HD_MARK(7);
+      conv_prelu_smem<64, 128, 2, 2, 4, 4, 1, 4, 3, 4>(A, F + g * 1152, Cf, w + OW_::W4, w + OW_::B4, w + OW_::A4, 0, 128);  // F[g] [128][3][3]
+      __syncthreads();
+      HD_MARK(8);
     }
-    conv_prelu_smem<32, 64, 3, 3, 23, 23, 1>(Bf, Cf, w + OW_::W2, w + OW_::B2, w + OW_::A2, 0, 64);       // Cf [64][21][21]
     __syncthreads();
-    maxpool_smem<3, 21, 21>(Cf, A, 64);                                                                  // A  [64][10][10]
+    fc_prelu_smem<1152, 256, OG>(F, A, Cf, w + OW_::W5, w + OW_::B5, w + OW_::A5);                        // A  [OG][256]
     __syncthreads();
-    conv_prelu_smem<64, 64, 3, 3, 10, 10, 1>(A, Bf, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);        // Bf [64][8][8]
-    __syncthreads();
-    maxpool_smem<2, 8, 8>(Bf, A, 64);                                                                    // A  [64][4][4]
-    __syncthreads();
-    conv_prelu_smem<64, 128, 2, 2, 4, 4, 1>(A, Bf, w + OW_::W4, w + OW_::B4, w + OW_::A4, 0, 128);        // Bf [128][3][3] = [1152]
-    __syncthreads();
-    fc_prelu_smem<1152, 256, 1>(Bf, A, Cf, w + OW_::W5, w + OW_::B5, w + OW_::A5);                        // A  [256]
-    __syncthreads();
-    if (threadIdx.x < 16) {
-      const int j = threadIdx.x;
-      float s = __ldg(w + OW_::B6 + j);
-      for (int k = 0; k < 256; ++k) s = fmaf(__ldg(w + OW_::W6 + k * 16 + j), A[k], s);
-      Cf[j] = s;
+    HD_MARK(9);
+    if (threadIdx.x < OG * 16) {
+      const int g = threadIdx.x >> 4, j = threadIdx.x & 15;
+      float sacc = __ldg(w + OW_::B6 + j);
+      for (int k = 0; k < 256; ++k) sacc = fmaf(__ldg(w + OW_::W6 + k * 16 + j), A[g * 256 + k], sacc);
+      Cf[threadIdx.x] = sacc;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const float l0 = Cf[0], l1 = Cf[1];
-      const float mx = fmaxf(l0, l1);
-      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
-      const bool empty = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);
-      a.prob[o] = empty ? 0.f : e1 / (e0 + e1);
-      a.reg[o] = make_float4(Cf[2], Cf[3], Cf[4], Cf[5]);
+    if (threadIdx.x < OG * 16) {
+      const int g = threadIdx.x >> 4, j = threadIdx.x & 15;
+      if (s_b[g] >= 0) {
+        const size_t o = (size_t)s_b[g] * a.cap + s_slot[g];
+        const float* h = Cf + g * 16;
+        if (j == 0) {
+          const float l0 = h[0], l1 = h[1];
+          const float mx = fmaxf(l0, l1);
+          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+          a.prob[o] = s_empty[g] ? 0.f : e1 / (e0 + e1);
+          a.reg[o] = make_float4(h[2], h[3], h[4], h[5]);
+        }
+        if (j >= 6) a.lmk[o * 10 + (j - 6)] = h[j];
+      }
     }
-    if (threadIdx.x < 10) a.lmk[o * 10 + threadIdx.x] = Cf[6 + threadIdx.x];
     __syncthreads();
   }
 }
@@ -368,6 +433,11 @@ __global__ void scan_counts_kernel(const int* __restrict__ count, int B, int cap
 }
 
 }  // namespace
+
+extern "C" int vnfr_heads_debug(long long* dev_buf) {      // debug hook (not part of include/vnfr_b200.h)
+  VNFR_CUDA(cudaMemcpyToSymbol(g_heads_dbg, &dev_buf, sizeof(dev_buf)));
+  return VNFR_OK;
+}
 
 extern "C" int vnfr_rnet_weight_floats(void) { return RW::END; }
 extern "C" int vnfr_onet_weight_floats(void) { return OW_::END; }

@@ -41,10 +41,11 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const uint32_t smem_b = smem_a + (uint32_t)S * A_STAGE_BYTES;
   const uint32_t smem_c = smem_b + (uint32_t)S * b_stage_bytes;             // staged C tile: 64-channel panels of 16 KB
   const uint32_t n_panels = p.epi_mode ? (uint32_t)((p.block_n + 63) >> 6) : 0u;
-  const uint32_t smem_bias = smem_c + n_panels * 16384u;                    // 2 x 256 floats
+  const uint32_t c_buf_bytes = n_panels * 16384u;
+  const uint32_t smem_bias = smem_c + (uint32_t)p.c_bufs * c_buf_bytes;     // 2 x 256 floats
   const uint32_t bars = smem_bias + 2048u;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bar_tfull + 16u,
-                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 8u, tmem_slot = bar_cfree + 8u;
+                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 16u, tmem_slot = bar_cfree + 16u;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x;
@@ -63,8 +64,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_init(bar_tfull + 8u * i, 1);
       mbar_init(bar_tempty + 8u * i, NUM_EPILOGUE_THREADS);
     }
-    mbar_init(bar_res, 1);
-    mbar_init(bar_cfree, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_res + 8u * i, 1); mbar_init(bar_cfree + 8u * i, 1); }
     fence_barrier_init();
   }
   if (warp == 16 && lane == 0) {
@@ -164,19 +164,28 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tmem_cols);
       if (p.epi_mode) {
-        // staged: the C panels are free (and hold the residual, if any) once bar_res completes for this tile
-        mbar_wait(bar_res, tcount & 1);
-        epilogue_row_staged<F16>(p, sb, t_row, smem_c, r, n_valid, chalf, p.residual != nullptr);
+        // staged: C buffer `cb` is free (and holds the residual, if any) once its bar_res completes for this tile
+        const int cb = p.c_bufs == 2 ? (tcount & 1) : 0;
+        const uint32_t cph = p.c_bufs == 2 ? (uint32_t)((tcount >> 1) & 1) : (uint32_t)(tcount & 1);
+        const uint32_t smem_cb = smem_c + (uint32_t)cb * c_buf_bytes;
+        mbar_wait(bar_res + 8u * cb, cph);
+        epilogue_row_staged<F16>(p, sb, t_row, smem_cb, r, n_valid, chalf, p.residual != nullptr);
         tc_fence_before();
         mbar_arrive(bar_tempty + 8u * ab);     // accumulator drained: the MMA warp may reuse it
         fence_proxy_async_smem();              // generic-proxy writes of the tile -> visible to the TMA store
         asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");
         if (et == 0) {
           const int m0 = (tile / n_tiles_n) * BLOCK_M;
-          for (int j = 0; j * 64 < n_valid; ++j) tma_store_2d(&tmap_c, smem_c + (uint32_t)j * 16384u, n0 + j * 64, m0);
+          for (int j = 0; j * 64 < n_valid; ++j) tma_store_2d(&tmap_c, smem_cb + (uint32_t)j * 16384u, n0 + j * 64, m0);
           tma_store_commit();
-          tma_store_wait_read();               // the panels have been read: they may be refilled
-          mbar_arrive(bar_cfree);
+          if (p.c_bufs == 2) {
+            // the OTHER buffer's store (previous tile) must have read its panels before they are handed back
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (tcount > 0) mbar_arrive(bar_cfree + 8u * (cb ^ 1));
+          } else {
+            tma_store_wait_read();             // the panels have been read: they may be refilled
+            mbar_arrive(bar_cfree);
+          }
         }
         continue;
       }
@@ -208,14 +217,17 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           // C panels: wait until the previous tile's TMA store has read them, then (re)fill them with this tile's
           // residual.  Issued AFTER the tile's K-block loads so that it never holds up the MMA pipeline; the ring depth
           // gives the load its lead time over the epilogue.
-          mbar_wait(bar_cfree, (uint32_t)((tn & 1) ^ 1));
+          const int cb = p.c_bufs == 2 ? (tn & 1) : 0;
+          const uint32_t cph = p.c_bufs == 2 ? (uint32_t)(((tn >> 1) & 1) ^ 1) : (uint32_t)((tn & 1) ^ 1);
+          const uint32_t smem_cb = smem_c + (uint32_t)cb * c_buf_bytes;
+          mbar_wait(bar_cfree + 8u * cb, cph);
           if (p.residual != nullptr) {
             const int n_valid = min(p.block_n, p.cout - n0);
             const int np = (n_valid + 63) >> 6;
-            mbar_arrive_expect_tx(bar_res, (uint32_t)np * 16384u);
-            for (int j = 0; j < np; ++j) tma_load_2d(smem_c + (uint32_t)j * 16384u, &tmap_r, bar_res, n0 + j * 64, m0);
+            mbar_arrive_expect_tx(bar_res + 8u * cb, (uint32_t)np * 16384u);
+            for (int j = 0; j < np; ++j) tma_load_2d(smem_cb + (uint32_t)j * 16384u, &tmap_r, bar_res + 8u * cb, n0 + j * 64, m0);
           } else {
-            mbar_arrive(bar_res);
+            mbar_arrive(bar_res + 8u * cb);
           }
           ++tn;
         }
@@ -269,7 +281,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 // ------------------------------------------------------------------------------------------------------------ host
 int g_num_sms = 148;
 
-int staging_bytes(int block_n, int epi_mode) { return epi_mode ? ((block_n + 63) / 64) * 16384 : 0; }
+// C staging buffers: two (epilogue of tile t overlaps the residual load of tile t+1 and the store of tile t-1) when at
+// least 3 pipeline stages still fit next to them
+int staging_bufs(int block_n, int epi_mode) {
+  if (!epi_mode) return 0;
+  const int one = ((block_n + 63) / 64) * 16384;
+  const int stage_bytes = A_STAGE_BYTES + block_n * 128;
+  return (220 * 1024 - 2 * one) / stage_bytes >= 3 ? 2 : 1;
+}
+int staging_bytes(int block_n, int epi_mode) { return staging_bufs(block_n, epi_mode) * ((block_n + 63) / 64) * 16384; }
 
 int pick_stages(int block_n, int epi_mode) {
   const int stage_bytes = A_STAGE_BYTES + block_n * 128;
@@ -405,6 +425,7 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   p.dtype = op->dtype;
   p.a_mode = op->a_mode;
   p.epi_mode = op->epi_mode;
+  p.c_bufs = staging_bufs(op->block_n, op->epi_mode);
   p.stages = pick_stages(op->block_n, op->epi_mode);
   int cols = 32;
   while (cols < op->block_n) cols <<= 1;

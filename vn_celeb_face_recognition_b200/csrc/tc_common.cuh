@@ -33,6 +33,7 @@ struct ConvParams {
   int a_mode;  // 0: cp.async gather by warps 0-7, 1: TMA tiled 2-D (1x1 convs), 2: TMA im2col
   int dtype;   // 0 = bf16, 1 = fp16 (both: fp32 accumulation in TMEM)
   int epi_mode;  // 1: shared-memory staged epilogue (TMA residual load, TMA store)
+  int c_bufs;    // staging buffers of the staged epilogue (1 or 2)
 };
 
 // ------------------------------------------------------------------------------------------------------------ PTX
