@@ -136,7 +136,9 @@ __global__ void __launch_bounds__(PYR_THREADS) pyramid_rows_kernel(const __grid_
     float* orow = levels + p.level_off[l] + (size_t)b * 3 * plane + (size_t)oy * lw;
     for (int i = threadIdx.x; i < 3 * lw; i += PYR_THREADS) {
       const int ch = i / lw, ox = i - ch * lw;
-      const int x0 = (int)(((long long)ox * p.W) / lw), x1 = (int)((((long long)ox + 1) * p.W + lw - 1) / lw);
+      // 32-bit unsigned division (ox * W < 2^31 is checked on the host): a 64-bit division costs ~8x as much
+      const int x0 = (int)(((unsigned)ox * (unsigned)p.W) / (unsigned)lw);
+      const int x1 = (int)((((unsigned)ox + 1u) * (unsigned)p.W + (unsigned)lw - 1u) / (unsigned)lw);
       uint32_t s = 0;
       for (int x = x0; x < x1; ++x) s += colsum[3 * x + ch];
       orow[ch * plane + ox] = mul_rn(sub_rn(div_rn(div_rn((float)s, kh), (float)(x1 - x0)), 127.5f), 0.0078125f);
@@ -161,6 +163,7 @@ extern "C" int vnfr_pyramid_resize_norm(const VnfrPyramid* pyr, const uint8_t* f
   const long long n_tasks = (long long)roff * p.B;
   const size_t smem = (size_t)p.W * 3 * sizeof(uint32_t);
   VNFR_REQUIRE(smem <= 200 * 1024, "frame too wide for the pyramid kernel (W*3*4 bytes of shared memory needed)");
+  VNFR_REQUIRE((long long)p.W * p.W < (1ll << 31) && (long long)p.H * p.H < (1ll << 31), "frame too large");
   const bool vec = ((size_t)p.W * 3) % 16 == 0 && ((uintptr_t)frames % 16) == 0;
   const int per_sm = smem > 0 ? (int)((220 * 1024) / (smem + 1024)) : 8;
   long long grid = 148LL * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
