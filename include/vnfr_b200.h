@@ -35,6 +35,8 @@ const char* vnfr_last_error(void);
 int vnfr_version(void);
 /* Number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long vnfr_launch_count(void);
+/* Adds n to the counter: kernels replayed by a CUDA graph captured around vnfr_run_ops. */
+int vnfr_count_launches(long long n);
 
 /* ---- detection: pyramid plan ------------------------------------------------------------------------------------ */
 /* Scale pyramid of detect_face (models/mtcnn_utils/detect_face.py:48-60, :71) and the derived P-Net map geometry

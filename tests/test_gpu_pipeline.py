@@ -265,7 +265,8 @@ def test_host_frame_path_overlapped_copy_equals_device_path(dev, models):
     fr = np.concatenate([synth.frames("small", 3, first_seed=0), synth.frames("small", 2, first_seed=7)])
     det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
     fp = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity")
-    fp.sub_batch = 2                                                    # 5 frames -> sub-batches 2 + 2 + 1
+    fp.sub_batch, fp.first_sub_batch = 2, 1                             # 5 frames -> sub-batches 1 + 2 + 2
+    assert fp._sub_batches(5) == [(0, 1), (1, 3), (3, 5)]
     ref = fp(torch.from_numpy(fr).to(dev))
     pinned = torch.from_numpy(fr).pin_memory()
     for _ in range(2):

@@ -63,6 +63,7 @@ _SIGS = {
     "vnfr_conv_prepare": [C.POINTER(ConvOp)],
     "vnfr_conv_run": [C.POINTER(ConvOp), _P],
     "vnfr_run_ops": [C.POINTER(Op), _I, _P],
+    "vnfr_count_launches": [_LL],
     "vnfr_maxpool3s2_nhwc": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "vnfr_avgpool_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "vnfr_nchw3_to_nhwc8": [_P, _I, _I, _I, _P, _I, _P],

@@ -31,6 +31,9 @@ if os.environ.get("VNFR_NO_SV"):
     SV_DEFAULT = {}
 
 
+USE_GRAPHS = not os.environ.get("VNFR_NO_GRAPH")
+
+
 def dtype_code(dt):
     return 1 if dt == torch.float16 else 0
 
@@ -157,6 +160,7 @@ class OpList:
         self.ops = []
         self.keep = []
         self._arr = None
+        self._graph, self._runs = None, 0
 
     def conv(self, pc, src, dst0, stride=1, pad=(0, 0), relu=True, dst1=None, n_split=None, residual=None, out_f32=None,
              sv=None):
@@ -231,7 +235,22 @@ class OpList:
             return
         if self._arr is None:
             self._arr = (_lib.Op * len(self.ops))(*self.ops)
+            self._graph, self._runs = None, 0
+        if self._graph is not None:
+            self._graph.replay()                        # one launch of the whole op list (no per-kernel launch gaps)
+            _lib.call("vnfr_count_launches", len(self.ops))
+            return
         _lib.call("vnfr_run_ops", self._arr, len(self.ops), _lib.stream_ptr())
+        self._runs += 1
+        if USE_GRAPHS and self._runs == 2 and len(self.ops) >= 8 and not torch.cuda.is_current_stream_capturing():
+            # the list is static (fixed pointers and shapes): capture it into a CUDA graph after two eager runs
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    _lib.call("vnfr_run_ops", self._arr, len(self.ops), _lib.stream_ptr())
+                self._graph = g
+            except Exception:
+                self._graph = None
 
 
 class EncoderWeights:

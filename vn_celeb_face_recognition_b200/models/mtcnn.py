@@ -299,10 +299,10 @@ class MTCNN(nn.Module):
         ws.frames = frames_u8
         return ws
 
-    def detect_device_chunked(self, frames_dev, ready_events, sub):
-        """The cascade over sub-batches of ``sub`` frames of ``frames_dev`` (CUDA u8 (B,H,W,3)); sub-batch i starts as
-        soon as ``ready_events[i]`` (recorded on the copy stream after its H2D) has fired.  Returns a ResultWorkspace
-        with the detections of the whole batch."""
+    def detect_device_chunked(self, frames_dev, ready_events, bounds):
+        """The cascade over the sub-batches ``bounds`` = [(b0, b1), ...] of ``frames_dev`` (CUDA u8 (B,H,W,3)); sub-batch
+        i starts as soon as ``ready_events[i]`` (recorded on the copy stream after its H2D) has fired.  Returns a
+        ResultWorkspace with the detections of the whole batch."""
         B, H, W, _ = frames_dev.shape
         dev = frames_dev.device
         key = ("result", B, H, W, tuple(self.caps), dev)
@@ -311,8 +311,7 @@ class MTCNN(nn.Module):
             full = self._ws[key] = ResultWorkspace(B, H, W, tuple(self.caps), dev)
         full.status.zero_()
         cur = torch.cuda.current_stream(dev)
-        for i, b0 in enumerate(range(0, B, sub)):
-            b1 = min(B, b0 + sub)
+        for i, (b0, b1) in enumerate(bounds):
             if ready_events is not None:
                 cur.wait_event(ready_events[i])
             ws = self.detect_device(frames_dev[b0:b1])

@@ -101,6 +101,17 @@ class FacePipeline:
 
     #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i)
     sub_batch = 16
+    #: the first sub-batch is smaller: nothing can overlap its copy, so it should land quickly
+    first_sub_batch = 4
+
+    def _sub_batches(self, B):
+        bounds, b0 = [], 0
+        first = min(self.first_sub_batch, self.sub_batch)
+        while b0 < B:
+            n = first if b0 == 0 else self.sub_batch
+            bounds.append((b0, min(B, b0 + n)))
+            b0 += n
+        return bounds
 
     def _run_host_frames(self, t, dev):
         """Pinned host frames -> device in sub-batches on a copy stream, the detection cascade of each sub-batch
@@ -115,15 +126,15 @@ class FacePipeline:
         cur = torch.cuda.current_stream(dev)
         cs.wait_stream(cur)                                  # the previous call's kernels are done reading the buffer
         events = []
+        bounds = self._sub_batches(B)
         with torch.cuda.stream(cs):
-            for b0 in range(0, B, self.sub_batch):
-                b1 = min(B, b0 + self.sub_batch)
+            for b0, b1 in bounds:
                 buf[b0:b1].copy_(t[b0:b1], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 events.append(ev)
         with torch.no_grad():
-            ws = self.det.detect_device_chunked(buf, events, self.sub_batch)
+            ws = self.det.detect_device_chunked(buf, events, bounds)
         return self._embed_classify(ws, lambda name: None)
 
     def __call__(self, frames):
