@@ -108,6 +108,119 @@ __device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, fl
   }
 }
 
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Same convolution with the weights STAGED through shared memory: when the CTA owns (almost) all of the SM's shared
+// memory the L1 cache is a few KB, every warp-uniform weight load goes to L2 and the FMAs stall on it (ncu source view
+// of the first version: 36 % of all warp-stall samples were long-scoreboard waits on exactly those loads).  Chunks of
+// CC input channels of [K][COUT] weights (for each of the KS reduction slices) are copied with cp.async into a double
+// buffer `wbuf` [2][KS][CC*KH*KW*COUT] one chunk ahead of the FMAs that read them as 16-byte broadcast LDS.
+template <int CIN, int COUT, int KH, int KW, int IH, int IW, int G, int CH, int POS, int KS, int CC>
+__device__ __forceinline__ void conv_prelu_smem_ws(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ scratch,
+                                                   float* __restrict__ wbuf, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, const float* __restrict__ alpha, int c_begin,
+                                                   int c_end) {
+  constexpr int OH = IH - KH + 1, OW = IW - KW + 1, NPOS = G * OH * OW, NQ = (NPOS + POS - 1) / POS;
+  constexpr int CI_PER = CIN / KS, NCHUNK = CI_PER / CC, CHUNK_F = CC * KH * KW * COUT, BUF_F = KS * CHUNK_F;
+  static_assert(CIN % KS == 0 && CI_PER % CC == 0 && CH % 4 == 0 && CHUNK_F % 4 == 0, "bad tiling");
+  const int ngroups = (c_end - c_begin) / CH;
+  const int cn = c_end - c_begin;
+  const int per_slice = ngroups * NQ;
+  const int n_items = KS * per_slice;
+  auto stage = [&](int chunk, int buf) {
+    // slice ks, chunk -> input channels [ks*CI_PER + chunk*CC, +CC): one contiguous block of CHUNK_F floats
+    for (int i = threadIdx.x; i < BUF_F / 4; i += NT) {
+      const int ks = i / (CHUNK_F / 4), j = i - ks * (CHUNK_F / 4);
+      cp_async16(wbuf + buf * BUF_F + ks * CHUNK_F + 4 * j, w + (size_t)((ks * CI_PER + chunk * CC) * KH * KW) * COUT + 4 * j);
+    }
+    cp_async_commit_group();
+  };
+  for (int base = 0; base < n_items; base += NT) {
+    const int item = base + threadIdx.x;
+    const bool active = item < n_items;
+    const int ks = active ? item / per_slice : 0, it2 = active ? item - ks * per_slice : 0;
+    const int cg = it2 / NQ, q = it2 - cg * NQ;
+    const int c0 = c_begin + CH * cg;
+    int off[POS];
+    bool ok[POS];
+#pragma unroll
+    for (int j = 0; j < POS; ++j) {
+      const int p = q + j * NQ;
+      ok[j] = active && p < NPOS;
+      const int pp = ok[j] ? p : 0;
+      const int g = pp / (OH * OW), r = pp - g * (OH * OW);
+      const int oy = r / OW, ox = r - oy * OW;
+      off[j] = (g * CIN * IH + oy) * IW + ox;
+    }
+    float acc[POS][CH];
+#pragma unroll
+    for (int c4 = 0; c4 < CH / 4; ++c4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ks == 0) b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c4));
+#pragma unroll
+      for (int j = 0; j < POS; ++j) { acc[j][4 * c4] = b4.x; acc[j][4 * c4 + 1] = b4.y; acc[j][4 * c4 + 2] = b4.z; acc[j][4 * c4 + 3] = b4.w; }
+    }
+    stage(0, 0);
+    for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+      const int buf = chunk & 1;
+      if (chunk + 1 < NCHUNK) { stage(chunk + 1, buf ^ 1); cp_async_wait_group<1>(); } else { cp_async_wait_group<0>(); }
+      __syncthreads();                                   // chunk `chunk` is visible to every thread
+      const float* wb = wbuf + buf * BUF_F + ks * CHUNK_F + c0;
+      const int ci0 = ks * CI_PER + chunk * CC;
+#pragma unroll 1
+      for (int cc = 0; cc < CC; ++cc) {
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx) {
+            float wv[CH];
+#pragma unroll
+            for (int c4 = 0; c4 < CH / 4; ++c4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wb + ((cc * KH + ky) * KW + kx) * COUT + 4 * c4);
+              wv[4 * c4] = w4.x; wv[4 * c4 + 1] = w4.y; wv[4 * c4 + 2] = w4.z; wv[4 * c4 + 3] = w4.w;
+            }
+            const int o = ((ci0 + cc) * IH + ky) * IW + kx;
+#pragma unroll
+            for (int j = 0; j < POS; ++j) {
+              const float v = in[off[j] + o];
+#pragma unroll
+              for (int c = 0; c < CH; ++c) acc[j][c] = fmaf(wv[c], v, acc[j][c]);
+            }
+          }
+      }
+      __syncthreads();                                   // everyone is done with `buf` before it is restaged
+    }
+    float* dst = KS == 1 ? out : scratch + ks * (G * cn * OH * OW);
+#pragma unroll
+    for (int j = 0; j < POS; ++j) {
+      if (!ok[j]) continue;
+      const int p = q + j * NQ;
+      const int g = p / (OH * OW), r = p - g * (OH * OW);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const float v = acc[j][c];
+        dst[(g * cn + CH * cg + c) * (OH * OW) + r] = KS == 1 ? prelu(v, __ldg(alpha + c0 + c)) : v;
+      }
+    }
+  }
+  if (KS > 1) {
+    __syncthreads();
+    const int total = G * cn * OH * OW;
+    for (int i = threadIdx.x; i < total; i += NT) {
+      float sum = scratch[i];
+#pragma unroll
+      for (int k = 1; k < KS; ++k) sum += scratch[k * total + i];
+      const int c = (i / (OH * OW)) % cn;
+      out[i] = prelu(sum, __ldg(alpha + c_begin + c));
+    }
+  }
+}
+
 // MaxPool2d(K, stride 2, ceil_mode=True) on [NC][IH][IW] -> [NC][OH][OW]  (windows clipped at the border)
 template <int K, int IH, int IW>
 __device__ __forceinline__ void maxpool_smem(const float* __restrict__ in, float* __restrict__ out, int nc) {
@@ -298,7 +411,7 @@ __global__ void __launch_bounds__(NT, 1) rnet_kernel(const HeadArgs a) {
       }
       __syncthreads();
     }
-    conv_prelu_smem<28, 48, 3, 3, 11, 11, RG, 8, 4, 1>(Bf, Cf, nullptr, w + RW::W2, w + RW::B2, w + RW::A2, 0, 48);      // Cf [RG][48][9][9]
+    conv_prelu_smem_ws<28, 48, 3, 3, 11, 11, RG, 8, 4, 1, 4>(Bf, Cf, nullptr, A, w + RW::W2, w + RW::B2, w + RW::A2, 0, 48);   // Cf [RG][48][9][9]
     __syncthreads();
     maxpool_smem<3, 9, 9>(Cf, A, RG * 48);                                                            // A  [RG][48][4][4]
     __syncthreads();
@@ -370,20 +483,21 @@ __global__ void __launch_bounds__(NT, 1) onet_kernel(const HeadArgs a) {
       if (a.crops_out != nullptr)
         for (int i = threadIdx.x; i < O_A; i += NT) a.crops_out[(size_t)flat * O_A + i] = A[i];
       for (int c0 = 0; c0 < 32; c0 += 8) {
-        conv_prelu_smem<3, 32, 3, 3, 48, 48, 1, 8, 5, 1>(A, Cf, nullptr, w + OW_::W1, w + OW_::B1, w + OW_::A1, c0, c0 + 8);   // Cf [8][46][46]
+        conv_prelu_smem_ws<3, 32, 3, 3, 48, 48, 1, 8, 5, 1, 3>(A, Cf, nullptr, Cf + 8 * 46 * 46, w + OW_::W1, w + OW_::B1, w + OW_::A1, c0, c0 + 8);   // Cf [8][46][46]
         __syncthreads();
         HD_MARK(2);
         maxpool_smem<3, 46, 46>(Cf, Bf + c0 * 23 * 23, 8);                                               // Bf [32][23][23]
         __syncthreads();
         HD_MARK(3);
       }
-      conv_prelu_smem<32, 64, 3, 3, 23, 23, 1, 8, 7, 1>(Bf, Cf, nullptr, w + OW_::W2, w + OW_::B2, w + OW_::A2, 0, 64);    // Cf [64][21][21]
+      // weights staged through A (the crop is no longer needed): 2 x 4 channels x 9 taps x 64 = 2 x 9 216 B
+      conv_prelu_smem_ws<32, 64, 3, 3, 23, 23, 1, 8, 7, 1, 4>(Bf, Cf, nullptr, A, w + OW_::W2, w + OW_::B2, w + OW_::A2, 0, 64);   // Cf [64][21][21]
       __syncthreads();
       HD_MARK(4);
       maxpool_smem<3, 21, 21>(Cf, A, 64);                                                                // A  [64][10][10]
       __syncthreads();
       HD_MARK(5);
-      conv_prelu_smem<64, 64, 3, 3, 10, 10, 1, 4, 4, 2>(A, Bf, Cf, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);          // Bf [64][8][8]
+      conv_prelu_smem_ws<64, 64, 3, 3, 10, 10, 1, 8, 4, 4, 2>(A, Bf, Cf, Cf + 16384, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);  // Bf [64][8][8]
       __syncthreads();
       HD_MARK(6);
       maxpool_smem<2, 8, 8>(Bf, A, 64);                                                                  // A  [64][4][4]
