@@ -86,7 +86,8 @@ int vnfr_nms_segments(int n_segments, int cap, const int32_t* count, const float
 /* Stage-1 tail on the device (detect_face.py:79-104): NMS(0.5) per (image, level), NMS(0.7) per image across levels,
  * regression without +1, rerec, pad.  keep1_count [B*L] / keep1 [B*L][cap1] are scratch.  Outputs per image b:
  * s2_count[b], s2_box[b][i][4] (squared-up float boxes), s2_pad[b][i] = (x, y, ex, ey) int32 (detect_face.py:277-289).
- * status: bit 0/1/2/3/4 set when cap1/cap2/cap3/capf/max_faces overflowed (results are then truncated).             */
+ * status: bit 0/1/2/3/4 set when cap1/cap2/cap3/capf/max_faces overflowed, bit 5 when an R-/O-Net crop workspace
+ * overflowed (results are then truncated).                                                                         */
 int vnfr_stage1_boxes(const VnfrPyramid* pyr_host, int cap1, const int32_t* cand_count, const uint32_t* cand_cell,
                       const float* cand_score, const float* cand_reg, int32_t* keep1_count, int32_t* keep1, int cap2,
                       int32_t* s2_count, float* s2_box, int32_t* s2_pad, int32_t* status, void* stream);
@@ -95,14 +96,17 @@ int vnfr_stage1_boxes(const VnfrPyramid* pyr_host, int cap1, const int32_t* cand
  * normalise, network forward (detect_face.py:108-117, :136-146, :16-23; mtcnn.py:84-99, :138-157).
  * weights: packed fp32 device buffer (vnfr_rnet_weight_floats() / vnfr_onet_weight_floats() floats; layout in
  * csrc/detect_heads.cu, produced by models/mtcnn.py).  prob[b][i] = softmax[:,1], reg[b][i][4], lmk[b][i][10].
- * offs [B+1] is scratch (exclusive scan of counts); crops_out (nullable) receives the resized crops for parity tests.*/
+ * offs [B+1] is scratch (exclusive scan of counts).  crops [crop_cap][3][S][S] fp32 (S = 24 / 48, 16-byte aligned) is the
+ * workspace the crop kernel fills, image-major in candidate order, and the network kernel reads; candidates beyond
+ * crop_cap are dropped and bit 5 of *status is set.                                                                 */
 int vnfr_rnet_weight_floats(void);
 int vnfr_onet_weight_floats(void);
 int vnfr_rnet_forward(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
-                      const float* weights, float* prob, float* reg, int32_t* offs, float* crops_out, void* stream);
+                      const float* weights, float* prob, float* reg, int32_t* offs, float* crops, int crop_cap,
+                      int32_t* status, void* stream);
 int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
-                      const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops_out,
-                      void* stream);
+                      const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops, int crop_cap,
+                      int32_t* status, void* stream);
 
 /* Stage-2 tail (detect_face.py:119-136): score > threshold, NMS(0.7), bbreg, rerec, pad. */
 int vnfr_stage2_boxes(int B, int H, int W, int cap2, const int32_t* s2_count, const float* s2_box, const float* s2_prob,

@@ -112,13 +112,15 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
         crops = torch.full((len(y), 3, size, size), float("nan"), device=dev)
         P = _lib.ptr
         d_cnt, d_pad = cnt.to(dev), pad.to(dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
         if net == "rnet":
             _lib.call("vnfr_rnet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(offs),
-                      P(crops), _lib.stream_ptr())
+                      P(crops), len(y), P(status), _lib.stream_ptr())
         else:
             _lib.call("vnfr_onet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(lmk),
-                      P(offs), P(crops), _lib.stream_ptr())
+                      P(offs), P(crops), len(y), P(status), _lib.stream_ptr())
         torch.cuda.synchronize()
+        assert status.item() == 0
         ref_in = taps[key_in][order]
         assert torch.equal(crops.cpu(), ref_in), "%s crops differ: %g" % (net, (crops.cpu() - ref_in).abs().max())
         outs = taps[key_out]

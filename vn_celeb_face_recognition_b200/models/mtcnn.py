@@ -160,6 +160,12 @@ class DetectWorkspace:
         self.s3_reg = torch.empty(B * cap3 * 4, **f32)
         self.s3_lmk = torch.empty(B * cap3 * 10, **f32)
         self.offs = torch.zeros(B + 1, **i32)
+        # crop workspaces of the R-Net / O-Net stages (fp32 [n][3][S][S]); sized for CROP_WS_PER_FRAME candidates per frame
+        # on average (overflow raises through the status word, like the caps)
+        self.rcrop_cap = max(1, min(B * cap2, max(2048, B * MTCNN.crop_ws_per_frame[0])))
+        self.ocrop_cap = max(1, min(B * cap3, max(512, B * MTCNN.crop_ws_per_frame[1])))
+        self.rcrops = torch.empty(self.rcrop_cap * 3 * 24 * 24, **f32)
+        self.ocrops = torch.empty(self.ocrop_cap * 3 * 48 * 48, **f32)
         self.out_box = torch.zeros(B, capf, 5, **f32)
         self.out_pts = torch.zeros(B, capf, 10, **f32)
 
@@ -186,6 +192,8 @@ class MTCNN(nn.Module):
     #: per-stage capacities (candidates per (image, level) / boxes per image into R-Net / into O-Net / faces per image).
     #: Exceeding one raises (results would otherwise be truncated); raise the cap and call again.
     caps = (4096, 4096, 2048, 256)
+    #: average R-Net / O-Net candidates per frame the crop workspaces are sized for (6.9 KB / 27.6 KB per crop)
+    crop_ws_per_frame = (2048, 512)
 
     def __init__(self, image_size=160, margin=0, min_face_size=20, thresholds=[0.6, 0.7, 0.7], factor=0.709,
                  post_process=True, select_largest=True, selection_method=None, keep_all=False, device=None):
@@ -285,13 +293,13 @@ class MTCNN(nn.Module):
                   P(ws.status), st)
         mark("stage1_nms")
         _lib.call("vnfr_rnet_forward", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
-                  P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), None, st)
+                  P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), P(ws.rcrops), ws.rcrop_cap, P(ws.status), st)
         mark("rnet")
         _lib.call("vnfr_stage2_boxes", B, H, W, cap2, P(ws.s2_count), P(ws.s2_box), P(ws.s2_prob), P(ws.s2_reg), t1, cap3,
                   P(ws.s3_count), P(ws.s3_box), P(ws.s3_pad), P(ws.status), st)
         mark("stage2_nms")
         _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
-                  P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), None, st)
+                  P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), ws.ocrop_cap, P(ws.status), st)
         mark("onet")
         _lib.call("vnfr_stage3_faces", B, cap3, P(ws.s3_count), P(ws.s3_box), P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), t2,
                   1 if sl else 0, capf, P(ws.out_count), P(ws.out_box), P(ws.out_pts), P(ws.status), st)
@@ -326,7 +334,8 @@ class MTCNN(nn.Module):
     def check_status(status):
         if status:
             names = ["cap1 (P-Net candidates per image/level)", "cap2 (boxes per image into R-Net)",
-                     "cap3 (boxes per image into O-Net)", "capf (faces per image)", "max_faces"]
+                     "cap3 (boxes per image into O-Net)", "capf (faces per image)", "max_faces",
+                     "crop workspace (MTCNN.crop_ws_per_frame)"]
             over = [n for i, n in enumerate(names) if status & (1 << i)]
             raise _lib.VnfrError("detection capacity exceeded: %s -- raise MTCNN.caps" % ", ".join(over))
 
