@@ -7,7 +7,7 @@
 using namespace tc;
 void vnfr_set_error(const char*, int, const char*) {}
 
-__global__ void __launch_bounds__(128, 1) k(int n, int nacc, int iters, int kind_tf32, long long* out) {
+__global__ void __launch_bounds__(128, 1) k(int n, int nacc, int iters, int kind_tf32, int row_bytes, int shift_rows, long long* out) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   const uint32_t sa = base, sb = base + 16384u, bar = sb + 32768u, slot = bar + 8u;
@@ -23,14 +23,16 @@ __global__ void __launch_bounds__(128, 1) k(int n, int nacc, int iters, int kind
   if (threadIdx.x < 32) {
     uint32_t idesc = make_idesc_f16(n, 1);
     if (kind_tf32) idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint64_t a0 = make_sw128_desc(sa), b0 = make_sw128_desc(sb);
+    const uint64_t a0 = make_sw_desc(sa + (uint32_t)(shift_rows * row_bytes), row_bytes, 0), b0 = make_sw_desc(sb, row_bytes, 0);
+    const int kmax = row_bytes / 32;
     const int stride = n < 32 ? 32 : n;
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
+        for (int kk4 = 0; kk4 < 4; ++kk4)
           for (int u = 0; u < nacc; ++u) {
+            const int kk = kk4 % kmax;
             if (kind_tf32)
               asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                            ::"r"(tmem + (uint32_t)(u * stride)), "l"(a0 + (uint64_t)(2 * kk)), "l"(b0 + (uint64_t)(2 * kk)), "r"(idesc), "r"(1u) : "memory");
@@ -57,16 +59,18 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
   const int iters = 2000;
-  for (int tf = 0; tf < 2; ++tf)
-    for (int grid : {1, 148})
-      for (int n : {32, 64, 128, 256})
-        for (int nacc : {1, 2, 4, 8}) {
+  for (int tf = 0; tf < 1; ++tf)
+    for (int rb : {128, 64, 32})
+     for (int shift : {0, 1, 3, 8})
+      for (int n : {32, 64, 128})
+        for (int nacc : {1, 4}) {
+          const int grid = 148;
           if (nacc * (n < 32 ? 32 : n) > 512) continue;
-          k<<<grid, 128, 60000>>>(n, nacc, iters, tf, d);
+          k<<<grid, 128, 60000>>>(n, nacc, iters, tf, rb, shift, d);
           long long c = 0;
           cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
           if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-          printf("%s grid %3d N %3d accumulators %d : %.1f cycles / mma\n", tf ? "tf32" : "f16 ", grid, n, nacc, (double)c / (iters * 4.0 * nacc));
+          printf("row %3d B shift %d rows N %3d accumulators %d : %.1f cycles / mma\n", rb, shift, n, nacc, (double)c / (iters * 4.0 * nacc));
         }
   return 0;
 }

@@ -215,28 +215,45 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         }
         SV_ACC(2, m1);
         tc_fence_after();
-        for (int ks = 0; ks < q.ksteps; ++ks) {
-          uint64_t b_desc;
-          if (q.b_resident) {
-            b_desc = b_desc0 + (uint64_t)((uint32_t)ks * b_tile16);
-          } else {
+        if (q.b_resident) {
+          // resident weights: nothing to wait for inside the K loop, so the whole loop runs inside ONE elected region
+          // (an elect + __syncwarp per K step costs more than the 2-4 MMAs it guards).  Issue order: for every K slice
+          // rotate over the group's accumulators (independent instructions back to back).
+          if (elect_one()) {
+            if (nt == 4) {
+              for (int ks = 0; ks < q.ksteps; ++ks) {
+                const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)ks * b_tile16);
+                const uint64_t ko = (uint64_t)q.koff[ks];
+#pragma unroll
+                for (int kk = 0; kk < MPS; ++kk) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
+                }
+              }
+            } else {
+              for (int ks = 0; ks < q.ksteps; ++ks) {
+                const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)ks * b_tile16);
+                const uint64_t ko = (uint64_t)q.koff[ks];
+#pragma unroll
+                for (int kk = 0; kk < MPS; ++kk) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (u < nt) umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
+                }
+              }
+            }
+          }
+          __syncwarp();
+        } else {
+          for (int ks = 0; ks < q.ksteps; ++ks) {
             const long long m2 = SV_T0();
             mbar_wait(bar_full + 8u * s, ph);
             SV_ACC(3, m2);
             tc_fence_after();
-            b_desc = b_desc0 + (uint64_t)((uint32_t)s * b_tile16);
-          }
-          const uint64_t ko = (uint64_t)q.koff[ks];
-          if (elect_one()) {
-            if (q.b_resident) {
-              // small N: rotate over the accumulators inside every K slice (independent instructions back to back)
-#pragma unroll
-              for (int kk = 0; kk < MPS; ++kk) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  if (u < nt) umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
-              }
-            } else {
+            const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)s * b_tile16);
+            const uint64_t ko = (uint64_t)q.koff[ks];
+            if (elect_one()) {
               // N = 128 (streamed weights): accumulator-major order measured faster (29.7 vs 37.0 us on Block17 1x7)
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -248,9 +265,9 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
               }
               umma_commit(bar_empty + 8u * s);
             }
+            __syncwarp();
+            if (++s == q.stages) { s = 0; ph ^= 1u; }
           }
-          __syncwarp();
-          if (!q.b_resident) { if (++s == q.stages) { s = 0; ph ^= 1u; } }
         }
         if (elect_one()) {
           int abc = ab;
