@@ -17,6 +17,19 @@ constexpr int NT = 512;   // threads per CTA
 
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 
+// Packed fp32 pair arithmetic of sm_100 (FFMA2): two IEEE fp32 FMAs per lane in ONE issue slot.  The convolutions here
+// are issue-bound (FMA + shared-memory loads + address arithmetic compete for the scheduler), so halving the FMA
+// instruction count raises the FMA pipe utilisation; results are bit-identical to scalar fmaf.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2f(float lo, float hi) {
+  return (f32x2)__float_as_uint(lo) | ((f32x2)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo2f(f32x2 v) { return __uint_as_float((unsigned)(v & 0xFFFFFFFFull)); }
+__device__ __forceinline__ float hi2f(f32x2 v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ void fma2(f32x2& acc, f32x2 a, f32x2 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // conv (valid, stride 1) + bias + PReLU on shared-memory activations for output channels [c_begin, c_end).
 //   in  [G][CIN][IH][IW]   out [G][c_end - c_begin][OH][OW] (channel c stored at index c - c_begin)
@@ -157,13 +170,13 @@ __device__ __forceinline__ void conv_prelu_smem_ws(const float* __restrict__ in,
       const int oy = r / OW, ox = r - oy * OW;
       off[j] = (g * CIN * IH + oy) * IW + ox;
     }
-    float acc[POS][CH];
+    f32x2 acc[POS][CH / 2];                              // channel pairs (c, c+1)
 #pragma unroll
     for (int c4 = 0; c4 < CH / 4; ++c4) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ks == 0) b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c4));
 #pragma unroll
-      for (int j = 0; j < POS; ++j) { acc[j][4 * c4] = b4.x; acc[j][4 * c4 + 1] = b4.y; acc[j][4 * c4 + 2] = b4.z; acc[j][4 * c4 + 3] = b4.w; }
+      for (int j = 0; j < POS; ++j) { acc[j][2 * c4] = pack2f(b4.x, b4.y); acc[j][2 * c4 + 1] = pack2f(b4.z, b4.w); }
     }
     stage(0, 0);
     for (int chunk = 0; chunk < NCHUNK; ++chunk) {
@@ -178,18 +191,19 @@ __device__ __forceinline__ void conv_prelu_smem_ws(const float* __restrict__ in,
         for (int ky = 0; ky < KH; ++ky)
 #pragma unroll
           for (int kx = 0; kx < KW; ++kx) {
-            float wv[CH];
+            f32x2 wv[CH / 2];
 #pragma unroll
             for (int c4 = 0; c4 < CH / 4; ++c4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wb + ((cc * KH + ky) * KW + kx) * COUT + 4 * c4);
-              wv[4 * c4] = w4.x; wv[4 * c4 + 1] = w4.y; wv[4 * c4 + 2] = w4.z; wv[4 * c4 + 3] = w4.w;
+              const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wb + ((cc * KH + ky) * KW + kx) * COUT + 4 * c4);
+              wv[2 * c4] = w4.x; wv[2 * c4 + 1] = w4.y;
             }
             const int o = ((ci0 + cc) * IH + ky) * IW + kx;
 #pragma unroll
             for (int j = 0; j < POS; ++j) {
               const float v = in[off[j] + o];
+              const f32x2 vv = pack2f(v, v);
 #pragma unroll
-              for (int c = 0; c < CH; ++c) acc[j][c] = fmaf(wv[c], v, acc[j][c]);
+              for (int c = 0; c < CH / 2; ++c) fma2(acc[j][c], wv[c], vv);
             }
           }
       }
@@ -203,7 +217,7 @@ __device__ __forceinline__ void conv_prelu_smem_ws(const float* __restrict__ in,
       const int g = p / (OH * OW), r = p - g * (OH * OW);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const float v = acc[j][c];
+        const float v = (c & 1) ? hi2f(acc[j][c >> 1]) : lo2f(acc[j][c >> 1]);
         dst[(g * cn + CH * cg + c) * (OH * OW) + r] = KS == 1 ? prelu(v, __ldg(alpha + c0 + c)) : v;
       }
     }
