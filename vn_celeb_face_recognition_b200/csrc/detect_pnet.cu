@@ -25,7 +25,7 @@ constexpr int C2T = T + 2;            // conv2 tile edge (18)
 constexpr int IT = 2 * PT + 2;        // input tile edge (42)
 constexpr int ITP = IT + 1;           // padded row pitch
 #ifndef PNET_MIN_CTAS
-#define PNET_MIN_CTAS 3
+#define PNET_MIN_CTAS 2
 #endif
 constexpr int NTHR = 128;             // threads per CTA: conv3 phase = 2 cells x 32 channels per thread
 
