@@ -348,8 +348,8 @@ struct HeadArgs {
 // taken by activations) cannot offer -- inside rnet_kernel this phase was 31 % of the time (profiles/).  One CTA per
 // crop at a time, one thread per output pixel; arithmetic identical to the reference's (exact integer sums).
 //
-// Mapping: one CTA per crop, one thread per output pixel (adjacent lanes read adjacent windows, so a warp-level load
-// covers a contiguous span of the frame row).  Measured alternatives that were SLOWER on the 1080p workload: a row-task
+// Mapping: one thread per output pixel over the flat (crop, pixel) index space (adjacent lanes read adjacent windows,
+// so a warp-level load covers a contiguous span of the frame row).  Measured alternatives that were SLOWER on the 1080p workload: a row-task
 // scheme with packed column sums and two barriers per output row (562 us vs 354 us per 3.5 k R-Net crops) and a
 // warp-per-output-pixel scheme for large boxes (1 072 us).
 constexpr int CROP_THREADS = 256;
@@ -359,25 +359,25 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_kernel(const HeadArgs a) {
   const int total_raw = a.offs[a.B];
   if (total_raw > a.crop_cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.status, 32);
   const int total = min(total_raw, a.crop_cap);
-  __shared__ int s_b, s_slot;
-  for (int flat = blockIdx.x; flat < total; flat += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x == 0) { int b, slot; locate(a.offs, a.B, flat, b, slot); s_b = b; s_slot = slot; }
-    __syncthreads();
-    const int4 pad = a.pad[(size_t)s_b * a.cap + s_slot];
-    const uint8_t* frame = a.frames + (size_t)s_b * a.H * a.W * 3;
+  // flat (crop, output pixel) index space: every thread slot is used whatever the crop count, no barriers
+  const long long n_out = (long long)total * (S * S);
+  for (long long idx = blockIdx.x * (long long)CROP_THREADS + threadIdx.x; idx < n_out; idx += (long long)gridDim.x * CROP_THREADS) {
+    const int flat = (int)(idx / (S * S));
+    const int i = (int)(idx - (long long)flat * (S * S));
+    int b, slot;
+    locate(a.offs, a.B, flat, b, slot);
+    const int4 pad = __ldg(a.pad + (size_t)b * a.cap + slot);
+    const uint8_t* frame = a.frames + (size_t)b * a.H * a.W * 3;
     float* dst = a.crops + (size_t)flat * 3 * S * S;
     const int x0 = pad.x - 1, y0 = pad.y - 1;
     const int cw = pad.z - x0, ch = pad.w - y0;
-    if (!(cw > 0 && ch > 0)) {                            // detect_face.py:110 skips empty boxes: the crop stays zero
-      for (int i = threadIdx.x; i < 3 * S * S; i += CROP_THREADS) dst[i] = 0.f;
-      continue;
-    }
-    for (int i = threadIdx.x; i < S * S; i += CROP_THREADS) {
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;                   // detect_face.py:110 skips empty boxes: the crop stays zero
+    if (cw > 0 && ch > 0) {
       const int oy = i / S, ox = i - oy * S;
       const int ys = (oy * ch) / S, ye = ((oy + 1) * ch + S - 1) / S;
       const int xs = (ox * cw) / S, xe = ((ox + 1) * cw + S - 1) / S;
       unsigned s0 = 0, s1 = 0, s2 = 0;
+      // (aligned 4-byte loads with rotating channel accumulators were measured at parity with these byte loads)
       for (int y = ys; y < ye; ++y) {
         const uint8_t* row = frame + ((size_t)(y0 + y) * a.W + (x0 + xs)) * 3;
         for (int x = 0; x < xe - xs; ++x) {
@@ -385,10 +385,11 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_kernel(const HeadArgs a) {
         }
       }
       const float kh = (float)(ye - ys), kw = (float)(xe - xs);
-      dst[i] = mul_rn(sub_rn(div_rn(div_rn((float)s0, kh), kw), 127.5f), 0.0078125f);
-      dst[S * S + i] = mul_rn(sub_rn(div_rn(div_rn((float)s1, kh), kw), 127.5f), 0.0078125f);
-      dst[2 * S * S + i] = mul_rn(sub_rn(div_rn(div_rn((float)s2, kh), kw), 127.5f), 0.0078125f);
+      r0 = mul_rn(sub_rn(div_rn(div_rn((float)s0, kh), kw), 127.5f), 0.0078125f);
+      r1 = mul_rn(sub_rn(div_rn(div_rn((float)s1, kh), kw), 127.5f), 0.0078125f);
+      r2 = mul_rn(sub_rn(div_rn(div_rn((float)s2, kh), kw), 127.5f), 0.0078125f);
     }
+    dst[i] = r0; dst[S * S + i] = r1; dst[2 * S * S + i] = r2;
   }
 }
 
