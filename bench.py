@@ -288,6 +288,30 @@ def run_ours(args):
                  "ms_per_batch": ms_emb, "tflops": args.embed_batch * (ENC_FLOP_PER_FACE + MLP_FLOP_PER_FACE) / (ms_emb * 1e-3) / 1e12,
                  "note": "InceptionResnetV1.forward + MLPModel.forward on (B,3,160,160) fp32 device tensors"}
 
+    # ---- config 5 figure: cosine top-5 of a batch of embeddings against this rank's gallery shard (+ NCCL merge)
+    topk = None
+    if not args.skip_e2e and args.gallery_rows > 0:
+        from vn_celeb_face_recognition_b200 import gallery
+        gen = torch.Generator(device=dev).manual_seed(2 + rank)
+        gshard = gallery.GalleryShard(torch.nn.functional.normalize(torch.randn(args.gallery_rows, 512, device=dev, generator=gen), dim=1),
+                                      index_offset=rank * args.gallery_rows)
+        qs = torch.nn.functional.normalize(torch.randn(args.gallery_queries, 512, device=dev, generator=gen), dim=1)
+        for _ in range(2):
+            tv, ti = gallery.merge_topk(*gshard.topk(qs, 5))
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(3):
+            tv, ti = gallery.merge_topk(*gshard.topk(qs, 5))
+        k1.record()
+        torch.cuda.synchronize()
+        ms_k = k0.elapsed_time(k1) / 3
+        topk = {"queries_per_s": args.gallery_queries / (ms_k * 1e-3), "queries": args.gallery_queries,
+                "gallery_rows_total": args.gallery_rows * world, "k": 5, "ms": ms_k,
+                "tflops": 2.0 * args.gallery_queries * args.gallery_rows * 512 / (ms_k * 1e-3) / 1e12,
+                "note": "every rank scores the same queries against its gallery shard, then all_gather + merge"}
+        del gshard
+
     # ---- reductions over ranks
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -330,7 +354,7 @@ def run_ours(args):
                 "e2e": {"value": faces_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_np.nbytes),
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps},
                 "gpu_launches": int(launches), "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-                "roofline": roof, "clocks": clocks, "embed": embed}
+                "roofline": roof, "clocks": clocks, "embed": embed, "gallery_topk": topk}
         if world == 1 and not args.no_cpu_baseline:
             enc_sd = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
             mlp_sd = {k: v.detach().float().cpu() for k, v in cls.state_dict().items()}
@@ -359,6 +383,8 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="1080p frames per rank per step (BASELINE config 3: 64)")
     ap.add_argument("--chunk", type=int, default=1024, help="encoder crops per internal chunk")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded CPU sample")
+    ap.add_argument("--gallery-rows", type=int, default=131072, help="gallery rows per rank of the cosine top-5 figure (config 5); 0 = skip")
+    ap.add_argument("--gallery-queries", type=int, default=8192)
     ap.add_argument("--embed-batch", type=int, default=1024, help="crops per rank of the embeds/s measurement (config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")

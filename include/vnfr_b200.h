@@ -191,7 +191,13 @@ int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void
  * logits fp32 [n][pitch] (first c valid) -> logp fp32 [n][c] (nullable), label int64 [n], prob fp32 [n].           */
 int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* logp, int64_t* label, float* prob,
                            void* stream);
-/* Adds a per-column fp32 bias and applies ReLU then converts fp32 -> bf16 (helper for tests). */
+/* Row-wise top-k (k <= 8; largest first, ties towards the lower index) of scores fp32 [n][pitch] (first g columns valid):
+ * out_val [n][k], out_idx [n][k] = col_offset + column.  accumulate != 0 merges with the values already in out_val /
+ * out_idx (tile-by-tile search of a gallery larger than one score buffer).  The scores are cosine similarities produced
+ * by vnfr_conv_run (queries as a [n][1][1][512] activation, a gallery tile as the [g][512] "weights"): the north star's
+ * cosine top-k against a gallery shard (BASELINE.json config 5; the reference itself has no gallery search). */
+int vnfr_topk_rows(const float* scores, int n, int g, int pitch, int k, int col_offset, int accumulate, float* out_val,
+                   int32_t* out_idx, void* stream);
 
 #ifdef __cplusplus
 }

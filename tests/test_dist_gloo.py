@@ -63,3 +63,37 @@ def test_shard_range_partitions_all_items():
             spans = [vdist.shard_range(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _topk_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vn_celeb_face_recognition_b200 import gallery
+    g = torch.Generator().manual_seed(0)
+    scores = torch.randn(6, 40, generator=g)                     # queries x global gallery rows (same on every rank)
+    scores[0, 3] = scores[0, 27] = 9.0                            # a tie across shards: the lower global index must win
+    lo, hi = rank * 20, (rank + 1) * 20                           # this rank's gallery shard
+    v, i = torch.topk(scores[:, lo:hi], 5, dim=1)
+    mv, mi = gallery.merge_topk(v, i + lo, k=5)
+    if rank == 0:
+        out.put((scores.numpy(), mv.numpy(), mi.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_gallery_topk_merge():
+    """merge_topk: per-shard top-5 lists all-gathered over 2 ranks equal the top-5 of the unsharded score matrix."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_topk_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    scores, mv, mi = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    rv, ri = torch.topk(torch.from_numpy(scores), 5, dim=1)
+    np.testing.assert_allclose(mv, rv.numpy())
+    assert mi[0, :2].tolist() == [3, 27]
+    np.testing.assert_array_equal(np.sort(mi, axis=1), np.sort(ri.numpy(), axis=1))

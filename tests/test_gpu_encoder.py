@@ -219,3 +219,34 @@ def test_encoder_and_mlp_match_oracle_and_golden(dev, dt, min_cos, margin_thr):
         e112 = enc(x112.to(dev)).cpu()
     cos112 = torch.nn.functional.cosine_similarity(e112, torch.from_numpy(g["emb112"]), dim=1)
     assert cos112.min().item() >= min_cos
+
+
+def test_gallery_topk_matches_torch(dev):
+    """Cosine top-5 against a gallery shard (config 5): tcgen05 score GEMM + running row-wise top-k over gallery tiles vs
+    torch.topk(E @ G^T) in fp32.  Operands are 16-bit, so near-ties may swap: every returned row must be (re-scored in
+    fp32) within 2e-3 of the true k-th best, values must match the fp32 scores of the returned rows, and well-separated
+    matches (planted duplicates) must be found exactly with global indices."""
+    from vn_celeb_face_recognition_b200 import gallery
+    g = torch.Generator(device="cpu").manual_seed(0)
+    G = torch.nn.functional.normalize(torch.randn(3000, 512, generator=g), dim=1)
+    Q = torch.nn.functional.normalize(torch.randn(70, 512, generator=g), dim=1)
+    Q[:10] = torch.nn.functional.normalize(G[100:110] + 0.05 * torch.randn(10, 512, generator=g), dim=1)   # planted matches
+    shard = gallery.GalleryShard(G.to(dev), index_offset=5000)
+    shard.tile = 1024                                              # 3 gallery tiles -> exercises the accumulate path
+    vals, idx = shard.topk(Q.to(dev), k=5)
+    torch.cuda.synchronize()
+    ref = Q @ G.t()
+    rv, ri = torch.topk(ref, 5, dim=1)
+    idx, vals = idx.cpu(), vals.cpu()
+    assert idx.shape == (70, 5) and (idx >= 5000).all() and (idx < 8000).all()
+    assert (idx[:10, 0] == torch.arange(100, 110) + 5000).all()
+    rescored = torch.gather(ref, 1, idx - 5000)
+    assert (rescored >= rv[:, 4:5] - 2e-3).all()
+    assert (vals - rescored).abs().max() < 2e-3
+    assert (vals[:, :-1] >= vals[:, 1:]).all()
+    for r in range(70):
+        assert len(set(idx[r].tolist())) == 5
+    # fewer gallery rows than k: missing entries are -1 / -inf
+    small = gallery.GalleryShard(G[:3].to(dev))
+    v2, i2 = small.topk(Q[:4].to(dev), k=5)
+    assert (i2[:, 3:] == -1).all() and torch.isinf(v2[:, 3:]).all() and (i2[:, :3] >= 0).all()

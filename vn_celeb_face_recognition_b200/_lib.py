@@ -70,6 +70,7 @@ _SIGS = {
     "vnfr_nchw3_to_s2d16": [_P, _I, _I, _I, _P, _I, _P],
     "vnfr_l2norm_rows": [_P, _I, _I, _I, _P, _P, _I, _P],
     "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "vnfr_topk_rows": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
 }
 
 

@@ -188,6 +188,67 @@ __global__ void logsoftmax_argmax_kernel(const float* __restrict__ logits, int n
   }
 }
 
+// Row-wise top-k (k <= 8) of a score matrix, largest first, ties towards the lower index.  One CTA per row: every thread
+// keeps a sorted local list over its strided columns, then k rounds of a block-wide arg-max pop the global winners.
+// With `accumulate` the row's previous (out_val, out_idx) entries are candidates too, so a gallery larger than one score
+// buffer is searched tile by tile.
+constexpr int TOPK_MAX = 8, TOPK_THREADS = 256;
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __restrict__ scores, int g, int pitch, int k,
+                                                                 int col_offset, int accumulate, float* __restrict__ out_val,
+                                                                 int* __restrict__ out_idx) {
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = scores + (size_t)row * pitch;
+  float v[TOPK_MAX];
+  int ix[TOPK_MAX];
+#pragma unroll
+  for (int j = 0; j < TOPK_MAX; ++j) { v[j] = -CUDART_INF_F; ix[j] = 0x7fffffff; }
+  auto insert = [&](float x, int i) {
+    // sorted insert (value descending, index ascending)
+    if (x > v[TOPK_MAX - 1] || (x == v[TOPK_MAX - 1] && i < ix[TOPK_MAX - 1])) {
+      v[TOPK_MAX - 1] = x; ix[TOPK_MAX - 1] = i;
+#pragma unroll
+      for (int j = TOPK_MAX - 1; j > 0; --j) {
+        const bool sw = v[j] > v[j - 1] || (v[j] == v[j - 1] && ix[j] < ix[j - 1]);
+        if (sw) { const float tv = v[j]; v[j] = v[j - 1]; v[j - 1] = tv; const int ti = ix[j]; ix[j] = ix[j - 1]; ix[j - 1] = ti; }
+      }
+    }
+  };
+  for (int i = tid; i < g; i += TOPK_THREADS) insert(xr[i], col_offset + i);
+  if (accumulate && tid < k) insert(out_val[(size_t)row * k + tid], out_idx[(size_t)row * k + tid]);
+  __shared__ float s_v[TOPK_THREADS / 32];
+  __shared__ int s_i[TOPK_THREADS / 32], s_owner[TOPK_THREADS / 32];
+  __shared__ int s_win_owner;
+  for (int r = 0; r < k; ++r) {
+    // every thread proposes the head of its list
+    float bv = v[0];
+    int bi = ix[0], bo = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o), oo = __shfl_xor_sync(0xffffffffu, bo, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; bo = oo; }
+    }
+    if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; s_owner[warp] = bo; }
+    __syncthreads();
+    if (tid == 0) {
+      float wv = s_v[0]; int wi = s_i[0], wo = s_owner[0];
+      for (int w = 1; w < TOPK_THREADS / 32; ++w)
+        if (s_v[w] > wv || (s_v[w] == wv && s_i[w] < wi)) { wv = s_v[w]; wi = s_i[w]; wo = s_owner[w]; }
+      out_val[(size_t)row * k + r] = wv;
+      out_idx[(size_t)row * k + r] = wi;
+      s_win_owner = wo;
+    }
+    __syncthreads();
+    if (tid == s_win_owner) {                 // pop the winner's head
+#pragma unroll
+      for (int j = 0; j < TOPK_MAX - 1; ++j) { v[j] = v[j + 1]; ix[j] = ix[j + 1]; }
+      v[TOPK_MAX - 1] = -CUDART_INF_F; ix[TOPK_MAX - 1] = 0x7fffffff;
+    }
+    __syncthreads();
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -254,6 +315,17 @@ extern "C" int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pit
                                       void* stream) {
   if (n == 0) return VNFR_OK;
   logsoftmax_argmax_kernel<<<ceil_div(n, 4), 128, 0, (cudaStream_t)stream>>>(logits, n, c, pitch, logp, (long long*)label, prob);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_topk_rows(const float* scores, int n, int g, int pitch, int k, int col_offset, int accumulate, float* out_val,
+                              int32_t* out_idx, void* stream) {
+  VNFR_REQUIRE(scores && out_val && out_idx, "null pointer");
+  VNFR_REQUIRE(k >= 1 && k <= TOPK_MAX && g >= 0 && pitch >= g, "k must be in [1,8] and pitch >= g");
+  if (n == 0) return VNFR_OK;
+  topk_rows_kernel<<<n, TOPK_THREADS, 0, (cudaStream_t)stream>>>(scores, g, pitch, k, col_offset, accumulate, out_val, out_idx);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
