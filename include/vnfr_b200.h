@@ -158,6 +158,12 @@ typedef struct {
                                      TMA residual load + TMA store (single 16-bit destination)                          */
   unsigned char tmap_c[128];      /* CUtensorMap of the destination (epi_mode 1)                                       */
   unsigned char tmap_r[128];      /* CUtensorMap of the residual (epi_mode 1, residual != NULL)                        */
+  const float* prelu_alpha;       /* nullable (shifted-view kernel only): per-channel PReLU slope applied instead of ReLU      */
+  const int32_t* n_img_dev;       /* nullable (shifted-view kernel only): DEVICE count of valid images (<= n_img)              */
+  int32_t split3;                 /* shifted-view kernel only: 1 = split-precision convolution.  `in` holds 3 planes of `cin/3`
+                                     channels (hi | mid | lo bf16 parts of an fp32 activation), the weights are packed per tap
+                                     as the 6 products (a0b0, a0b1, a1b0, a0b2, a1b1, a2b0): k = (tap*6 + j)*sv_ck + c; the
+                                     fp32 accumulator then carries ~fp32 accuracy (dropped terms are O(2^-24))               */
   int32_t reserved[1];            /* [0] = sv_ck: 0, or 32 / 64 = request the shifted-view kernel (stride-1 k x k convs, cout <=
                                      256) with weights packed k = (tap*ceil(cin/sv_ck) + chunk)*sv_ck + c               */
 } VnfrConvOp;

@@ -250,3 +250,31 @@ def test_gallery_topk_matches_torch(dev):
     small = gallery.GalleryShard(G[:3].to(dev))
     v2, i2 = small.topk(Q[:4].to(dev), k=5)
     assert (i2[:, 3:] == -1).all() and torch.isinf(v2[:, 3:]).all() and (i2[:, :3] >= 0).all()
+
+
+def test_shifted_view_split_precision_conv(dev):
+    """Split-precision mode of the shifted-view kernel: fp32 activations and weights as 3 bf16 parts each, 6 tensor-core
+    products per K slice, fp32 accumulation -> fp32-level accuracy (the mode the detector heads need: their thresholded
+    decisions must match the fp32 reference).  Also covers PReLU, fp32 output and the device-side image count."""
+    from vn_celeb_face_recognition_b200 import encoder_plan as ep
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n, h, w, cin, cout = 5, 23, 23, 32, 64
+    x = torch.randn(n, h, w, cin, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    alpha = torch.rand(cout, generator=g)
+    xs = torch.cat(ep.split3_bf16(x), dim=-1).to(dev).contiguous()                     # (n, h, w, 96): hi | mid | lo
+    pc = ep.pack_conv_split3(wt, bias, dev, ck=32)
+    out = torch.full((n * 21 * 21, cout), float("nan"), dtype=torch.float32, device=dev)
+    live = torch.tensor([4], dtype=torch.int32, device=dev)                            # only 4 of the 5 images are valid
+    ol = ep.OpList()
+    ol.conv(pc, ep.View(xs), None, relu=False, out_f32=out, sv=32, alpha=alpha.to(dev), n_img_dev=live)
+    assert ol.ops[-1].conv.a_mode == 3
+    ol.run()
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double())
+    ref = torch.where(ref > 0, ref, ref * alpha.double().view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(n * 21 * 21, cout)
+    got = out.cpu().double()
+    assert torch.isnan(got[4 * 441:]).all(), "images beyond the device-side count must not be written"
+    err = (got[:4 * 441] - ref[:4 * 441]).abs().max().item()
+    assert err < 3e-6 * max(1.0, ref.abs().max().item()), err

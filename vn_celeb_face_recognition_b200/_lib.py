@@ -36,7 +36,8 @@ class ConvOp(C.Structure):
         ("cout", C.c_int32), ("cout_pad", C.c_int32), ("k_pad", C.c_int32), ("block_n", C.c_int32),
         ("n_split", C.c_int32), ("out0_pitch", C.c_int32), ("out1_pitch", C.c_int32), ("res_pitch", C.c_int32),
         ("out_f32_pitch", C.c_int32), ("relu", C.c_int32), ("dtype", C.c_int32), ("a_mode", C.c_int32), ("epi_mode", C.c_int32),
-        ("tmap_c", C.c_ubyte * 128), ("tmap_r", C.c_ubyte * 128), ("reserved", C.c_int32 * 1),
+        ("tmap_c", C.c_ubyte * 128), ("tmap_r", C.c_ubyte * 128),
+        ("prelu_alpha", C.c_void_p), ("n_img_dev", C.c_void_p), ("split3", C.c_int32), ("reserved", C.c_int32 * 1),
     ]
 
 

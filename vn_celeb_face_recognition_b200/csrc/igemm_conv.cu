@@ -424,6 +424,7 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   p.relu = op->relu;
   p.dtype = op->dtype;
   p.a_mode = op->a_mode;
+  p.alpha = nullptr;
   p.epi_mode = op->epi_mode;
   p.c_bufs = staging_bufs(op->block_n, op->epi_mode);
   p.stages = pick_stages(op->block_n, op->epi_mode);

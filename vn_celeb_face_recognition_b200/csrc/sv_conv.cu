@@ -47,6 +47,7 @@ struct SvParams {
   int nbuf;                // TMEM accumulator buffers (2 * mt)
   int tmem_cols;           // columns per buffer
   int use_base_offset;     // descriptor base-offset field = (addr >> 7) & 7
+  const int* n_img_dev;    // nullable: device-side count of valid images (bands beyond it are skipped)
   uint32_t koff[128];      // descriptor offset (16-byte units) of K step ks = (tap, chunk): chunk plane + (ky*P + kx) rows
 };
 
@@ -77,6 +78,9 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   uint32_t* s_koff = reinterpret_cast<uint32_t*>(smem_raw + (smem_koff - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // data-dependent batch: the number of valid images may live on the device (detector candidate counts)
+  const int n_img_live = q.n_img_dev != nullptr ? min(p.n_img, __ldg(q.n_img_dev)) : p.n_img;
+  const int n_bands_live = q.bands_y * ((n_img_live + q.nb - 1) / q.nb);
   long long* dbg = blockIdx.x == 0 ? g_sv_dbg : nullptr;
   if (lane != 0) dbg = nullptr;
   const long long t_kernel = SV_T0();
@@ -111,7 +115,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int chalf = warp >> 2;
     int ab = 0;
     uint32_t tph = 0;
-    for (int band = blockIdx.x; band < q.n_bands; band += gridDim.x) {
+    for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x) {
       const int n0_img = (band / q.bands_y) * q.nb;
       const int y0 = (band % q.bands_y) * q.R;
       const int r_valid = min(q.R, p.out_h - y0);
@@ -122,7 +126,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int rr = rem / q.P;
         const int x = rem - rr * q.P;
         const int img = n0_img + il;
-        const bool row_ok = il < q.nb && img < p.n_img && rr < r_valid && x < p.out_w;
+        const bool row_ok = il < q.nb && img < n_img_live && rr < r_valid && x < p.out_w;
         const int m = (img * p.out_h + y0 + rr) * p.out_w + x;
         const long long e0 = (dbg && warp == 0) ? clock64() : 0ll;
         mbar_wait(bar_tfull + 8u * ab, tph);
@@ -140,7 +144,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     // ================================================= A band producer (TMA, one lane)
     if (lane == 0) {
       int j = 0;
-      for (int band = blockIdx.x; band < q.n_bands; band += gridDim.x, ++j) {
+      for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x, ++j) {
         const int buf = j & 1;
         const int n0_img = (band / q.bands_y) * q.nb;
         const int y0 = (band % q.bands_y) * q.R;
@@ -163,7 +167,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       } else {
         int s = 0;
         uint32_t ph = 1;                         // producer starts on the "previous phase complete" parity
-        for (int band = blockIdx.x; band < q.n_bands; band += gridDim.x) {
+        for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x) {
           for (int t = 0; t < q.tiles_per_band; t += q.mt) {
             for (int ks = 0; ks < q.ksteps; ++ks) {
               mbar_wait(bar_empty + 8u * s, ph);
@@ -187,7 +191,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     int s = 0, ab = 0;                         // weight ring stage, TMEM buffer of the next tile
     uint32_t ph = 0, tph = 1;                  // their phase parities (consumer / "buffer drained")
     int j = 0;
-    for (int band = blockIdx.x; band < q.n_bands; band += gridDim.x, ++j) {
+    for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x, ++j) {
       const int buf = j & 1;
       const long long m0 = SV_T0();
       mbar_wait(bar_afull + 8u * buf, (j >> 1) & 1);
@@ -297,17 +301,18 @@ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   if (op->stride != 1 || (op->kh == 1 && op->kw == 1)) return false;
   if (op->cout > 256 || op->block_n != op->cout || op->cout_pad != op->cout) return false;
-  if (op->out_f32 != nullptr) return false;
   const int ck = op->reserved[0];
   if (ck != 16 && ck != 32 && ck != 64) return false;
   const int row_bytes = 2 * ck;
-  const int n_chunks = (op->cin + ck - 1) / ck;
+  const int n_chunks = (op->cin + ck - 1) / ck;        // channel planes of the A band
   const int taps = op->kh * op->kw;
-  if (op->k_pad < taps * n_chunks * ck) return false;
+  if (op->split3 && (n_chunks != 3 || op->cin != 3 * ck)) return false;
+  const int kchunks = op->split3 ? 6 : n_chunks;        // K steps per tap
+  if (op->k_pad < taps * kchunks * ck) return false;
   const int P = op->in_w + 2 * op->pad_w;
   if (P > 256) return false;
   const int b_tile = op->block_n * row_bytes;
-  const int ksteps = taps * n_chunks;
+  const int ksteps = taps * kchunks;
   if (ksteps > 128) return false;
   int tmem_cols = 32;
   while (tmem_cols < op->block_n) tmem_cols <<= 1;
@@ -370,11 +375,14 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   // any number of rows (also odd multiples of 64 bytes in 64B-swizzle mode) reads correctly with base_offset = 0; setting
   // the field to (addr >> 7) & 7 applies the phase twice (tests/test_gpu_encoder.py::test_shifted_view_conv_matches_torch).
   q->use_base_offset = 0;
+  static const int split_plane[6] = {0, 0, 1, 0, 1, 2};      // activation part of product j (weights: 0,1,0,2,1,0)
   for (int ks = 0; ks < ksteps; ++ks) {
-    const int tap = ks / n_chunks, c = ks - tap * n_chunks;
+    const int tap = ks / kchunks, j = ks - tap * kchunks;
+    const int c = op->split3 ? split_plane[j] : j;
     const int ky = tap / op->kw, kx = tap - ky * op->kw;
     q->koff[ks] = ((uint32_t)c * (uint32_t)q->plane_bytes + (uint32_t)(ky * P + kx) * (uint32_t)row_bytes) >> 4;
   }
+  q->n_img_dev = op->n_img_dev;
   return true;
 }
 
@@ -454,14 +462,15 @@ int vnfr_sv_run(const VnfrConvOp* op, void* stream) {
   p.residual = (const __nv_bfloat16*)op->residual;
   p.out0 = (__nv_bfloat16*)op->out0;
   p.out1 = (__nv_bfloat16*)op->out1;
-  p.out_f32 = nullptr;
+  p.out_f32 = op->out_f32;
+  p.alpha = op->prelu_alpha;
   p.n_img = op->n_img; p.in_h = op->in_h; p.in_w = op->in_w; p.cin = op->cin; p.in_pitch = op->in_pitch;
   p.kh = op->kh; p.kw = op->kw; p.stride = 1; p.pad_h = op->pad_h; p.pad_w = op->pad_w;
   p.out_h = op->out_h; p.out_w = op->out_w;
   p.M = op->n_img * op->out_h * op->out_w;
   p.cout = op->cout; p.block_n = op->block_n;
   p.n_split = op->n_split; p.out0_pitch = op->out0_pitch; p.out1_pitch = op->out1_pitch;
-  p.res_pitch = op->res_pitch; p.out_f32_pitch = 0;
+  p.res_pitch = op->res_pitch; p.out_f32_pitch = op->out_f32_pitch;
   p.relu = op->relu; p.dtype = op->dtype; p.a_mode = 3;
   p.tmem_cols = q.tmem_cols; p.stages = q.stages;
   if (p.M <= 0) return VNFR_OK;

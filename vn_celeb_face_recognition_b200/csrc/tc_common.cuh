@@ -34,6 +34,7 @@ struct ConvParams {
   int dtype;   // 0 = bf16, 1 = fp16 (both: fp32 accumulation in TMEM)
   int epi_mode;  // 1: shared-memory staged epilogue (TMA residual load, TMA store)
   int c_bufs;    // staging buffers of the staged epilogue (1 or 2)
+  const float* alpha;   // nullable: per-channel PReLU slope (applied instead of ReLU)
 };
 
 // ------------------------------------------------------------------------------------------------------------ PTX
@@ -310,6 +311,10 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
       if (p.relu) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+      }
+      if (p.alpha != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * __ldg(p.alpha + n + i);
       }
       if (p.out_f32 != nullptr) {
         float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.out_f32_pitch + n);

@@ -84,6 +84,38 @@ def pack_conv(w, scale, bias, device, cin_pad=None, block_n=None, dtype=None):
     return PackedConv(wp, bp, kh, kw, cin_p, cout16, bn)
 
 
+def split3_bf16(x):
+    """fp32 tensor -> (hi, mid, lo) bf16 parts with hi + mid + lo == x to ~2^-24 relative (each part is the bf16 rounding
+    of what the previous parts left over)."""
+    x = x.float()
+    hi = x.to(torch.bfloat16)
+    r1 = x - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    return hi, mid, lo
+
+
+def pack_conv_split3(w, bias, device, ck):
+    """Split-precision weights for the shifted-view kernel (VnfrConvOp.split3): w (cout, cin, kh, kw) fp32 with
+    cin <= ck -> bf16 [cout][taps*6*ck], K step (tap, j) holding weight part (0,1,0,2,1,0)[j] -- the partner of activation
+    part (0,0,1,0,1,2)[j] -- so that the six bf16 products sum to the fp32 product up to O(2^-24)."""
+    w = w.detach().to(device=device, dtype=torch.float32)
+    cout, cin, kh, kw = w.shape
+    assert cin <= ck and cout % 16 == 0
+    wp = torch.zeros(cout, kh * kw, ck, dtype=torch.float32, device=device)
+    wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    parts = split3_bf16(wp)
+    order = (0, 1, 0, 2, 1, 0)
+    packed = torch.stack([parts[j] for j in order], dim=2)                 # cout, taps, 6, ck
+    packed = packed.reshape(cout, kh * kw * 6 * ck).contiguous()
+    k_pad = _ceil(packed.shape[1], 64)
+    if k_pad != packed.shape[1]:
+        packed = torch.nn.functional.pad(packed, (0, k_pad - packed.shape[1]))
+    pc = PackedConv(packed.contiguous(), bias.detach().to(device=device, dtype=torch.float32).contiguous(), kh, kw, 3 * ck, cout, cout)
+    pc.split3 = True
+    return pc
+
+
 def fold_bn(sd, p):
     """BasicConv2d ``p`` -> (weight, scale, bias) with eval-mode BN folded."""
     g, b = sd[p + ".bn.weight"].float(), sd[p + ".bn.bias"].float()
@@ -163,9 +195,10 @@ class OpList:
         self._graph, self._runs = None, 0
 
     def conv(self, pc, src, dst0, stride=1, pad=(0, 0), relu=True, dst1=None, n_split=None, residual=None, out_f32=None,
-             sv=None):
+             sv=None, alpha=None, n_img_dev=None):
         """``sv`` = 32 / 64 requests the shifted-view kernel (csrc/sv_conv.cu) with that many channels per plane; the
         packed weights must then be laid out with cin padded to a multiple of ``sv`` (pc.cin)."""
+        split3 = bool(getattr(pc, "split3", False))
         if sv is None:
             sv = SV_DEFAULT.get(src.c) if (stride == 1 and pc.kh * pc.kw > 1 and pc.cout <= 256 and out_f32 is None
                                             and pc.block_n == pc.cout == pc.cout_pad) else 0
@@ -200,7 +233,16 @@ class OpList:
         if residual is not None:
             c.residual, c.res_pitch = residual.ptr, residual.pitch
         c.reserved[0] = int(sv or 0)
+        c.split3 = 1 if split3 else 0
+        if alpha is not None:
+            c.prelu_alpha = alpha.data_ptr()
+            self.keep.append(alpha)
+        if n_img_dev is not None:
+            c.n_img_dev = n_img_dev.data_ptr()
+            self.keep.append(n_img_dev)
         _lib.call("vnfr_conv_prepare", C.byref(c))
+        if split3 and c.a_mode != 3:
+            raise _lib.VnfrError("split-precision convolution needs the shifted-view kernel, but the geometry does not qualify")
         if pc.cin != src.c and c.a_mode != 3:
             raise _lib.VnfrError("weights were packed for the shifted-view kernel but the geometry does not qualify")
         self.ops.append(op)
