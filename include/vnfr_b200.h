@@ -108,6 +108,14 @@ int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const
                       const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops, int crop_cap,
                       int32_t* status, void* stream);
 
+/* O-Net with conv2 (63 % of its FLOPs) on the tensor cores in split precision: three bf16 parts per fp32 operand, six
+ * products, fp32 accumulation (vnfr_conv_run with VnfrConvOp.split3) over all crops in one launch; the other layers stay on
+ * the fp32 FMA path.  w2_split: bf16 [64][1728] (conv2 weights, split3 layout); p1: bf16 [crop_cap][23][23][96] and
+ * c2: fp32 [crop_cap][441][64] workspaces.  Same outputs and semantics as vnfr_onet_forward.                         */
+int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                         const float* weights, const void* w2_split, float* prob, float* reg, float* lmk, int32_t* offs,
+                         float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream);
+
 /* Stage-2 tail (detect_face.py:119-136): score > threshold, NMS(0.7), bbreg, rerec, pad. */
 int vnfr_stage2_boxes(int B, int H, int W, int cap2, const int32_t* s2_count, const float* s2_box, const float* s2_prob,
                       const float* s2_reg, float threshold, int cap3, int32_t* s3_count, float* s3_box, int32_t* s3_pad,

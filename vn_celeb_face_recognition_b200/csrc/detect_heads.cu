@@ -8,6 +8,7 @@
 // Arithmetic is fp32 FMA: the `score > threshold` decisions of stages 2/3 must match the fp32 reference.
 #include "common.cuh"
 #include <math_constants.h>
+#include <string.h>
 
 extern long long g_vnfr_launches;
 
@@ -339,6 +340,8 @@ struct HeadArgs {
   float4* reg;           // [B][cap]
   float* lmk;            // [B][cap][10] (O-Net)
   float* crops;          // workspace [crop_cap][3][S][S]: the resized, normalised crops (written by crop_kernel)
+  __nv_bfloat16* p1;     // O-Net tensor-core path: pooled conv1 map [crop][23][23][96] = hi | mid | lo bf16 parts
+  const float* c2;       // O-Net tensor-core path: conv2 + PReLU output [crop][21*21][64] fp32 (written by sv_conv)
   int crop_cap;          // crops the workspace holds; flat indices beyond it are dropped and flagged in *status (bit 5)
   int* status;
 };
@@ -584,6 +587,126 @@ __global__ void __launch_bounds__(NT, 1) onet_kernel(const HeadArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ O-Net, tensor-core conv2
+// conv2 (32 -> 64, 3x3) is 63 % of O-Net's FLOPs; on the fp32 FMA pipe it ran at 64 % of peak and still took half of the
+// kernel.  Here it runs on the tensor cores in split precision (three bf16 parts per operand, six products, fp32
+// accumulation -- sv_conv.cu, VnfrConvOp.split3) over ALL crops of the batch in one launch:
+//   onet_front_kernel: crop -> conv1 + PReLU -> maxpool 3/2 -> 3-way bf16 split, NHWC [crop][23][23][96]      (global)
+//   sv_conv_kernel   : conv2 + bias + PReLU -> fp32 NHWC [crop][441][64]                                      (global)
+//   onet_back_kernel : maxpool 3/2 -> conv3 -> maxpool 2/2 -> conv4 -> dense5 (4 crops per pass) -> heads
+constexpr int OF_A = 3 * 48 * 48, OF_B = 32 * 23 * 23, OF_C = 8 * 46 * 46 + 2 * 864;
+constexpr int OF_SMEM = (OF_A + OF_B + OF_C) * 4;
+
+__device__ __forceinline__ unsigned short bf16_bits(float x) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  return *reinterpret_cast<const unsigned short*>(&h);
+}
+__device__ __forceinline__ float bf16_to_float(unsigned short b) { return __uint_as_float((unsigned)b << 16); }
+
+__global__ void __launch_bounds__(NT, 1) onet_front_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm; float* Bf = sm + OF_A; float* Cf = Bf + OF_B;
+  const int total = min(a.offs[a.B], a.crop_cap);
+  const float* w = a.w;
+  for (int flat = blockIdx.x; flat < total; flat += gridDim.x) {
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(a.crops + (size_t)flat * OF_A);
+      for (int i = threadIdx.x; i < OF_A / 4; i += NT) reinterpret_cast<float4*>(A)[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      conv_prelu_smem_ws<3, 32, 3, 3, 48, 48, 1, 8, 5, 1, 3>(A, Cf, nullptr, Cf + 8 * 46 * 46, w + OW_::W1, w + OW_::B1, w + OW_::A1, c0, c0 + 8);
+      __syncthreads();
+      maxpool_smem<3, 46, 46>(Cf, Bf + c0 * 23 * 23, 8);
+      __syncthreads();
+    }
+    // 3-way bf16 split, pixel-major: thread -> (pixel, channel) with the channel fastest (64-byte runs per part)
+    unsigned short* dst = reinterpret_cast<unsigned short*>(a.p1) + (size_t)flat * 529 * 96;
+    for (int i = threadIdx.x; i < 529 * 32; i += NT) {
+      const int px = i >> 5, c = i & 31;
+      const float x = Bf[c * 529 + px];
+      const unsigned short hi = bf16_bits(x);
+      const float r1 = x - bf16_to_float(hi);
+      const unsigned short mid = bf16_bits(r1);
+      const unsigned short lo = bf16_bits(r1 - bf16_to_float(mid));
+      unsigned short* q = dst + (size_t)px * 96 + c;
+      q[0] = hi; q[32] = mid; q[64] = lo;
+    }
+  }
+}
+
+constexpr int OB_A = 64 * 10 * 10 + 512, OB_B = 64 * 8 * 8, OB_C = 16384 + 9216;
+constexpr int OB_SMEM = (OB_A + OB_B + OB_C + O_F) * 4;
+
+__global__ void __launch_bounds__(NT, 1) onet_back_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm; float* Bf = sm + OB_A; float* Cf = Bf + OB_B; float* F = Cf + OB_C;
+  __shared__ int s_b[OG], s_slot[OG], s_empty[OG];
+  const int total = min(a.offs[a.B], a.crop_cap);
+  const float* w = a.w;
+  for (int k0 = 0; blockIdx.x + k0 * gridDim.x < total; k0 += OG) {
+    for (int g = 0; g < OG; ++g) {
+      const int flat = blockIdx.x + (k0 + g) * gridDim.x;
+      if (flat >= total) {
+        if (threadIdx.x == 0) s_b[g] = -1;
+        for (int i = threadIdx.x; i < 1152; i += NT) F[g * 1152 + i] = 0.f;
+        continue;
+      }
+      if (threadIdx.x == 0) {
+        int b, slot; locate(a.offs, a.B, flat, b, slot); s_b[g] = b; s_slot[g] = slot;
+        const int4 pd = a.pad[(size_t)b * a.cap + slot];
+        s_empty[g] = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);
+      }
+      // maxpool 3/2 (21 -> 10: every window is complete) straight from the fp32 NHWC conv2 output; channel fastest
+      const float* src = a.c2 + (size_t)flat * 441 * 64;
+      for (int i = threadIdx.x; i < 100 * 64; i += NT) {
+        const int pos = i >> 6, c = i & 63;
+        const int oy = pos / 10, ox = pos - oy * 10;
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) m = fmaxf(m, __ldg(src + (size_t)((2 * oy + ky) * 21 + 2 * ox + kx) * 64 + c));
+        A[c * 100 + pos] = m;
+      }
+      __syncthreads();
+      conv_prelu_smem_ws<64, 64, 3, 3, 10, 10, 1, 8, 4, 4, 2>(A, Bf, Cf, Cf + 16384, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);
+      __syncthreads();
+      maxpool_smem<2, 8, 8>(Bf, A, 64);
+      __syncthreads();
+      conv_prelu_smem<64, 128, 2, 2, 4, 4, 1, 4, 3, 4>(A, F + g * 1152, Cf, w + OW_::W4, w + OW_::B4, w + OW_::A4, 0, 128);
+      __syncthreads();
+    }
+    __syncthreads();
+    fc_prelu_smem<1152, 256, OG>(F, A, Cf, w + OW_::W5, w + OW_::B5, w + OW_::A5);
+    __syncthreads();
+    if (threadIdx.x < OG * 16) {
+      const int g = threadIdx.x >> 4, j = threadIdx.x & 15;
+      float sacc = __ldg(w + OW_::B6 + j);
+      for (int k = 0; k < 256; ++k) sacc = fmaf(__ldg(w + OW_::W6 + k * 16 + j), A[g * 256 + k], sacc);
+      Cf[threadIdx.x] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x < OG * 16) {
+      const int g = threadIdx.x >> 4, j = threadIdx.x & 15;
+      if (s_b[g] >= 0) {
+        const size_t o = (size_t)s_b[g] * a.cap + s_slot[g];
+        const float* h = Cf + g * 16;
+        if (j == 0) {
+          const float l0 = h[0], l1 = h[1];
+          const float mx = fmaxf(l0, l1);
+          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+          a.prob[o] = s_empty[g] ? 0.f : e1 / (e0 + e1);
+          a.reg[o] = make_float4(h[2], h[3], h[4], h[5]);
+        }
+        if (j >= 6) a.lmk[o * 10 + (j - 6)] = h[j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void scan_counts_kernel(const int* __restrict__ count, int B, int cap, int* __restrict__ offs) {
   // B is small (frames per batch): a single thread does the exclusive scan
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -617,6 +740,7 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
+  a.p1 = nullptr; a.c2 = nullptr;
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(rnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
@@ -629,6 +753,62 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
   // persistent grid: one CTA per SM (shared memory bound), each loops over the flat candidate list
   if (onet) onet_kernel<<<148 * 1, NT, O_SMEM, st>>>(a);
   else rnet_kernel<<<148 * 1, NT, R_SMEM, st>>>(a);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+// O-Net with conv2 on the tensor cores (see onet_front_kernel).  w2_split: bf16 [64][1728] split-precision weights of conv2
+// (encoder_plan.pack_conv_split3 layout); p1 / c2: workspaces for crop_cap crops (101 568 B and 112 896 B per crop).
+extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                                    const float* weights, const void* w2_split, float* prob, float* reg, float* lmk, int32_t* offs,
+                                    float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream) {
+  VNFR_REQUIRE(frames && count && pad && weights && w2_split && prob && reg && lmk && offs && crops && p1 && c2 && status, "null pointer");
+  VNFR_REQUIRE(crop_cap > 0 && ((uintptr_t)crops % 16) == 0 && ((uintptr_t)p1 % 16) == 0 && ((uintptr_t)c2 % 16) == 0,
+               "workspaces must hold at least one crop and be 16-byte aligned");
+  if (B == 0) return VNFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_counts_kernel<<<1, 32, 0, st>>>(count, B, cap, offs);
+  ++g_vnfr_launches;
+  HeadArgs a;
+  a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
+  a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
+  a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
+  a.p1 = (__nv_bfloat16*)p1; a.c2 = c2;
+  static bool attr = false;
+  if (!attr) {
+    VNFR_CUDA(cudaFuncSetAttribute(onet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
+    attr = true;
+  }
+  crop_kernel<48><<<148 * 8, CROP_THREADS, 0, st>>>(a);
+  onet_front_kernel<<<148, NT, OF_SMEM, st>>>(a);
+  g_vnfr_launches += 2;
+  VNFR_CHECK_LAUNCH();
+  // conv2 on the tensor cores; the tensor maps are re-encoded only when a pointer or the capacity changes
+  static VnfrConvOp op;
+  static const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+  static int key_cap = -1;
+  if (key[0] != p1 || key[1] != w2_split || key[2] != (const void*)c2 || key[3] != (const void*)weights || key_cap != crop_cap) {
+    memset(&op, 0, sizeof(op));
+    op.in = p1; op.weights = w2_split; op.bias = weights + OW_::B2; op.prelu_alpha = weights + OW_::A2;
+    op.out_f32 = c2; op.out_f32_pitch = 64;
+    op.n_img = crop_cap; op.in_h = 23; op.in_w = 23; op.cin = 96; op.in_pitch = 96;
+    op.kh = 3; op.kw = 3; op.stride = 1; op.pad_h = 0; op.pad_w = 0; op.out_h = 21; op.out_w = 21;
+    op.cout = 64; op.cout_pad = 64; op.k_pad = 1728; op.block_n = 64; op.n_split = 64;
+    op.relu = 0; op.dtype = 0; op.reserved[0] = 32; op.split3 = 1;
+    op.n_img_dev = offs + B;                     // total candidate count, written by scan_counts_kernel
+    const int rc = vnfr_conv_prepare(&op);
+    if (rc != VNFR_OK) return rc;
+    VNFR_REQUIRE(op.a_mode == 3, "split-precision conv2 did not qualify for the shifted-view kernel");
+    key[0] = p1; key[1] = w2_split; key[2] = c2; key[3] = weights; key_cap = crop_cap;
+  }
+  op.n_img_dev = offs + B;
+  {
+    const int rc = vnfr_conv_run(&op, stream);
+    if (rc != VNFR_OK) return rc;
+  }
+  onet_back_kernel<<<148, NT, OB_SMEM, st>>>(a);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

@@ -47,6 +47,8 @@ struct SvParams {
   int nbuf;                // TMEM accumulator buffers (2 * mt)
   int tmem_cols;           // columns per buffer
   int use_base_offset;     // descriptor base-offset field = (addr >> 7) & 7
+  int a_bufs;              // band buffers: 2 (next band loads under this band's MMAs) or 1 (large bands)
+  int order;               // MMA issue order inside a K step: 0 = accumulator-major, 1 = rotate over accumulators per K slice
   const int* n_img_dev;    // nullable: device-side count of valid images (bands beyond it are skipped)
   uint32_t koff[128];      // descriptor offset (16-byte units) of K step ks = (tap, chunk): chunk plane + (ky*P + kx) rows
 };
@@ -65,7 +67,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   const ConvParams& p = q.p;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;                                            // 2 band buffers
-  const uint32_t smem_b = smem_a + 2u * (uint32_t)q.a_buf_bytes;                // resident weights or ring
+  const uint32_t smem_b = smem_a + (uint32_t)q.a_bufs * (uint32_t)q.a_buf_bytes;   // resident weights or ring
   const uint32_t b_bytes = (uint32_t)(q.b_resident ? q.ksteps : q.stages) * (uint32_t)q.b_tile_bytes;
   const uint32_t smem_bias = smem_b + b_bytes;                                  // 256 floats
   const uint32_t smem_koff = smem_bias + 1024u;                                 // 128 x u32 shifted-view offsets (>> 4)
@@ -145,11 +147,11 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     if (lane == 0) {
       int j = 0;
       for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x, ++j) {
-        const int buf = j & 1;
+        const int buf = q.a_bufs == 2 ? (j & 1) : 0;
         const int n0_img = (band / q.bands_y) * q.nb;
         const int y0 = (band % q.bands_y) * q.R;
         const long long p0 = SV_T0();
-        mbar_wait(bar_aempty + 8u * buf, ((j >> 1) & 1) ^ 1);
+        mbar_wait(bar_aempty + 8u * buf, (uint32_t)(((q.a_bufs == 2 ? (j >> 1) : j) & 1) ^ 1));
         SV_ACC(7, p0);
         mbar_arrive_expect_tx(bar_afull + 8u * buf, (uint32_t)q.n_chunks * (uint32_t)q.a_box_bytes);
         for (int c = 0; c < q.n_chunks; ++c)
@@ -192,9 +194,9 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     uint32_t ph = 0, tph = 1;                  // their phase parities (consumer / "buffer drained")
     int j = 0;
     for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x, ++j) {
-      const int buf = j & 1;
+      const int buf = q.a_bufs == 2 ? (j & 1) : 0;
       const long long m0 = SV_T0();
-      mbar_wait(bar_afull + 8u * buf, (j >> 1) & 1);
+      mbar_wait(bar_afull + 8u * buf, (uint32_t)((q.a_bufs == 2 ? (j >> 1) : j) & 1));
       SV_ACC(1, m0);
       tc_fence_after();
       const uint64_t a_desc0 = make_sw_desc(smem_a + (uint32_t)buf * q.a_buf_bytes, row_bytes, 0);
@@ -224,7 +226,20 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           // (an elect + __syncwarp per K step costs more than the 2-4 MMAs it guards).  Issue order: for every K slice
           // rotate over the group's accumulators (independent instructions back to back).
           if (elect_one()) {
-            if (nt == 4) {
+            if (q.order == 0) {
+              for (int ks = 0; ks < q.ksteps; ++ks) {
+                const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)ks * b_tile16);
+                const uint64_t ko = (uint64_t)q.koff[ks];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (u < nt) {
+#pragma unroll
+                    for (int kk = 0; kk < MPS; ++kk)
+                      umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
+                  }
+                }
+              }
+            } else if (nt == 4) {
               for (int ks = 0; ks < q.ksteps; ++ks) {
                 const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)ks * b_tile16);
                 const uint64_t ko = (uint64_t)q.koff[ks];
@@ -258,13 +273,23 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)s * b_tile16);
             const uint64_t ko = (uint64_t)q.koff[ks];
             if (elect_one()) {
-              // N = 128 (streamed weights): accumulator-major order measured faster (29.7 vs 37.0 us on Block17 1x7)
+              if (q.order == 0) {
+                // N = 128: accumulator-major order measured faster (29.7 vs 37.0 us on Block17 1x7)
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (u < nt) {
+                for (int u = 0; u < 4; ++u) {
+                  if (u < nt) {
 #pragma unroll
-                  for (int kk = 0; kk < MPS; ++kk)
-                    umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
+                    for (int kk = 0; kk < MPS; ++kk)
+                      umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
+                  }
+                }
+              } else {
+                // small N: back-to-back instructions into one accumulator serialise (126 cycles): rotate per K slice
+#pragma unroll
+                for (int kk = 0; kk < MPS; ++kk) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    if (u < nt) umma_bf16(d[u], a_t[u] + ko + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (ks | kk) != 0);
                 }
               }
               umma_commit(bar_empty + 8u * s);
@@ -326,34 +351,43 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   // streamed weights are only worth it when two accumulator tiles share every weight stage (otherwise the generic
   // kernel moves fewer bytes per useful output)
   if (!b_res && mt < 2) return false;
-  int stages = b_res ? 1 : 4;
+  // weight ring: deep enough to cover the TMA latency with small tiles (4 KB tiles of the split-precision O-Net conv2
+  // need ~16 in flight), 64 KB at most
+  int stages = 1;
+  if (!b_res) {
+    stages = (64 * 1024) / b_tile;
+    if (stages < 4) stages = 4;
+    if (stages > 16) stages = 16;
+  }
   const int b_bytes = b_res ? ksteps * b_tile : stages * b_tile;
-  const int a_budget = (budget - b_bytes - 2048) / 2;       // per band buffer
   const int px_align = 1024 / row_bytes;
-  // candidates: (R, nb); maximise useful accumulator rows per issued row, prefer fewer halo re-reads
+  // candidates: (R, nb, band buffers); maximise useful accumulator rows per issued row, prefer fewer halo re-reads and
+  // full weight-stage sharing; a single band buffer (no load/MMA overlap between bands) is allowed at a 10 % discount
   double best = -1;
-  int bR = 0, bnb = 0;
-  for (int R = 1; R <= op->out_h; ++R) {
-    const int rows_in = R + op->kh - 1;
-    if (rows_in > 256) break;
-    const int img_px = rows_in * P;
-    const int nb_max = R == op->out_h ? 16 : 1;
-    for (int nb = 1; nb <= nb_max && nb <= op->n_img; ++nb) {
-      const int lin = (nb - 1) * img_px + R * P;
-      const int tiles = (lin + 127) / 128;
-      const int alloc_px = round_up(tiles * 128 + (op->kh - 1) * P + op->kw - 1, px_align);
-      if (alloc_px < nb * img_px) continue;
-      const long long a_bytes = (long long)n_chunks * alloc_px * row_bytes;
-      if (a_bytes > a_budget) continue;
-      if ((long long)nb * img_px * row_bytes > 200 * 1024) continue;
-      const int bands_y = (op->out_h + R - 1) / R;
-      // efficiency: valid outputs over all bands / accumulator rows issued, discounted by the halo re-read factor
-      const double valid = (double)op->out_h * op->out_w * nb;
-      const double issued = (double)bands_y * tiles * 128;
-      const double halo = (double)(R + op->kh - 1) / (R + 0.25 * (op->kh - 1));
-      const double share = b_res ? 1.0 : (double)tiles / (double)(mt * ((tiles + mt - 1) / mt));   // weight-stage sharing
-      const double score = valid / issued / halo * share;
-      if (score > best) { best = score; bR = R; bnb = nb; }
+  int bR = 0, bnb = 0, bbufs = 2;
+  for (int bufs = 2; bufs >= 1; --bufs) {
+    const int a_budget = (budget - b_bytes - 2048) / bufs;    // per band buffer
+    for (int R = 1; R <= op->out_h; ++R) {
+      const int rows_in = R + op->kh - 1;
+      if (rows_in > 256) break;
+      const int img_px = rows_in * P;
+      const int nb_max = R == op->out_h ? 16 : 1;
+      for (int nb = 1; nb <= nb_max && nb <= op->n_img; ++nb) {
+        const int lin = (nb - 1) * img_px + R * P;
+        const int tiles = (lin + 127) / 128;
+        const int alloc_px = round_up(tiles * 128 + (op->kh - 1) * P + op->kw - 1, px_align);
+        if (alloc_px < nb * img_px) continue;
+        const long long a_bytes = (long long)n_chunks * alloc_px * row_bytes;
+        if (a_bytes > a_budget) continue;
+        if ((long long)nb * img_px * row_bytes > 200 * 1024) continue;
+        const int bands_y = (op->out_h + R - 1) / R;
+        const double valid = (double)op->out_h * op->out_w * nb;
+        const double issued = (double)bands_y * tiles * 128;
+        const double halo = (double)(R + op->kh - 1) / (R + 0.25 * (op->kh - 1));
+        const double share = b_res ? 1.0 : (double)tiles / (double)(mt * ((tiles + mt - 1) / mt));   // weight-stage sharing
+        const double score = valid / issued / halo * share * (bufs == 2 ? 1.0 : 0.9);
+        if (score > best) { best = score; bR = R; bnb = nb; bbufs = bufs; }
+      }
     }
   }
   if (best < 0) return false;
@@ -382,13 +416,16 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
     const int ky = tap / op->kw, kx = tap - ky * op->kw;
     q->koff[ks] = ((uint32_t)c * (uint32_t)q->plane_bytes + (uint32_t)(ky * P + kx) * (uint32_t)row_bytes) >> 4;
   }
+  q->a_bufs = bbufs;
   q->n_img_dev = op->n_img_dev;
+  q->order = 0;      // accumulator-major measured at least as fast as rotating per K slice in every layer (profiles/)
+  if (getenv("VNFR_SV_ORDER") != nullptr) q->order = atoi(getenv("VNFR_SV_ORDER"));
   return true;
 }
 
 size_t sv_smem_bytes(const SvParams& q) {
   const size_t b_bytes = (size_t)(q.b_resident ? q.ksteps : q.stages) * q.b_tile_bytes;
-  return 1024 + 2 * (size_t)q.a_buf_bytes + b_bytes + 1024 + 512 + 40 + 16 * q.stages + 16 * q.nbuf + 16;
+  return 1024 + (size_t)q.a_bufs * q.a_buf_bytes + b_bytes + 1024 + 512 + 40 + 16 * q.stages + 16 * q.nbuf + 16;
 }
 
 }  // namespace

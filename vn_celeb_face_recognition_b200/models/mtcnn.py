@@ -166,6 +166,10 @@ class DetectWorkspace:
         self.ocrop_cap = max(1, min(B * cap3, max(512, B * MTCNN.crop_ws_per_frame[1])))
         self.rcrops = torch.empty(self.rcrop_cap * 3 * 24 * 24, **f32)
         self.ocrops = torch.empty(self.ocrop_cap * 3 * 48 * 48, **f32)
+        if MTCNN.onet_tensor_cores:
+            # O-Net conv2 on the tensor cores: pooled conv1 map as 3 bf16 parts, conv2 output in fp32 (vnfr_onet_forward_tc)
+            self.op1 = torch.empty(self.ocrop_cap * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
+            self.oc2 = torch.empty(self.ocrop_cap * 21 * 21 * 64, **f32)
         self.out_box = torch.zeros(B, capf, 5, **f32)
         self.out_pts = torch.zeros(B, capf, 10, **f32)
 
@@ -193,7 +197,9 @@ class MTCNN(nn.Module):
     #: Exceeding one raises (results would otherwise be truncated); raise the cap and call again.
     caps = (4096, 4096, 2048, 256)
     #: average R-Net / O-Net candidates per frame the crop workspaces are sized for (6.9 KB / 27.6 KB per crop)
-    crop_ws_per_frame = (2048, 512)
+    crop_ws_per_frame = (2048, 256)
+    #: run O-Net's conv2 on the tensor cores in split precision (fp32-level accuracy); VNFR_ONET_FMA=1 keeps it on the FMA pipe
+    onet_tensor_cores = not os.environ.get("VNFR_ONET_FMA")
 
     def __init__(self, image_size=160, margin=0, min_face_size=20, thresholds=[0.6, 0.7, 0.7], factor=0.709,
                  post_process=True, select_largest=True, selection_method=None, keep_all=False, device=None):
@@ -246,7 +252,10 @@ class MTCNN(nn.Module):
             rw = _pack_rnet(self.rnet.state_dict())
             ow = _pack_onet(self.onet.state_dict())
             assert rw.numel() == _lib.lib().vnfr_rnet_weight_floats() and ow.numel() == _lib.lib().vnfr_onet_weight_floats()
-            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev)}
+            from .. import encoder_plan
+            osd = self.onet.state_dict()
+            w2s = encoder_plan.pack_conv_split3(osd["conv2.weight"], osd["conv2.bias"], dev, 32)
+            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w}
             MTCNN._pnet_owner = None
         if MTCNN._pnet_owner is not self._packed:
             # P-Net weights live in __constant__ memory (one set per process): re-upload when another instance used it
@@ -298,8 +307,13 @@ class MTCNN(nn.Module):
         _lib.call("vnfr_stage2_boxes", B, H, W, cap2, P(ws.s2_count), P(ws.s2_box), P(ws.s2_prob), P(ws.s2_reg), t1, cap3,
                   P(ws.s3_count), P(ws.s3_box), P(ws.s3_pad), P(ws.status), st)
         mark("stage2_nms")
-        _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
-                  P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), ws.ocrop_cap, P(ws.status), st)
+        if hasattr(ws, "op1"):
+            _lib.call("vnfr_onet_forward_tc", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
+                      P(wts["onet_w2s"]), P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), P(ws.op1),
+                      P(ws.oc2), ws.ocrop_cap, P(ws.status), st)
+        else:
+            _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
+                      P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), ws.ocrop_cap, P(ws.status), st)
         mark("onet")
         _lib.call("vnfr_stage3_faces", B, cap3, P(ws.s3_count), P(ws.s3_box), P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), t2,
                   1 if sl else 0, capf, P(ws.out_count), P(ws.out_box), P(ws.out_pts), P(ws.status), st)
