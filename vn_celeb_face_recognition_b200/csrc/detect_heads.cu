@@ -65,13 +65,13 @@ __device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, fl
       const int oy = r / OW, ox = r - oy * OW;
       off[j] = (g * CIN * IH + oy) * IW + ox;
     }
-    float acc[POS][CH];
+    f32x2 acc[POS][CH / 2];                              // channel pairs (c, c+1), packed FFMA2
 #pragma unroll
     for (int c4 = 0; c4 < CH / 4; ++c4) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ks == 0) b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * c4));
 #pragma unroll
-      for (int j = 0; j < POS; ++j) { acc[j][4 * c4] = b4.x; acc[j][4 * c4 + 1] = b4.y; acc[j][4 * c4 + 2] = b4.z; acc[j][4 * c4 + 3] = b4.w; }
+      for (int j = 0; j < POS; ++j) { acc[j][2 * c4] = pack2f(b4.x, b4.y); acc[j][2 * c4 + 1] = pack2f(b4.z, b4.w); }
     }
     const float* wp = w + c0;
     const int ci0 = ks * CI_PER;
@@ -81,18 +81,19 @@ __device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, fl
       for (int ky = 0; ky < KH; ++ky)
 #pragma unroll
         for (int kx = 0; kx < KW; ++kx) {
-          float wv[CH];
+          f32x2 wv[CH / 2];
 #pragma unroll
           for (int c4 = 0; c4 < CH / 4; ++c4) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wp + ((ci * KH + ky) * KW + kx) * COUT) + c4);
-            wv[4 * c4] = w4.x; wv[4 * c4 + 1] = w4.y; wv[4 * c4 + 2] = w4.z; wv[4 * c4 + 3] = w4.w;
+            const ulonglong2 w4 = __ldg(reinterpret_cast<const ulonglong2*>(wp + ((ci * KH + ky) * KW + kx) * COUT) + c4);
+            wv[2 * c4] = w4.x; wv[2 * c4 + 1] = w4.y;
           }
           const int o = (ci * IH + ky) * IW + kx;
 #pragma unroll
           for (int j = 0; j < POS; ++j) {
             const float v = in[off[j] + o];
+            const f32x2 vv = pack2f(v, v);
 #pragma unroll
-            for (int c = 0; c < CH; ++c) acc[j][c] = fmaf(wv[c], v, acc[j][c]);
+            for (int c = 0; c < CH / 2; ++c) fma2(acc[j][c], wv[c], vv);
           }
         }
     }
@@ -104,7 +105,7 @@ __device__ __forceinline__ void conv_prelu_smem(const float* __restrict__ in, fl
       const int g = p / (OH * OW), r = p - g * (OH * OW);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const float v = acc[j][c];
+        const float v = (c & 1) ? hi2f(acc[j][c >> 1]) : lo2f(acc[j][c >> 1]);
         dst[(g * cn + CH * cg + c) * (OH * OW) + r] = KS == 1 ? prelu(v, __ldg(alpha + c0 + c)) : v;
       }
     }
