@@ -292,3 +292,18 @@ def test_host_frame_path_overlapped_copy_equals_device_path(dev, models):
             np.testing.assert_array_equal(a["labels"], b["labels"])
             np.testing.assert_array_equal(a["emb"], b["emb"])
     assert sum(len(r["labels"]) for r in ref) > 0
+
+
+def test_crop_workspace_overflow_grows_and_repeats(dev, models):
+    """More R-/O-Net candidates than the crop workspaces hold (crowded frames): the status word flags it, the host grows
+    the workspaces and repeats the pass -- results equal the amply sized run, nothing is silently dropped."""
+    from oracle import synth
+    fr = synth.frames("small", 3)
+    ref = models["MTCNN"](image_size=160, keep_all=True, min_face_size=20, device=dev).detect(fr, landmarks=True)
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=20, device=dev)
+    det.crop_ws_floor, det.crop_ws_per_frame = (4, 2), (4, 2)
+    got = det.detect(fr, landmarks=True)
+    assert det.crop_ws_per_frame[0] > 4, "the workspace must have been grown"
+    for a, b in zip(got, ref):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y))

@@ -125,7 +125,7 @@ def _pack_onet(sd):
 class DetectWorkspace:
     """Device buffers of one detection pass for a fixed (B, H, W, min_face_size, factor, caps)."""
 
-    def __init__(self, B, H, W, minsize, factor, caps, dev):
+    def __init__(self, B, H, W, minsize, factor, caps, dev, crop_ws=(2048, 256), crop_floor=(2048, 512)):
         self.pyr = _lib.Pyramid()
         _lib.call("vnfr_pyramid_plan", B, H, W, int(minsize), float(factor), C.byref(self.pyr))
         p = self.pyr
@@ -162,8 +162,8 @@ class DetectWorkspace:
         self.offs = torch.zeros(B + 1, **i32)
         # crop workspaces of the R-Net / O-Net stages (fp32 [n][3][S][S]); sized for CROP_WS_PER_FRAME candidates per frame
         # on average (overflow raises through the status word, like the caps)
-        self.rcrop_cap = max(1, min(B * cap2, max(2048, B * MTCNN.crop_ws_per_frame[0])))
-        self.ocrop_cap = max(1, min(B * cap3, max(512, B * MTCNN.crop_ws_per_frame[1])))
+        self.rcrop_cap = max(1, min(B * cap2, max(crop_floor[0], B * crop_ws[0])))
+        self.ocrop_cap = max(1, min(B * cap3, max(crop_floor[1], B * crop_ws[1])))
         self.rcrops = torch.empty(self.rcrop_cap * 3 * 24 * 24, **f32)
         self.ocrops = torch.empty(self.ocrop_cap * 3 * 48 * 48, **f32)
         if MTCNN.onet_tensor_cores:
@@ -172,6 +172,10 @@ class DetectWorkspace:
             self.oc2 = torch.empty(self.ocrop_cap * 21 * 21 * 64, **f32)
         self.out_box = torch.zeros(B, capf, 5, **f32)
         self.out_pts = torch.zeros(B, capf, 10, **f32)
+
+
+class CropWorkspaceOverflow(_lib.VnfrError):
+    """More R-/O-Net candidates than the crop workspaces hold: callers grow the workspace and repeat the pass."""
 
 
 class ResultWorkspace:
@@ -198,6 +202,8 @@ class MTCNN(nn.Module):
     caps = (4096, 4096, 2048, 256)
     #: average R-Net / O-Net candidates per frame the crop workspaces are sized for (6.9 KB / 27.6 KB per crop)
     crop_ws_per_frame = (2048, 256)
+    #: minimum size (crops) of the two workspaces whatever the batch
+    crop_ws_floor = (2048, 512)
     #: run O-Net's conv2 on the tensor cores in split precision (fp32-level accuracy); VNFR_ONET_FMA=1 keeps it on the FMA pipe
     onet_tensor_cores = not os.environ.get("VNFR_ONET_FMA")
 
@@ -282,7 +288,8 @@ class MTCNN(nn.Module):
         if ws is None:
             if len(self._ws) > 8:
                 self._ws.clear()
-            ws = self._ws[key] = DetectWorkspace(B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev)
+            ws = self._ws[key] = DetectWorkspace(B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev,
+                                                 tuple(self.crop_ws_per_frame), tuple(self.crop_ws_floor))
         cap1, cap2, cap3, capf = ws.caps
         st = _lib.stream_ptr()
         P = _lib.ptr
@@ -344,8 +351,16 @@ class MTCNN(nn.Module):
         full.frames = frames_dev
         return full
 
+    def grow_crop_workspace(self):
+        """Doubles the per-frame sizing of the R-/O-Net crop workspaces (called after a crop-workspace overflow) and drops
+        the cached workspaces so that the next pass allocates the larger ones."""
+        self.crop_ws_per_frame = tuple(2 * v for v in self.crop_ws_per_frame)
+        self._ws.clear()
+
     @staticmethod
     def check_status(status):
+        if status & 32 and not (status & 31):
+            raise CropWorkspaceOverflow("R-/O-Net crop workspace exceeded (MTCNN.crop_ws_per_frame)")
         if status:
             names = ["cap1 (P-Net candidates per image/level)", "cap2 (boxes per image into R-Net)",
                      "cap3 (boxes per image into O-Net)", "capf (faces per image)", "max_faces",
@@ -407,9 +422,16 @@ class MTCNN(nn.Module):
         """mtcnn.py:278-361.  Returns host numpy (boxes, probs[, points]); ragged batches come back as object arrays."""
         with torch.no_grad():
             frames = self._to_frames(img)
-            ws = self.detect_device(frames)
-            cnt = ws.out_count.cpu().numpy()
-            self.check_status(int(ws.status.item()))
+            for attempt in range(6):
+                ws = self.detect_device(frames)
+                cnt = ws.out_count.cpu().numpy()
+                try:
+                    self.check_status(int(ws.status.item()))
+                    break
+                except CropWorkspaceOverflow:
+                    if attempt == 5:
+                        raise
+                    self.grow_crop_workspace()
             nmax = int(cnt.max()) if len(cnt) else 0
             box = ws.out_box[:, :max(nmax, 1)].cpu().numpy()
             pts = ws.out_pts[:, :max(nmax, 1)].cpu().numpy()

@@ -65,10 +65,17 @@ class FacePipeline:
         """frames_u8: CUDA uint8 (B,H,W,3).  Returns a dict of DEVICE tensors + the face count (one tiny sync to size
         the encoder batch): count (B,), boxes (B,capf,5), points (B,capf,10), faces_u8 (F,S,S,3), emb (F,512),
         label (F,), prob (F,), face_img (F,)."""
+        from .models.mtcnn import CropWorkspaceOverflow
         mark = mark or (lambda name: None)
         with torch.no_grad():
-            ws = self.det.detect_device(frames_u8, mark=mark)
-            return self._embed_classify(ws, mark)
+            for attempt in range(6):
+                ws = self.det.detect_device(frames_u8, mark=mark)
+                try:
+                    return self._embed_classify(ws, mark)
+                except CropWorkspaceOverflow:          # more candidates than the crop workspaces hold: grow and repeat
+                    if attempt == 5:
+                        raise
+                    self.det.grow_crop_workspace()
 
     def _embed_classify(self, ws, mark):
         """detections (DetectWorkspace / ResultWorkspace) -> aligned crops -> encoder -> classifier, on the device."""
@@ -133,9 +140,16 @@ class FacePipeline:
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 events.append(ev)
-        with torch.no_grad():
-            ws = self.det.detect_device_chunked(buf, events, bounds)
-        return self._embed_classify(ws, lambda name: None)
+        from .models.mtcnn import CropWorkspaceOverflow
+        for attempt in range(6):
+            with torch.no_grad():
+                ws = self.det.detect_device_chunked(buf, events if attempt == 0 else None, bounds)
+            try:
+                return self._embed_classify(ws, lambda name: None)
+            except CropWorkspaceOverflow:
+                if attempt == 5:
+                    raise
+                self.det.grow_crop_workspace()
 
     def __call__(self, frames):
         """frames: (B,H,W,3) uint8 numpy / torch (host or device).  Returns per-frame lists (boxes (n,4) numpy, labels,
@@ -173,10 +187,18 @@ def parallel_detect_and_align(rgb_images, detection_md, center_point, target_fs,
     dev = detection_md._cuda_device()
     frames = torch.as_tensor(np.stack([np.asarray(im) for im in rgb_images])).to(dev)
     with torch.no_grad():
-        ws = detection_md.detect_device(frames)
-        u8, _, _, _ = detection_md.face_crops_device(ws, 1, int(target_fs[0]), 0, center_point)
-        cnt = ws.out_count.cpu().numpy()
-        detection_md.check_status(int(ws.status.item()))
+        from .models.mtcnn import CropWorkspaceOverflow
+        for attempt in range(6):
+            ws = detection_md.detect_device(frames)
+            u8, _, _, _ = detection_md.face_crops_device(ws, 1, int(target_fs[0]), 0, center_point)
+            cnt = ws.out_count.cpu().numpy()
+            try:
+                detection_md.check_status(int(ws.status.item()))
+                break
+            except CropWorkspaceOverflow:
+                if attempt == 5:
+                    raise
+                detection_md.grow_crop_workspace()
         F = int(cnt.sum())
         faces = u8[:F].cpu().numpy()
         nmax = int(cnt.max()) if len(cnt) else 0
