@@ -202,9 +202,14 @@ __global__ void __launch_bounds__(NTHR, PNET_MIN_CTAS) pnet_kernel(const __grid_
 
     // ---- conv3 (16->32, 3x3) + PReLU + heads: thread = cells (y, x) and (y + 8, x), 32 channels each in registers
     const int y = tid >> 4, x = tid & 15;
-    float acc[2][32];
+    // packed fp32 pairs (FFMA2, fma.rn.f32x2): accp[h][q] = channels (2q, 2q+1) of cell h -- half the FMA issue slots,
+    // bit-identical results
+    unsigned long long accp[2][16];
 #pragma unroll
-    for (int co = 0; co < 32; ++co) { acc[0][co] = s_w[D_B3 + co]; acc[1][co] = acc[0][co]; }
+    for (int q = 0; q < 16; ++q) {
+      const unsigned long long b2 = *reinterpret_cast<const unsigned long long*>(s_w + D_B3 + 2 * q);
+      accp[0][q] = b2; accp[1][q] = b2;
+    }
 #pragma unroll 1
     for (int ci = 0; ci < 16; ++ci) {
 #pragma unroll
@@ -213,17 +218,27 @@ __global__ void __launch_bounds__(NTHR, PNET_MIN_CTAS) pnet_kernel(const __grid_
         for (int kx = 0; kx < 3; ++kx) {
           const float v0 = s_buf[(ci * C2T + y + ky) * C2T + x + kx];
           const float v1 = s_buf[(ci * C2T + y + 8 + ky) * C2T + x + kx];
-          const float4* wr = reinterpret_cast<const float4*>(s_w + D_W3 + ((ci * 3 + ky) * 3 + kx) * 32);
+          const unsigned long long vv0 = (unsigned long long)__float_as_uint(v0) | ((unsigned long long)__float_as_uint(v0) << 32);
+          const unsigned long long vv1 = (unsigned long long)__float_as_uint(v1) | ((unsigned long long)__float_as_uint(v1) << 32);
+          const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(s_w + D_W3 + ((ci * 3 + ky) * 3 + kx) * 32);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 w4 = wr[q];
-            acc[0][4 * q + 0] = fmaf(w4.x, v0, acc[0][4 * q + 0]); acc[1][4 * q + 0] = fmaf(w4.x, v1, acc[1][4 * q + 0]);
-            acc[0][4 * q + 1] = fmaf(w4.y, v0, acc[0][4 * q + 1]); acc[1][4 * q + 1] = fmaf(w4.y, v1, acc[1][4 * q + 1]);
-            acc[0][4 * q + 2] = fmaf(w4.z, v0, acc[0][4 * q + 2]); acc[1][4 * q + 2] = fmaf(w4.z, v1, acc[1][4 * q + 2]);
-            acc[0][4 * q + 3] = fmaf(w4.w, v0, acc[0][4 * q + 3]); acc[1][4 * q + 3] = fmaf(w4.w, v1, acc[1][4 * q + 3]);
+            const ulonglong2 w4 = wr[q];
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(accp[0][2 * q]) : "l"(w4.x), "l"(vv0));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(accp[1][2 * q]) : "l"(w4.x), "l"(vv1));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(accp[0][2 * q + 1]) : "l"(w4.y), "l"(vv0));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(accp[1][2 * q + 1]) : "l"(w4.y), "l"(vv1));
           }
         }
     }
+    float acc[2][32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        acc[h][2 * q] = __uint_as_float((unsigned)(accp[h][q] & 0xFFFFFFFFull));
+        acc[h][2 * q + 1] = __uint_as_float((unsigned)(accp[h][q] >> 32));
+      }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float o[8];
