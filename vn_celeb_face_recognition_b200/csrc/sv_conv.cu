@@ -47,6 +47,7 @@ struct SvParams {
   int nbuf;                // TMEM accumulator buffers (2 * mt)
   int tmem_cols;           // columns per buffer
   int use_base_offset;     // descriptor base-offset field = (addr >> 7) & 7
+  int epi_split;           // 1: the two epilogue warp groups take alternate tiles (narrow tiles)
   int a_bufs;              // band buffers: 2 (next band loads under this band's MMAs) or 1 (large bands)
   int order;               // MMA issue order inside a K step: 0 = accumulator-major, 1 = rotate over accumulators per K slice
   const int* n_img_dev;    // nullable: device-side count of valid images (bands beyond it are skipped)
@@ -92,7 +93,10 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + 8u * i, 1); mbar_init(bar_aempty + 8u * i, 1); }
     mbar_init(bar_bres, 1);
     for (int s = 0; s < q.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-    for (int i = 0; i < q.nbuf; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, SV_EPI_THREADS); }
+    for (int i = 0; i < q.nbuf; ++i) {
+      mbar_init(bar_tfull + 8u * i, 1);
+      mbar_init(bar_tempty + 8u * i, q.epi_split ? SV_EPI_THREADS / 2 : SV_EPI_THREADS);
+    }
     fence_barrier_init();
   }
   if (warp == 8 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -115,30 +119,41 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int qq = warp & 3;
     const int r = qq * 32 + lane;
     const int chalf = warp >> 2;
-    int ab = 0;
+    int ab = 0, tseq = 0;
     uint32_t tph = 0;
     for (int band = blockIdx.x; band < n_bands_live; band += gridDim.x) {
       const int n0_img = (band / q.bands_y) * q.nb;
       const int y0 = (band % q.bands_y) * q.R;
       const int r_valid = min(q.R, p.out_h - y0);
       for (int t = 0; t < q.tiles_per_band; ++t) {
-        const int lin = t * 128 + r;
-        const int il = lin / q.img_px;
-        const int rem = lin - il * q.img_px;
-        const int rr = rem / q.P;
-        const int x = rem - rr * q.P;
-        const int img = n0_img + il;
-        const bool row_ok = il < q.nb && img < n_img_live && rr < r_valid && x < p.out_w;
-        const int m = (img * p.out_h + y0 + rr) * p.out_w + x;
-        const long long e0 = (dbg && warp == 0) ? clock64() : 0ll;
-        mbar_wait(bar_tfull + 8u * ab, tph);
-        const long long e1 = (dbg && warp == 0) ? clock64() : 0ll;
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ab * q.tmem_cols);
-        epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, chalf);
-        tc_fence_before();
-        mbar_arrive(bar_tempty + 8u * ab);
-        if (dbg && warp == 0) { dbg[5] += e1 - e0; dbg[6] += clock64() - e1; }
+        // narrow tiles (cout <= 64): the two warp groups take alternate tiles (each warp then covers all columns of its
+        // rows), which halves the per-tile wait -> load -> store -> arrive latency chain the MMA warp sees
+        const bool mine = !q.epi_split || ((tseq & 1) == (warp >> 2));
+        ++tseq;
+        if (mine) {
+          const int lin = t * 128 + r;
+          const int il = lin / q.img_px;
+          const int rem = lin - il * q.img_px;
+          const int rr = rem / q.P;
+          const int x = rem - rr * q.P;
+          const int img = n0_img + il;
+          const bool row_ok = il < q.nb && img < n_img_live && rr < r_valid && x < p.out_w;
+          const int m = (img * p.out_h + y0 + rr) * p.out_w + x;
+          const long long e0 = (dbg && warp == 0) ? clock64() : 0ll;
+          mbar_wait(bar_tfull + 8u * ab, tph);
+          const long long e1 = (dbg && warp == 0) ? clock64() : 0ll;
+          tc_fence_after();
+          const uint32_t t_row = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ab * q.tmem_cols);
+          if (q.epi_split) {
+            epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, 0);
+            epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, 1);
+          } else {
+            epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, chalf);
+          }
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8u * ab);
+          if (dbg && warp == 0) { dbg[5] += e1 - e0; dbg[6] += clock64() - e1; }
+        }
         if (++ab == q.nbuf) { ab = 0; tph ^= 1u; }
       }
     }
@@ -417,6 +432,7 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
     q->koff[ks] = ((uint32_t)c * (uint32_t)q->plane_bytes + (uint32_t)(ky * P + kx) * (uint32_t)row_bytes) >> 4;
   }
   q->a_bufs = bbufs;
+  q->epi_split = (op->cout <= 64 && getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr) ? 1 : 0;
   q->n_img_dev = op->n_img_dev;
   q->order = 0;      // accumulator-major measured at least as fast as rotating per K slice in every layer (profiles/)
   if (getenv("VNFR_SV_ORDER") != nullptr) q->order = atoi(getenv("VNFR_SV_ORDER"));
