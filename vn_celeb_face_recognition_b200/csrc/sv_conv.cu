@@ -145,8 +145,8 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           tc_fence_after();
           const uint32_t t_row = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ab * q.tmem_cols);
           if (q.epi_split) {
-            epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, 0);
-            epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, 1);
+            if (p.cout == 32) epilogue_row_narrow<F16, 32>(p, s_bias, t_row, m, row_ok);
+            else epilogue_row_narrow<F16, 64>(p, s_bias, t_row, m, row_ok);
           } else {
             epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, chalf);
           }
@@ -432,7 +432,9 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
     q->koff[ks] = ((uint32_t)c * (uint32_t)q->plane_bytes + (uint32_t)(ky * P + kx) * (uint32_t)row_bytes) >> 4;
   }
   q->a_bufs = bbufs;
-  q->epi_split = (op->cout <= 64 && getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr) ? 1 : 0;
+  // narrow single-destination tiles without residual: alternate tiles between the two epilogue warp groups
+  q->epi_split = ((op->cout == 32 || op->cout == 64) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
+                  getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr) ? 1 : 0;
   q->n_img_dev = op->n_img_dev;
   q->order = 0;      // accumulator-major measured at least as fast as rotating per K slice in every layer (profiles/)
   if (getenv("VNFR_SV_ORDER") != nullptr) q->order = atoi(getenv("VNFR_SV_ORDER"));

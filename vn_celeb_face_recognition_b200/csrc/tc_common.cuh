@@ -334,6 +334,43 @@ __device__ __forceinline__ void epilogue_row(const ConvParams& p, const float* s
   }
 }
 
+// Narrow-tile variant (NC = 32 or 64 columns, one destination, no residual): all tcgen05.ld of the row are issued back to
+// back and waited for once, so the TMEM load latency is paid once per tile instead of once per 16-column chunk.
+template <bool F16, int NC>
+__device__ __forceinline__ void epilogue_row_narrow(const ConvParams& p, const float* sb, uint32_t t_row, int m, bool row_ok) {
+  float v[NC];
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC / 16; ++c) tmem_ld16_issue(t_row + (uint32_t)(16 * c), v + 16 * c);
+#pragma unroll
+  for (int c = 0; c < NC / 16; ++c) tmem_ld_wait(v + 16 * c);
+  if (!row_ok) return;
+#pragma unroll
+  for (int i = 0; i < NC / 4; ++i) {
+    const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * i);
+    v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  if (p.alpha != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * __ldg(p.alpha + i);
+  }
+  if (p.out_f32 != nullptr) {
+    float4* o = reinterpret_cast<float4*>(p.out_f32 + (size_t)m * p.out_f32_pitch);
+#pragma unroll
+    for (int qq = 0; qq < NC / 4; ++qq) o[qq] = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(p.out0 + (size_t)m * p.out0_pitch);
+#pragma unroll
+    for (int qq = 0; qq < NC / 8; ++qq)
+      o[qq] = make_uint4(pack2<F16>(v[8 * qq], v[8 * qq + 1]), pack2<F16>(v[8 * qq + 2], v[8 * qq + 3]),
+                         pack2<F16>(v[8 * qq + 4], v[8 * qq + 5]), pack2<F16>(v[8 * qq + 6], v[8 * qq + 7]));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
