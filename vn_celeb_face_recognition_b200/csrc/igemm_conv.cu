@@ -29,6 +29,13 @@ namespace {
 // Three barrier rings: smem full/empty per stage (global K-block counter runs across tiles, so the load pipeline never
 // drains at a tile boundary), TMEM full/empty per accumulator buffer.
 // Shared memory: [A stage 0..S) 16 KB each][W stage 0..S) block_n*128 B each][bias 2 x 256 fp32][barriers].
+// Optional cycle breakdown of CTA 0 (tools/ig_probe.py): [0] kernel, [1] MMA warp waiting for a full stage, [2] for a
+// drained accumulator, [3] epilogue waiting for the accumulator, [4] for the residual / free C buffer, [5] epilogue work,
+// [6] store issue + wait, [7] producer waiting for an empty stage, [8] producer waiting for a free C buffer.
+__device__ long long* g_ig_dbg = nullptr;
+#define IG_T0() (dbg ? clock64() : 0ll)
+#define IG_ACC(i, t0) do { if (dbg) dbg[i] += clock64() - (t0); } while (0)
+
 template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
@@ -36,24 +43,32 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int S = p.stages;
+  const int KB0 = p.k_blocks;
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_a + (uint32_t)S * A_STAGE_BYTES;
-  const uint32_t smem_c = smem_b + (uint32_t)S * b_stage_bytes;             // staged C tile: 64-channel panels of 16 KB
+  const uint32_t smem_c = smem_b + (uint32_t)(p.b_res ? KB0 : S) * b_stage_bytes;   // staged C tile: 64-channel panels of 16 KB
   const uint32_t n_panels = p.epi_mode ? (uint32_t)((p.block_n + 63) >> 6) : 0u;
   const uint32_t c_buf_bytes = n_panels * 16384u;
   const uint32_t smem_bias = smem_c + (uint32_t)p.c_bufs * c_buf_bytes;     // 2 x 256 floats
   const uint32_t bars = smem_bias + 2048u;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bar_tfull + 16u,
-                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 16u, tmem_slot = bar_cfree + 16u;
+                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 16u, bar_bres = bar_cfree + 16u, tmem_slot = bar_bres + 8u;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  long long* dbg = (blockIdx.x == 0 && lane == 0) ? g_ig_dbg : nullptr;
+  const long long t_kernel = IG_T0();
   const int KB = p.k_blocks;
   const int n_tiles_n = p.n_tiles_n;
   const int total_tiles = p.n_tiles_m * n_tiles_n;
+  // Tile walk.  Default: tile = blockIdx.x, += gridDim.x.  Resident-weights mode (b_res): the CTA is bound to ONE N tile
+  // (blockIdx.x % n_tiles_n) whose K x block_n weight slab stays in shared memory for the whole kernel, and walks the M
+  // tiles of that column -- for the small-K projection convolutions the weight slab was 40 % of a tile's L2 traffic.
+  const int tile_first = p.b_res ? (blockIdx.x / n_tiles_n) * n_tiles_n + (blockIdx.x % n_tiles_n) : (int)blockIdx.x;
+  const int tile_step = p.b_res ? ((int)gridDim.x / n_tiles_n) * n_tiles_n : (int)gridDim.x;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -65,6 +80,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_init(bar_tempty + 8u * i, NUM_EPILOGUE_THREADS);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_res + 8u * i, 1); mbar_init(bar_cfree + 8u * i, 1); }
+    mbar_init(bar_bres, 1);
     fence_barrier_init();
   }
   if (warp == 16 && lane == 0) {
@@ -95,7 +111,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int hw = p.out_h * p.out_w;
     int s = 0;                                 // ring stage / phase parity: wrapping counters, no division in the loop
     uint32_t ph = 1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int m_base = (tile / n_tiles_n) * BLOCK_M;
       int iy0[4], ix0[4];
       const __nv_bfloat16* img_base[4];
@@ -150,7 +166,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     const int et = tid - NUM_PRODUCER_THREADS; // 0..255
     const int chalf = (warp - 8) >> 2;         // this warp handles 16-column chunks with (chunk & 1) == chalf
     int tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
       const int ab = tcount & 1;
       const int m = (tile / n_tiles_n) * BLOCK_M + r;
       const int n0 = (tile % n_tiles_n) * p.block_n;
@@ -160,7 +176,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       float* sb = s_bias + ab * 256;
       for (int i = et; i < n_valid; i += NUM_EPILOGUE_THREADS) sb[i] = __ldg(p.bias + n0 + i);
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");      // bias visible to the 8 epilogue warps
+      long long* edbg = warp == 8 ? dbg : nullptr;
+      const long long e0 = edbg ? clock64() : 0ll;
       mbar_wait(bar_tfull + 8u * ab, (tcount >> 1) & 1);
+      if (edbg) edbg[3] += clock64() - e0;
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.tmem_cols);
       if (p.epi_mode) {
@@ -168,24 +187,31 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int cb = p.c_bufs == 2 ? (tcount & 1) : 0;
         const uint32_t cph = p.c_bufs == 2 ? (uint32_t)((tcount >> 1) & 1) : (uint32_t)(tcount & 1);
         const uint32_t smem_cb = smem_c + (uint32_t)cb * c_buf_bytes;
+        if (p.c_bufs == 2 && et == 0 && tcount > 0) {
+          // the store of the previous tile (other buffer) was issued a whole tile ago: once it has read its panels the
+          // buffer goes back to the producer, which refills it with the NEXT tile's residual while this tile is processed
+          tma_store_wait_read();
+          mbar_arrive(bar_cfree + 8u * (cb ^ 1));
+        }
+        const long long e1 = edbg ? clock64() : 0ll;
         mbar_wait(bar_res + 8u * cb, cph);
+        const long long e2 = edbg ? clock64() : 0ll;
         epilogue_row_staged<F16>(p, sb, t_row, smem_cb, r, n_valid, chalf, p.residual != nullptr);
         tc_fence_before();
         mbar_arrive(bar_tempty + 8u * ab);     // accumulator drained: the MMA warp may reuse it
         fence_proxy_async_smem();              // generic-proxy writes of the tile -> visible to the TMA store
         asm volatile("bar.sync 2, %0;" ::"n"(NUM_EPILOGUE_THREADS) : "memory");
+        const long long e3 = edbg ? clock64() : 0ll;
+        if (edbg) { edbg[4] += e2 - e1; edbg[5] += e3 - e2; }
         if (et == 0) {
           const int m0 = (tile / n_tiles_n) * BLOCK_M;
           for (int j = 0; j * 64 < n_valid; ++j) tma_store_2d(&tmap_c, smem_cb + (uint32_t)j * 16384u, n0 + j * 64, m0);
           tma_store_commit();
-          if (p.c_bufs == 2) {
-            // the OTHER buffer's store (previous tile) must have read its panels before they are handed back
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            if (tcount > 0) mbar_arrive(bar_cfree + 8u * (cb ^ 1));
-          } else {
+          if (p.c_bufs != 2) {
             tma_store_wait_read();             // the panels have been read: they may be refilled
             mbar_arrive(bar_cfree);
           }
+          if (edbg) edbg[6] += clock64() - e3;
         }
         continue;
       }
@@ -198,19 +224,27 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     if (lane == 0) {
       int s = 0, tn = 0;
       uint32_t ph = 1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      if (p.b_res && tile_first < total_tiles) {
+        // the weight slab of this CTA's N tile: loaded once
+        const int n0 = (tile_first % n_tiles_n) * p.block_n;
+        mbar_arrive_expect_tx(bar_bres, (uint32_t)KB * b_stage_bytes);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_b + (uint32_t)kb * b_stage_bytes, &tmap_w, bar_bres, kb * BLOCK_K, n0);
+      }
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % n_tiles_n) * p.block_n;
         const int m0 = (tile / n_tiles_n) * BLOCK_M;
         for (int kb = 0; kb < KB; ++kb) {
+          const long long p0 = IG_T0();
           mbar_wait(bar_empty + 8u * s, ph);
+          IG_ACC(7, p0);
           if (p.a_mode == 1) {
             // 1x1 convolution: the A tile is a plain 2-D box of the [M][pitch] activation matrix
-            mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes + A_STAGE_BYTES);
+            mbar_arrive_expect_tx(bar_full + 8u * s, (p.b_res ? 0u : b_stage_bytes) + A_STAGE_BYTES);
             tma_load_2d(smem_a + (uint32_t)s * A_STAGE_BYTES, &tmap_a, bar_full + 8u * s, kb * BLOCK_K, m0);
           } else {
             mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
           }
-          tma_load_2d(smem_b + (uint32_t)s * b_stage_bytes, &tmap_w, bar_full + 8u * s, kb * BLOCK_K, n0);
+          if (!p.b_res) tma_load_2d(smem_b + (uint32_t)s * b_stage_bytes, &tmap_w, bar_full + 8u * s, kb * BLOCK_K, n0);
           if (++s == S) { s = 0; ph ^= 1u; }
         }
         if (p.epi_mode) {
@@ -220,7 +254,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
           const int cb = p.c_bufs == 2 ? (tn & 1) : 0;
           const uint32_t cph = p.c_bufs == 2 ? (uint32_t)(((tn >> 1) & 1) ^ 1) : (uint32_t)((tn & 1) ^ 1);
           const uint32_t smem_cb = smem_c + (uint32_t)cb * c_buf_bytes;
+          const long long p1 = IG_T0();
           mbar_wait(bar_cfree + 8u * cb, cph);
+          IG_ACC(8, p1);
           if (p.residual != nullptr) {
             const int n_valid = min(p.block_n, p.cout - n0);
             const int np = (n_valid + 63) >> 6;
@@ -243,17 +279,22 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     uint32_t ph = 0;
     const uint64_t a_desc0 = make_sw128_desc(smem_a), b_desc0 = make_sw128_desc(smem_b);
     const uint32_t b_stage16 = b_stage_bytes >> 4;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    if (p.b_res && tile_first < total_tiles) mbar_wait(bar_bres, 0);
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
       const int ab = tcount & 1;
+      const long long m0 = IG_T0();
       mbar_wait(bar_tempty + 8u * ab, ((tcount >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+      IG_ACC(2, m0);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ab * p.tmem_cols);
       for (int kb = 0; kb < KB; ++kb) {
+        const long long m1 = IG_T0();
         mbar_wait(bar_full + 8u * s, ph);
+        IG_ACC(1, m1);
         if (p.a_mode == 0) fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
         tc_fence_after();
         const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)s * (A_STAGE_BYTES >> 4));
-        const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)s * b_stage16);
+        const uint64_t b_desc = b_desc0 + (uint64_t)((uint32_t)(p.b_res ? kb : s) * b_stage16);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 16; ++kk) {
@@ -272,6 +313,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
 
   if (p.epi_mode && tid == NUM_PRODUCER_THREADS) tma_store_wait_all();     // the storing thread: writes have landed
   __syncthreads();
+  if (dbg && tid == 0) dbg[0] += clock64() - t_kernel;
   if (warp == 17) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * p.tmem_cols)) : "memory");
@@ -291,22 +333,39 @@ int staging_bufs(int block_n, int epi_mode) {
 }
 int staging_bytes(int block_n, int epi_mode) { return staging_bufs(block_n, epi_mode) * ((block_n + 63) / 64) * 16384; }
 
-int pick_stages(int block_n, int epi_mode) {
-  const int stage_bytes = A_STAGE_BYTES + block_n * 128;
-  int s = (220 * 1024 - staging_bytes(block_n, epi_mode)) / stage_bytes;   // one persistent CTA per SM owns (almost) all of its shared memory
+int pick_stages(int block_n, int epi_mode, int b_res_kb) {
+  // b_res_kb > 0: the weights (b_res_kb K blocks) are resident, the ring carries only A
+  const int stage_bytes = A_STAGE_BYTES + (b_res_kb ? 0 : block_n * 128);
+  int s = (220 * 1024 - staging_bytes(block_n, epi_mode) - b_res_kb * block_n * 128) / stage_bytes;   // one persistent CTA per SM
   if (s < 2) s = 2;
   if (s > MAX_STAGES) s = MAX_STAGES;
   return s;
 }
 
-size_t smem_bytes_for(int block_n, int stages, int epi_mode) {
-  return 1024 /*alignment slack*/ + (size_t)stages * (A_STAGE_BYTES + block_n * 128) + staging_bytes(block_n, epi_mode) +
-         2048 /*bias*/ + 16 * stages + 96;
+size_t smem_bytes_for(int block_n, int stages, int epi_mode, int b_res_kb) {
+  return 1024 /*alignment slack*/ + (size_t)stages * (A_STAGE_BYTES + (b_res_kb ? 0 : block_n * 128)) + (size_t)b_res_kb * block_n * 128 +
+         staging_bytes(block_n, epi_mode) + 2048 /*bias*/ + 16 * stages + 104;
+}
+
+// Resident weights pay off for the small-K projection convolutions: TMA-fed 1x1 with a staged epilogue, a weight slab of at
+// most 96 KB that still leaves >= 3 A stages, several N tiles and enough M tiles per CTA column.
+bool use_resident_weights(const VnfrConvOp* op, int k_blocks, int n_tiles_m, int n_tiles_n) {
+  if (op->a_mode != 1 || !op->epi_mode || getenv("VNFR_NO_BRES") != nullptr) return false;
+  const int slab = k_blocks * op->block_n * 128;
+  if (slab > 96 * 1024 || n_tiles_n < 2 || n_tiles_n > 74) return false;
+  if ((220 * 1024 - staging_bytes(op->block_n, op->epi_mode) - slab) / A_STAGE_BYTES < 3) return false;
+  return n_tiles_m >= 4 * (148 / n_tiles_n);
 }
 
 }  // namespace
 
 extern long long g_vnfr_launches;
+
+// debug hook (not part of include/vnfr_b200.h): device buffer of 16 int64 cycle counters, or null to switch off
+extern "C" int vnfr_ig_debug(long long* dev_buf) {
+  VNFR_CUDA(cudaMemcpyToSymbol(g_ig_dbg, &dev_buf, sizeof(dev_buf)));
+  return VNFR_OK;
+}
 
 extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
   VNFR_REQUIRE(op != nullptr, "op is null");
@@ -427,7 +486,11 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   p.alpha = nullptr;
   p.epi_mode = op->epi_mode;
   p.c_bufs = staging_bufs(op->block_n, op->epi_mode);
-  p.stages = pick_stages(op->block_n, op->epi_mode);
+  p.n_tiles_m = ceil_div(p.M, BLOCK_M);
+  p.n_tiles_n = ceil_div(op->cout, op->block_n);
+  p.b_res = use_resident_weights(op, p.k_blocks, p.n_tiles_m, p.n_tiles_n) ? 1 : 0;
+  const int b_res_kb = p.b_res ? p.k_blocks : 0;
+  p.stages = pick_stages(op->block_n, op->epi_mode, b_res_kb);
   int cols = 32;
   while (cols < op->block_n) cols <<= 1;
   p.tmem_cols = cols;
@@ -437,14 +500,13 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   memcpy(&ta, op->a_mode != 0 ? op->tmap_a : op->tmap_w, sizeof(ta));
   memcpy(&tc_, op->epi_mode ? op->tmap_c : op->tmap_w, sizeof(tc_));
   memcpy(&tr, (op->epi_mode && op->residual != nullptr) ? op->tmap_r : op->tmap_w, sizeof(tr));
-  p.n_tiles_m = ceil_div(p.M, BLOCK_M);
-  p.n_tiles_n = ceil_div(op->cout, op->block_n);
   const int total_tiles = p.n_tiles_m * p.n_tiles_n;
   dim3 grid(total_tiles < g_num_sms ? total_tiles : g_num_sms);
+  if (p.b_res) grid = dim3((g_num_sms / p.n_tiles_n) * p.n_tiles_n);
   if (op->dtype == 1)
-    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
+    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode, b_res_kb), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
   else
-    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
+    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode, b_res_kb), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

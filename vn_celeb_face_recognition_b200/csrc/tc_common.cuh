@@ -34,6 +34,7 @@ struct ConvParams {
   int dtype;   // 0 = bf16, 1 = fp16 (both: fp32 accumulation in TMEM)
   int epi_mode;  // 1: shared-memory staged epilogue (TMA residual load, TMA store)
   int c_bufs;    // staging buffers of the staged epilogue (1 or 2)
+  int b_res;     // igemm: the CTA's weight slab (all K blocks of one N tile) is resident in shared memory
   const float* alpha;   // nullable: per-channel PReLU slope (applied instead of ReLU)
 };
 

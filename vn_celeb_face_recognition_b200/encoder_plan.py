@@ -154,6 +154,10 @@ def pack_stem_s2d(sd, prefix, device, dtype=None):
 
 def pack_projection(sd, p, scale, device, block_n=None, dtype=None):
     """Block projection conv2d (with bias), residual scale folded in."""
+    # N tiles of 128: the K x 128 weight slab of a projection (K = 96 / 256 / 384) then stays resident in shared memory
+    # (igemm_conv.cu use_resident_weights) and two C staging buffers fit
+    if block_n is None:
+        block_n = int(os.environ.get("VNFR_PROJ_BLOCK_N", "128"))
     return pack_conv(sd[p + ".weight"].float() * scale, None, sd[p + ".bias"].float() * scale, device, None, block_n, dtype)
 
 
