@@ -32,3 +32,7 @@ fp.sub_batch, fp.first_sub_batch = 16, 4
 bounds = fp._sub_batches(64)
 print("detect whole: %.2f ms" % timeit(lambda: det.detect_device(devf)))
 print("detect chunked (device frames, no copies): %.2f ms" % timeit(lambda: det.detect_device_chunked(devf, None, bounds)))
+for nch in (2, 4, 8):
+    sz = 64 // nch
+    b = [(i * sz, (i + 1) * sz) for i in range(nch)]
+    print("detect %d chunks of %d on 2 streams: %.2f ms" % (nch, sz, timeit(lambda: det.detect_device_chunked(devf, None, b))))

@@ -274,7 +274,7 @@ class MTCNN(nn.Module):
     _pnet_owner = None
 
     # ---- the device pipeline ------------------------------------------------------------------------------------
-    def detect_device(self, frames_u8, select_largest=None, mark=None):
+    def detect_device(self, frames_u8, select_largest=None, mark=None, slot=0):
         """frames_u8: CUDA uint8 (B,H,W,3) RGB.  Runs the whole three-stage cascade on the current stream and returns
         the DetectWorkspace holding out_count (B,), out_box (B,capf,5), out_pts (B,capf,10), status -- all on device,
         nothing synchronised."""
@@ -283,10 +283,10 @@ class MTCNN(nn.Module):
         dev = frames_u8.device
         B, H, W, _ = frames_u8.shape
         wts = self._weights(dev)
-        key = (B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev)
+        key = (B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev, slot)
         ws = self._ws.get(key)
         if ws is None:
-            if len(self._ws) > 8:
+            if len(self._ws) > 12:
                 self._ws.clear()
             ws = self._ws[key] = DetectWorkspace(B, H, W, self.min_face_size, self.factor, tuple(self.caps), dev,
                                                  tuple(self.crop_ws_per_frame), tuple(self.crop_ws_floor))
@@ -340,14 +340,24 @@ class MTCNN(nn.Module):
             full = self._ws[key] = ResultWorkspace(B, H, W, tuple(self.caps), dev)
         full.status.zero_()
         cur = torch.cuda.current_stream(dev)
+        # consecutive sub-batches run on two alternating streams (each with its own workspace): the low-occupancy stage
+        # kernels of one sub-batch (one CTA per image NMS, persistent-kernel tails) overlap the P-Net / R-Net of the next
+        if getattr(self, "_chunk_streams", None) is None or self._chunk_streams[0].device != dev:
+            self._chunk_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        for s_ in self._chunk_streams:
+            s_.wait_stream(cur)
         for i, (b0, b1) in enumerate(bounds):
-            if ready_events is not None:
-                cur.wait_event(ready_events[i])
-            ws = self.detect_device(frames_dev[b0:b1])
-            full.out_count[b0:b1].copy_(ws.out_count)
-            full.out_box[b0:b1].copy_(ws.out_box)
-            full.out_pts[b0:b1].copy_(ws.out_pts)
-            full.status.bitwise_or_(ws.status)
+            st = self._chunk_streams[i & 1]
+            with torch.cuda.stream(st):
+                if ready_events is not None:
+                    st.wait_event(ready_events[i])
+                ws = self.detect_device(frames_dev[b0:b1], slot=i & 1)
+                full.out_count[b0:b1].copy_(ws.out_count)
+                full.out_box[b0:b1].copy_(ws.out_box)
+                full.out_pts[b0:b1].copy_(ws.out_pts)
+                full.status.bitwise_or_(ws.status)
+        for s_ in self._chunk_streams:
+            cur.wait_stream(s_)
         full.frames = frames_dev
         return full
 

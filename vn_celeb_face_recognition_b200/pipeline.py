@@ -107,7 +107,7 @@ class FacePipeline:
         return out
 
     #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i)
-    sub_batch = 16
+    sub_batch = 8
     #: the first sub-batch is smaller: nothing can overlap its copy, so it should land quickly
     first_sub_batch = 4
 
