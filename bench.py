@@ -239,17 +239,22 @@ def run_ours(args):
     faces = 0
     t0.record()
     for _ in range(args.steps):
-        out = step_device(True)
+        out = step_device(False)
         faces += out["n_faces"]
     t1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.launch_count() - l0
     ms = t0.elapsed_time(t1)
-    # per-stage device time from the event marks (averaged over the timed steps)
+    # per-stage device time: separate instrumented passes (stage markers force the single-stream cascade; the timed loop
+    # above runs the production path, whose two detection half-batches overlap on two streams)
+    n_inst = 3
+    for _ in range(n_inst):
+        out = step_device(True)
+    barrier()
     for (n0, e0), (n1, e1) in zip(ev_log[:-1], ev_log[1:]):
         if n1 != "start":
-            stage_ms[n1] = stage_ms.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
+            stage_ms[n1] = stage_ms.get(n1, 0.0) + e0.elapsed_time(e1) / n_inst
 
     # ---- end to end through the public API: pinned host frames in, host results out (`e2e`)
     e2e_steps = 1 if args.skip_e2e else args.steps
@@ -341,7 +346,9 @@ def run_ours(args):
                               "InceptionResnetV1 stage of one step", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                     "traffic": None, "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
-                    "stage_ms": enc_ms, "share_of_step": enc_ms / (ms / args.steps)}
+                    "stage_ms": enc_ms, "share_of_step": enc_ms / sum(stage_ms.values()),
+                    "note": "stage times come from instrumented single-stream passes; the timed loop overlaps the two "
+                            "detection half-batches on two streams, so ms_per_step < sum(stage_ms)"}
         line = {"metric": METRIC, "value": faces / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": _half_name(enc.half_dtype), "data": "synthetic",

@@ -66,10 +66,17 @@ class FacePipeline:
         the encoder batch): count (B,), boxes (B,capf,5), points (B,capf,10), faces_u8 (F,S,S,3), emb (F,512),
         label (F,), prob (F,), face_img (F,)."""
         from .models.mtcnn import CropWorkspaceOverflow
+        marked = mark is not None                      # stage markers need the single-stream cascade
         mark = mark or (lambda name: None)
         with torch.no_grad():
+            B = frames_u8.shape[0]
             for attempt in range(6):
-                ws = self.det.detect_device(frames_u8, mark=mark)
+                if marked or B < 32:
+                    ws = self.det.detect_device(frames_u8, mark=mark)
+                else:
+                    # two halves on two streams: the low-occupancy stage kernels of one half overlap the other half's
+                    # P-Net / R-Net / O-Net (measured 8.14 -> 7.74 ms for 64 x 1080p)
+                    ws = self.det.detect_device_chunked(frames_u8, None, [(0, B // 2), (B // 2, B)])
                 try:
                     return self._embed_classify(ws, mark)
                 except CropWorkspaceOverflow:          # more candidates than the crop workspaces hold: grow and repeat
