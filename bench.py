@@ -58,6 +58,9 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    #: NVML poll period; VNFR_CLOCK_POLL_MS overrides (probing whether the sampler itself perturbs the timed region)
+    POLL_S = float(os.environ.get("VNFR_CLOCK_POLL_MS", "10")) * 1e-3
+
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc, self.nvml, self._stop = gpu_index, [], None, None, False
         self.sm, self.reasons, self.max_sm = [], set(), None
@@ -106,7 +109,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.POLL_S)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -219,7 +222,11 @@ def run_ours(args):
     def step_device(timed):
         out = fp.run_device(frames_dev, mark=mark if timed else None)
         if world > 1:
-            vdist.all_gather_faces(out["emb"], out["label"], out["prob"])
+            if os.environ.get("VNFR_RAGGED_GATHER"):
+                vdist.all_gather_faces(out["emb"], out["label"], out["prob"])
+            else:
+                # the step's exchange: one sync-free collective over a fixed-capacity payload (dist.py)
+                out["gathered"] = vdist.all_gather_faces_padded(out["emb"], out["label"], out["prob"], B * fp.max_faces_per_frame)
         return out
 
     def barrier():

@@ -32,6 +32,16 @@ def _worker(rank, world, port, out):
     label = idx * 3
     prob = idx.float() / 100
     e, l, p, c = vdist.all_gather_faces(emb, label, prob)
+    # the sync-free fixed-capacity variant must compact to exactly the same result
+    payload, D = vdist.all_gather_faces_padded(emb, label, prob, cap=12)
+    assert payload.shape == (world, 13, 10)
+    e2, l2, p2, c2 = vdist.compact_faces(payload, D)
+    assert torch.equal(e, e2) and torch.equal(l, l2) and torch.equal(p, p2) and torch.equal(c, c2)
+    try:                                                          # n > cap raises on every rank before the collective
+        vdist.all_gather_faces_padded(emb, label, prob, cap=n - 1)
+        raise AssertionError("capacity overflow must raise")
+    except ValueError:
+        pass
     if rank == 0:
         out.put((e.numpy(), l.numpy(), p.numpy(), c.numpy(), (lo, hi)))
     dist.barrier()

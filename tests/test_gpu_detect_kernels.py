@@ -22,11 +22,20 @@ def _plan(B, H, W, minsize, factor=0.709):
     return p
 
 
-@pytest.mark.parametrize("kind,n,minsize", [("small", 3, 50), ("small", 2, 20), ("1080p", 1, 50)])
+# noise:HxW cases exercise the strip kernel's geometry: several column tiles (W*3/16 > 384 chunks), more than 10 levels
+# (two launches), many strips per frame, and the one-task-per-row fallback (rows not 16-byte aligned / upscaling level)
+@pytest.mark.parametrize("kind,n,minsize", [("small", 3, 50), ("small", 2, 20), ("1080p", 1, 50), ("1080p", 2, 20),
+                                            ("noise:300x2560", 2, 40), ("noise:257x4112", 1, 16), ("noise:700x96", 3, 13),
+                                            ("noise:120x482", 2, 30), ("noise:96x128", 2, 12)])
 def test_pyramid_resize_bit_exact(dev, kind, n, minsize):
     from oracle import detect, synth
     from vn_celeb_face_recognition_b200 import _lib
-    fr = synth.frames(kind, n)
+    if kind.startswith("noise:"):
+        h, w = [int(v) for v in kind[6:].split("x")]
+        fr = np.random.RandomState(h * w).randint(0, 256, size=(n, h, w, 3)).astype(np.uint8)
+        fr[0, : h // 2] = 255                                   # saturated columns: the u16 lanes must not overflow
+    else:
+        fr = synth.frames(kind, n)
     B, H, W, _ = fr.shape
     p = _plan(B, H, W, minsize)
     scales = detect.scale_pyramid(H, W, minsize, 0.709)

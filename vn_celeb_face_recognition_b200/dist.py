@@ -35,3 +35,36 @@ def all_gather_faces(emb, label, prob, group=None):
     parts = [g[:int(c)] for g, c in zip(gathered, counts.tolist())]
     allp = torch.cat(parts, 0)
     return allp[:, :D].contiguous(), allp[:, D].long(), allp[:, D + 1].contiguous(), counts
+
+
+def all_gather_faces_padded(emb, label, prob, cap, group=None):
+    """The same exchange without any host synchronisation: ONE collective over a fixed-capacity payload, so the host
+    keeps enqueueing the next step while this one drains (the ragged variant above reads the counts back twice).
+    ``cap`` = rows reserved per rank, identical on every rank (e.g. frames_per_rank * max_faces_per_frame).
+    Returns (payload (world, cap + 1, D + 2) fp32 on device, D): rank r's faces are payload[r, :n_r] with columns
+    [:D] embedding, [D] label, [D + 1] probability; n_r rides in payload[r, cap, 0] (exact: counts < 2^24).
+    ``compact_faces`` turns it into the ragged concatenation when the consumer needs it on the host side."""
+    n, D = emb.shape
+    if n > cap:
+        raise ValueError("all_gather_faces_padded: %d faces on this rank exceed the per-rank capacity %d" % (n, cap))
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    mine = torch.zeros(cap + 1, D + 2, dtype=torch.float32, device=emb.device)
+    mine[:n, :D] = emb
+    mine[:n, D] = label
+    mine[:n, D + 1] = prob
+    mine[cap, 0] = float(n)
+    if world == 1:
+        return mine.unsqueeze(0), D
+    out = torch.empty(world * (cap + 1), D + 2, dtype=torch.float32, device=emb.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.view(world, cap + 1, D + 2), D
+
+
+def compact_faces(payload, D):
+    """(payload, D) of all_gather_faces_padded -> (emb, label, prob, counts) exactly as all_gather_faces returns them
+    (rank-order concatenation).  Reads the per-rank counts back: this is the one synchronising step."""
+    cap = payload.shape[1] - 1
+    counts = payload[:, cap, 0].long()
+    parts = [payload[r, :c] for r, c in enumerate(counts.tolist())]
+    allp = torch.cat(parts, 0)
+    return allp[:, :D].contiguous(), allp[:, D].long(), allp[:, D + 1].contiguous(), counts

@@ -47,8 +47,10 @@ def _block(kind):
 class InceptionResnetV1(nn.Module):
     """See module docstring.  Keyword arguments as in the reference (inception_resnet_v1.py:202)."""
 
-    #: crops per internal chunk: bounds activation memory and keeps a chunk's layer-to-layer traffic inside the 126 MB L2
-    chunk = 128
+    #: crops per internal chunk: bounds activation memory (about 2.7 MB per crop).  Large chunks are faster: the small
+    #: late layers (8x8 / 3x3 maps) only fill the 148 SMs at several hundred crops (measured 768 crops: 4.8 ms in one
+    #: chunk vs 10 ms in six chunks of 128)
+    chunk = 1024
 
     def __init__(self, pretrained=None, classify=False, num_classes=None, dropout_prob=0.6, device=None):
         super().__init__()
