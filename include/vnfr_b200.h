@@ -108,13 +108,14 @@ int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const
                       const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops, int crop_cap,
                       int32_t* status, void* stream);
 
-/* O-Net with conv2 (63 % of its FLOPs) on the tensor cores in split precision: three bf16 parts per fp32 operand, six
- * products, fp32 accumulation (vnfr_conv_run with VnfrConvOp.split3) over all crops in one launch; the other layers stay on
- * the fp32 FMA path.  w2_split: bf16 [64][1728] (conv2 weights, split3 layout); p1: bf16 [crop_cap][23][23][96] and
- * c2: fp32 [crop_cap][441][64] workspaces.  Same outputs and semantics as vnfr_onet_forward.                         */
+/* O-Net with conv2 (63 % of its FLOPs) on the tensor cores in split precision, fp32 accumulation (vnfr_conv_run with
+ * VnfrConvOp.split3 = split_mode) over all crops in one launch; the other layers stay on the fp32 FMA path.
+ *   split_mode 1: three bf16 parts per fp32 operand, six products.  w2_split: bf16 [64][1728], p1: bf16 [crop_cap][23][23][96]
+ *   split_mode 2: two fp16 parts, three products (half the tensor work). w2_split: fp16 [64][896], p1: fp16 [crop_cap][23][23][64]
+ * c2: fp32 [crop_cap][441][64] workspace.  Same outputs and semantics as vnfr_onet_forward.                          */
 int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
-                         const float* weights, const void* w2_split, float* prob, float* reg, float* lmk, int32_t* offs,
-                         float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream);
+                         const float* weights, const void* w2_split, int split_mode, float* prob, float* reg, float* lmk,
+                         int32_t* offs, float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream);
 
 /* Stage-2 tail (detect_face.py:119-136): score > threshold, NMS(0.7), bbreg, rerec, pad. */
 int vnfr_stage2_boxes(int B, int H, int W, int cap2, const int32_t* s2_count, const float* s2_box, const float* s2_prob,
@@ -171,7 +172,10 @@ typedef struct {
   int32_t split3;                 /* shifted-view kernel only: 1 = split-precision convolution.  `in` holds 3 planes of `cin/3`
                                      channels (hi | mid | lo bf16 parts of an fp32 activation), the weights are packed per tap
                                      as the 6 products (a0b0, a0b1, a1b0, a0b2, a1b1, a2b0): k = (tap*6 + j)*sv_ck + c; the
-                                     fp32 accumulator then carries ~fp32 accuracy (dropped terms are O(2^-24))               */
+                                     fp32 accumulator then carries ~fp32 accuracy (dropped terms are O(2^-24)).
+                                     2 = the same with 2 fp16 parts (hi | lo, dtype must be 1): `in` holds 2 planes of `cin/2`
+                                     channels, 3 products (a0b0, a0b1, a1b0): k = (tap*3 + j)*sv_ck + c; dropped term O(2^-22),
+                                     half the tensor-core work                                                               */
   int32_t reserved[1];            /* [0] = sv_ck: 0, or 32 / 64 = request the shifted-view kernel (stride-1 k x k convs, cout <=
                                      256) with weights packed k = (tap*ceil(cin/sv_ck) + chunk)*sv_ck + c               */
 } VnfrConvOp;

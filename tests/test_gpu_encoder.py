@@ -252,19 +252,26 @@ def test_gallery_topk_matches_torch(dev):
     assert (i2[:, 3:] == -1).all() and torch.isinf(v2[:, 3:]).all() and (i2[:, :3] >= 0).all()
 
 
-def test_shifted_view_split_precision_conv(dev):
-    """Split-precision mode of the shifted-view kernel: fp32 activations and weights as 3 bf16 parts each, 6 tensor-core
-    products per K slice, fp32 accumulation -> fp32-level accuracy (the mode the detector heads need: their thresholded
-    decisions must match the fp32 reference).  Also covers PReLU, fp32 output and the device-side image count."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_shifted_view_split_precision_conv(dev, mode):
+    """Split-precision modes of the shifted-view kernel: fp32 activations and weights as 3 bf16 parts each (6 tensor-core
+    products per K slice) or 2 fp16 parts each (3 products), fp32 accumulation -> fp32-level accuracy (the mode the
+    detector heads need: their thresholded decisions must match the fp32 reference).  Also covers PReLU, fp32 output and
+    the device-side image count."""
     from vn_celeb_face_recognition_b200 import encoder_plan as ep
     g = torch.Generator(device="cpu").manual_seed(3)
     n, h, w, cin, cout = 5, 23, 23, 32, 64
     x = torch.randn(n, h, w, cin, generator=g)
+    x[0, :4] *= 1e-3                                                                   # small activations: fp16 subnormal residuals
     wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
     bias = torch.randn(cout, generator=g)
     alpha = torch.rand(cout, generator=g)
-    xs = torch.cat(ep.split3_bf16(x), dim=-1).to(dev).contiguous()                     # (n, h, w, 96): hi | mid | lo
-    pc = ep.pack_conv_split3(wt, bias, dev, ck=32)
+    if mode == 1:
+        xs = torch.cat(ep.split3_bf16(x), dim=-1).to(dev).contiguous()                 # (n, h, w, 96): hi | mid | lo
+        pc = ep.pack_conv_split3(wt, bias, dev, ck=32)
+    else:
+        xs = torch.cat(ep.split2_fp16(x), dim=-1).to(dev).contiguous()                 # (n, h, w, 64): hi | lo
+        pc = ep.pack_conv_split2(wt, bias, dev, ck=32)
     out = torch.full((n * 21 * 21, cout), float("nan"), dtype=torch.float32, device=dev)
     live = torch.tensor([4], dtype=torch.int32, device=dev)                            # only 4 of the 5 images are valid
     ol = ep.OpList()
@@ -277,4 +284,9 @@ def test_shifted_view_split_precision_conv(dev):
     got = out.cpu().double()
     assert torch.isnan(got[4 * 441:]).all(), "images beyond the device-side count must not be written"
     err = (got[:4 * 441] - ref[:4 * 441]).abs().max().item()
+    # an fp32 FMA convolution of the same operands for scale: the split modes must be in the same error class
+    ref32 = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), wt, bias)
+    ref32 = torch.where(ref32 > 0, ref32, ref32 * alpha.view(1, -1, 1, 1)).permute(0, 2, 3, 1).reshape(n * 21 * 21, cout)
+    err32 = (ref32[:4 * 441].double() - ref[:4 * 441]).abs().max().item()
+    print("split mode %d: max err %.3e (fp32 conv2d: %.3e)" % (mode, err, err32))
     assert err < 3e-6 * max(1.0, ref.abs().max().item()), err

@@ -119,19 +119,26 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
         else:
             _lib.call("vnfr_onet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(lmk),
                       P(offs), P(crops), len(y), P(status), _lib.stream_ptr())
-            # the same through the tensor-core conv2 path (split-precision bf16 x3): must agree with the FMA path to fp32 noise
+            # the same through the tensor-core conv2 path (split precision: 3 x bf16 / 2 x fp16 parts): must agree with the
+            # FMA path to fp32 noise
             from vn_celeb_face_recognition_b200 import encoder_plan as ep
-            w2s = ep.pack_conv_split3(sds[net]["conv2.weight"], sds[net]["conv2.bias"], dev, 32).w
-            prob_t = torch.zeros_like(prob); reg_t = torch.zeros_like(reg); lmk_t = torch.zeros_like(lmk)
-            crops_t = torch.empty_like(crops)
-            p1 = torch.empty(len(y) * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
-            c2 = torch.empty(len(y) * 441 * 64, device=dev)
-            _lib.call("vnfr_onet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), P(prob_t), P(reg_t),
-                      P(lmk_t), P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), _lib.stream_ptr())
-            torch.cuda.synchronize()
-            assert torch.equal(crops_t, crops)
-            assert (prob_t - prob).abs().max().item() < 5e-6 and (reg_t - reg).abs().max().item() < 2e-5
-            assert (lmk_t - lmk).abs().max().item() < 2e-5
+            for mode in (1, 2):
+                pack = ep.pack_conv_split2 if mode == 2 else ep.pack_conv_split3
+                w2s = pack(sds[net]["conv2.weight"], sds[net]["conv2.bias"], dev, 32).w
+                prob_t = torch.zeros_like(prob); reg_t = torch.zeros_like(reg); lmk_t = torch.zeros_like(lmk)
+                crops_t = torch.empty_like(crops)
+                if mode == 2:
+                    p1 = torch.empty(len(y) * 23 * 23 * 64, dtype=torch.float16, device=dev)
+                else:
+                    p1 = torch.empty(len(y) * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
+                c2 = torch.empty(len(y) * 441 * 64, device=dev)
+                _lib.call("vnfr_onet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), mode, P(prob_t),
+                          P(reg_t), P(lmk_t), P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), _lib.stream_ptr())
+                torch.cuda.synchronize()
+                assert torch.equal(crops_t, crops)
+                errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item(), (lmk_t - lmk).abs().max().item())
+                print("onet tensor-core conv2, split mode %d: max |d prob| %.2e  |d reg| %.2e  |d lmk| %.2e" % ((mode,) + errs))
+                assert errs[0] < 5e-6 and errs[1] < 2e-5 and errs[2] < 2e-5, (mode, errs)
         torch.cuda.synchronize()
         assert status.item() == 0
         ref_in = taps[key_in][order]

@@ -8,6 +8,7 @@
 // Arithmetic is fp32 FMA: the `score > threshold` decisions of stages 2/3 must match the fp32 reference.
 #include "common.cuh"
 #include <math_constants.h>
+#include <cuda_fp16.h>
 #include <string.h>
 
 extern long long g_vnfr_launches;
@@ -341,7 +342,9 @@ struct HeadArgs {
   float4* reg;           // [B][cap]
   float* lmk;            // [B][cap][10] (O-Net)
   float* crops;          // workspace [crop_cap][3][S][S]: the resized, normalised crops (written by crop_kernel)
-  __nv_bfloat16* p1;     // O-Net tensor-core path: pooled conv1 map [crop][23][23][96] = hi | mid | lo bf16 parts
+  void* p1;              // O-Net tensor-core path: pooled conv1 map, split parts per pixel: [crop][23][23][96] bf16 (hi | mid | lo)
+                         // or [crop][23][23][64] fp16 (hi | lo)
+  int split_mode;        // 1 = three bf16 parts, 2 = two fp16 parts
   const float* c2;       // O-Net tensor-core path: conv2 + PReLU output [crop][21*21][64] fp32 (written by sv_conv)
   int crop_cap;          // crops the workspace holds; flat indices beyond it are dropped and flagged in *status (bit 5)
   int* status;
@@ -622,17 +625,30 @@ __global__ void __launch_bounds__(NT, 1) onet_front_kernel(const HeadArgs a) {
       maxpool_smem<3, 46, 46>(Cf, Bf + c0 * 23 * 23, 8);
       __syncthreads();
     }
-    // 3-way bf16 split, pixel-major: thread -> (pixel, channel) with the channel fastest (64-byte runs per part)
-    unsigned short* dst = reinterpret_cast<unsigned short*>(a.p1) + (size_t)flat * 529 * 96;
-    for (int i = threadIdx.x; i < 529 * 32; i += NT) {
-      const int px = i >> 5, c = i & 31;
-      const float x = Bf[c * 529 + px];
-      const unsigned short hi = bf16_bits(x);
-      const float r1 = x - bf16_to_float(hi);
-      const unsigned short mid = bf16_bits(r1);
-      const unsigned short lo = bf16_bits(r1 - bf16_to_float(mid));
-      unsigned short* q = dst + (size_t)px * 96 + c;
-      q[0] = hi; q[32] = mid; q[64] = lo;
+    // split into 16-bit parts, pixel-major: thread -> (pixel, channel) with the channel fastest (64-byte runs per part)
+    if (a.split_mode == 2) {
+      // two fp16 parts: x = hi + lo to 2^-22 relative (residuals below 6e-5 land on fp16 subnormals, absolute step 6e-8)
+      unsigned short* dst = reinterpret_cast<unsigned short*>(a.p1) + (size_t)flat * 529 * 64;
+      for (int i = threadIdx.x; i < 529 * 32; i += NT) {
+        const int px = i >> 5, c = i & 31;
+        const float x = Bf[c * 529 + px];
+        const __half hi = __float2half_rn(x);
+        const __half lo = __float2half_rn(x - __half2float(hi));
+        unsigned short* q = dst + (size_t)px * 64 + c;
+        q[0] = __half_as_ushort(hi); q[32] = __half_as_ushort(lo);
+      }
+    } else {
+      unsigned short* dst = reinterpret_cast<unsigned short*>(a.p1) + (size_t)flat * 529 * 96;
+      for (int i = threadIdx.x; i < 529 * 32; i += NT) {
+        const int px = i >> 5, c = i & 31;
+        const float x = Bf[c * 529 + px];
+        const unsigned short hi = bf16_bits(x);
+        const float r1 = x - bf16_to_float(hi);
+        const unsigned short mid = bf16_bits(r1);
+        const unsigned short lo = bf16_bits(r1 - bf16_to_float(mid));
+        unsigned short* q = dst + (size_t)px * 96 + c;
+        q[0] = hi; q[32] = mid; q[64] = lo;
+      }
     }
   }
 }
@@ -741,7 +757,7 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
-  a.p1 = nullptr; a.c2 = nullptr;
+  a.p1 = nullptr; a.c2 = nullptr; a.split_mode = 0;
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(rnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
@@ -759,12 +775,14 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
   return VNFR_OK;
 }
 
-// O-Net with conv2 on the tensor cores (see onet_front_kernel).  w2_split: bf16 [64][1728] split-precision weights of conv2
-// (encoder_plan.pack_conv_split3 layout); p1 / c2: workspaces for crop_cap crops (101 568 B and 112 896 B per crop).
+// O-Net with conv2 on the tensor cores (see onet_front_kernel).  split_mode 1: w2_split bf16 [64][1728]
+// (encoder_plan.pack_conv_split3), p1 101 568 B per crop; split_mode 2: w2_split fp16 [64][896] (pack_conv_split2), p1
+// 67 712 B per crop; c2: 112 896 B per crop.
 extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
-                                    const float* weights, const void* w2_split, float* prob, float* reg, float* lmk, int32_t* offs,
-                                    float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream) {
+                                    const float* weights, const void* w2_split, int split_mode, float* prob, float* reg, float* lmk,
+                                    int32_t* offs, float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream) {
   VNFR_REQUIRE(frames && count && pad && weights && w2_split && prob && reg && lmk && offs && crops && p1 && c2 && status, "null pointer");
+  VNFR_REQUIRE(split_mode == 1 || split_mode == 2, "split_mode must be 1 (3 x bf16) or 2 (2 x fp16)");
   VNFR_REQUIRE(crop_cap > 0 && ((uintptr_t)crops % 16) == 0 && ((uintptr_t)p1 % 16) == 0 && ((uintptr_t)c2 % 16) == 0,
                "workspaces must hold at least one crop and be 16-byte aligned");
   if (B == 0) return VNFR_OK;
@@ -775,7 +793,7 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
-  a.p1 = (__nv_bfloat16*)p1; a.c2 = c2;
+  a.p1 = p1; a.c2 = c2; a.split_mode = split_mode;
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(onet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM));
@@ -789,20 +807,22 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   // conv2 on the tensor cores; the tensor maps are re-encoded only when a pointer or the capacity changes
   static VnfrConvOp op;
   static const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
-  static int key_cap = -1;
-  if (key[0] != p1 || key[1] != w2_split || key[2] != (const void*)c2 || key[3] != (const void*)weights || key_cap != crop_cap) {
+  static int key_cap = -1, key_mode = 0;
+  if (key[0] != p1 || key[1] != w2_split || key[2] != (const void*)c2 || key[3] != (const void*)weights || key_cap != crop_cap ||
+      key_mode != split_mode) {
     memset(&op, 0, sizeof(op));
     op.in = p1; op.weights = w2_split; op.bias = weights + OW_::B2; op.prelu_alpha = weights + OW_::A2;
     op.out_f32 = c2; op.out_f32_pitch = 64;
-    op.n_img = crop_cap; op.in_h = 23; op.in_w = 23; op.cin = 96; op.in_pitch = 96;
+    const int parts = split_mode == 2 ? 2 : 3;
+    op.n_img = crop_cap; op.in_h = 23; op.in_w = 23; op.cin = 32 * parts; op.in_pitch = 32 * parts;
     op.kh = 3; op.kw = 3; op.stride = 1; op.pad_h = 0; op.pad_w = 0; op.out_h = 21; op.out_w = 21;
-    op.cout = 64; op.cout_pad = 64; op.k_pad = 1728; op.block_n = 64; op.n_split = 64;
-    op.relu = 0; op.dtype = 0; op.reserved[0] = 32; op.split3 = 1;
+    op.cout = 64; op.cout_pad = 64; op.k_pad = split_mode == 2 ? 896 : 1728; op.block_n = 64; op.n_split = 64;
+    op.relu = 0; op.dtype = split_mode == 2 ? 1 : 0; op.reserved[0] = 32; op.split3 = split_mode;
     op.n_img_dev = offs + B;                     // total candidate count, written by scan_counts_kernel
     const int rc = vnfr_conv_prepare(&op);
     if (rc != VNFR_OK) return rc;
     VNFR_REQUIRE(op.a_mode == 3, "split-precision conv2 did not qualify for the shifted-view kernel");
-    key[0] = p1; key[1] = w2_split; key[2] = c2; key[3] = weights; key_cap = crop_cap;
+    key[0] = p1; key[1] = w2_split; key[2] = c2; key[3] = weights; key_cap = crop_cap; key_mode = split_mode;
   }
   op.n_img_dev = offs + B;
   {

@@ -346,8 +346,12 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   const int row_bytes = 2 * ck;
   const int n_chunks = (op->cin + ck - 1) / ck;        // channel planes of the A band
   const int taps = op->kh * op->kw;
-  if (op->split3 && (n_chunks != 3 || op->cin != 3 * ck)) return false;
-  const int kchunks = op->split3 ? 6 : n_chunks;        // K steps per tap
+  // split precision: 1 = 3 bf16 parts / 6 products, 2 = 2 fp16 parts / 3 products
+  if (op->split3 != 0 && op->split3 != 1 && op->split3 != 2) return false;
+  const int n_parts = op->split3 == 2 ? 2 : 3;
+  if (op->split3 && (n_chunks != n_parts || op->cin != n_parts * ck)) return false;
+  if (op->split3 == 2 && op->dtype != 1) return false;   // the two-part split needs fp16's 11-bit significand
+  const int kchunks = op->split3 == 2 ? 3 : (op->split3 ? 6 : n_chunks);        // K steps per tap
   if (op->k_pad < taps * kchunks * ck) return false;
   const int P = op->in_w + 2 * op->pad_w;
   if (P > 256) return false;
@@ -424,7 +428,9 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   // any number of rows (also odd multiples of 64 bytes in 64B-swizzle mode) reads correctly with base_offset = 0; setting
   // the field to (addr >> 7) & 7 applies the phase twice (tests/test_gpu_encoder.py::test_shifted_view_conv_matches_torch).
   q->use_base_offset = 0;
-  static const int split_plane[6] = {0, 0, 1, 0, 1, 2};      // activation part of product j (weights: 0,1,0,2,1,0)
+  // activation part of product j: 3 bf16 parts (weights: 0,1,0,2,1,0) / 2 fp16 parts (weights: 0,1,0)
+  static const int split_plane3[6] = {0, 0, 1, 0, 1, 2}, split_plane2[3] = {0, 0, 1};
+  const int* split_plane = op->split3 == 2 ? split_plane2 : split_plane3;
   for (int ks = 0; ks < ksteps; ++ks) {
     const int tap = ks / kchunks, j = ks - tap * kchunks;
     const int c = op->split3 ? split_plane[j] : j;

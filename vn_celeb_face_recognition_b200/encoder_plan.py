@@ -101,6 +101,34 @@ def split3_bf16(x):
     return hi, mid, lo
 
 
+def split2_fp16(x):
+    """fp32 tensor -> (hi, lo) fp16 parts with hi + lo == x to ~2^-22 relative (fp16 keeps 11 significant bits per part;
+    small residuals fall into fp16's subnormal range, whose absolute step 6e-8 is far below the rounding of the large
+    terms of a dot product)."""
+    x = x.float()
+    hi = x.to(torch.float16)
+    lo = (x - hi.float()).to(torch.float16)
+    return hi, lo
+
+
+def pack_conv_split2(w, bias, device, ck):
+    """Two-part fp16 variant of pack_conv_split3 (VnfrConvOp.split3 = 2): fp16 [cout][taps*3*ck], K step (tap, j) holding
+    weight part (0,1,0)[j] -- the partner of activation part (0,0,1)[j]; the dropped lo*lo product is O(2^-22)."""
+    w = w.detach().to(device=device, dtype=torch.float32)
+    cout, cin, kh, kw = w.shape
+    assert cin <= ck and cout % 16 == 0
+    wp = torch.zeros(cout, kh * kw, ck, dtype=torch.float32, device=device)
+    wp[:, :, :cin] = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+    parts = split2_fp16(wp)
+    packed = torch.stack([parts[j] for j in (0, 1, 0)], dim=2).reshape(cout, kh * kw * 3 * ck).contiguous()
+    k_pad = _ceil(packed.shape[1], 64)
+    if k_pad != packed.shape[1]:
+        packed = torch.nn.functional.pad(packed, (0, k_pad - packed.shape[1]))
+    pc = PackedConv(packed.contiguous(), bias.detach().to(device=device, dtype=torch.float32).contiguous(), kh, kw, 2 * ck, cout, cout)
+    pc.split3 = 2
+    return pc
+
+
 def pack_conv_split3(w, bias, device, ck):
     """Split-precision weights for the shifted-view kernel (VnfrConvOp.split3): w (cout, cin, kh, kw) fp32 with
     cin <= ck -> bf16 [cout][taps*6*ck], K step (tap, j) holding weight part (0,1,0,2,1,0)[j] -- the partner of activation
@@ -118,7 +146,7 @@ def pack_conv_split3(w, bias, device, ck):
     if k_pad != packed.shape[1]:
         packed = torch.nn.functional.pad(packed, (0, k_pad - packed.shape[1]))
     pc = PackedConv(packed.contiguous(), bias.detach().to(device=device, dtype=torch.float32).contiguous(), kh, kw, 3 * ck, cout, cout)
-    pc.split3 = True
+    pc.split3 = 1
     return pc
 
 
@@ -208,7 +236,7 @@ class OpList:
              sv=None, alpha=None, n_img_dev=None):
         """``sv`` = 32 / 64 requests the shifted-view kernel (csrc/sv_conv.cu) with that many channels per plane; the
         packed weights must then be laid out with cin padded to a multiple of ``sv`` (pc.cin)."""
-        split3 = bool(getattr(pc, "split3", False))
+        split3 = int(getattr(pc, "split3", 0))
         if sv is None:
             sv = SV_DEFAULT.get(src.c) if (stride == 1 and pc.kh * pc.kw > 1 and pc.cout <= 256 and out_f32 is None
                                             and pc.block_n == pc.cout == pc.cout_pad) else 0
@@ -247,7 +275,7 @@ class OpList:
         if residual is not None:
             c.residual, c.res_pitch = residual.ptr, residual.pitch
         c.reserved[0] = int(sv or 0)
-        c.split3 = 1 if split3 else 0
+        c.split3 = split3
         if alpha is not None:
             c.prelu_alpha = alpha.data_ptr()
             self.keep.append(alpha)

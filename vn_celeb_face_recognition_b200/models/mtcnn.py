@@ -167,8 +167,11 @@ class DetectWorkspace:
         self.rcrops = torch.empty(self.rcrop_cap * 3 * 24 * 24, **f32)
         self.ocrops = torch.empty(self.ocrop_cap * 3 * 48 * 48, **f32)
         if MTCNN.onet_tensor_cores:
-            # O-Net conv2 on the tensor cores: pooled conv1 map as 3 bf16 parts, conv2 output in fp32 (vnfr_onet_forward_tc)
-            self.op1 = torch.empty(self.ocrop_cap * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
+            # O-Net conv2 on the tensor cores: pooled conv1 map as 2 fp16 / 3 bf16 parts, conv2 output in fp32 (vnfr_onet_forward_tc)
+            if MTCNN.onet_split_mode == 2:
+                self.op1 = torch.empty(self.ocrop_cap * 23 * 23 * 64, dtype=torch.float16, device=dev)
+            else:
+                self.op1 = torch.empty(self.ocrop_cap * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
             self.oc2 = torch.empty(self.ocrop_cap * 21 * 21 * 64, **f32)
         self.out_box = torch.zeros(B, capf, 5, **f32)
         self.out_pts = torch.zeros(B, capf, 10, **f32)
@@ -206,6 +209,9 @@ class MTCNN(nn.Module):
     crop_ws_floor = (2048, 512)
     #: run O-Net's conv2 on the tensor cores in split precision (fp32-level accuracy); VNFR_ONET_FMA=1 keeps it on the FMA pipe
     onet_tensor_cores = not os.environ.get("VNFR_ONET_FMA")
+    #: split of the fp32 operands of that convolution: 2 = two fp16 parts, three products (default); 1 = three bf16 parts, six
+    #: products (VNFR_ONET_SPLIT=1)
+    onet_split_mode = int(os.environ.get("VNFR_ONET_SPLIT", "2"))
 
     def __init__(self, image_size=160, margin=0, min_face_size=20, thresholds=[0.6, 0.7, 0.7], factor=0.709,
                  post_process=True, select_largest=True, selection_method=None, keep_all=False, device=None):
@@ -260,7 +266,8 @@ class MTCNN(nn.Module):
             assert rw.numel() == _lib.lib().vnfr_rnet_weight_floats() and ow.numel() == _lib.lib().vnfr_onet_weight_floats()
             from .. import encoder_plan
             osd = self.onet.state_dict()
-            w2s = encoder_plan.pack_conv_split3(osd["conv2.weight"], osd["conv2.bias"], dev, 32)
+            pack = encoder_plan.pack_conv_split2 if MTCNN.onet_split_mode == 2 else encoder_plan.pack_conv_split3
+            w2s = pack(osd["conv2.weight"], osd["conv2.bias"], dev, 32)
             self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w}
             MTCNN._pnet_owner = None
         if MTCNN._pnet_owner is not self._packed:
@@ -316,7 +323,7 @@ class MTCNN(nn.Module):
         mark("stage2_nms")
         if hasattr(ws, "op1"):
             _lib.call("vnfr_onet_forward_tc", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
-                      P(wts["onet_w2s"]), P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), P(ws.op1),
+                      P(wts["onet_w2s"]), MTCNN.onet_split_mode, P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), P(ws.op1),
                       P(ws.oc2), ws.ocrop_cap, P(ws.status), st)
         else:
             _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
