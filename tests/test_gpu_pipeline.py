@@ -152,6 +152,61 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
                 assert (lmk[b, s].cpu() - outs[1][k]).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("hw", [(1080, 1920), (300, 482)])
+def test_crop_kernels_wide_tiny_offset_and_empty_boxes(dev, hw):
+    """Crop + area-resize of hand-made boxes, bit-exact against the oracle: every byte alignment of the box start, boxes wider
+    than the warp slice of the row kernel (2048 byte columns), one-pixel boxes, a full-frame box and an empty box; the
+    482-wide frame (rows not 4-byte aligned) takes the byte-gather kernel."""
+    from oracle import detect
+    from vn_celeb_face_recognition_b200 import _lib
+    from vn_celeb_face_recognition_b200.models import mtcnn as M
+    from vn_celeb_face_recognition_b200 import synthetic
+    H, W = hw
+    fr = np.random.RandomState(7).randint(0, 256, size=(2, H, W, 3)).astype(np.uint8)
+    fr[1, : H // 2] = 255
+    # (x, y, ex, ey) as detect_face.pad returns them: crop = img[y-1:ey, x-1:ex]
+    boxes = [(1, 1, W, H), (2, 3, min(W, 905), min(H, 701)), (3, 1, 3, 1), (4, 7, 9, 9), (5, 2, 60, 75), (6, 10, 200, 290),
+             (7, 1, min(W, 699), 40), (10, 20, 9, 19), (W - 30, H - 25, W, H), (101, 55, 149, 160), (12, 9, 12 + 23, 9 + 47)]
+    sds = synthetic.mtcnn_state_dicts()
+    d_fr = torch.from_numpy(fr).to(dev)
+    B, cap = 2, 32
+    cnt = torch.tensor([len(boxes), len(boxes) - 2], dtype=torch.int32)
+    pad = torch.zeros(B, cap, 4, dtype=torch.int32)
+    for b in range(B):
+        for i in range(int(cnt[b])):
+            pad[b, i] = torch.tensor(boxes[i], dtype=torch.int32)
+    n = int(cnt.sum())
+    P = _lib.ptr
+    for net, size in (("rnet", 24), ("onet", 48)):
+        w = (M._pack_rnet if net == "rnet" else M._pack_onet)(sds[net]).to(dev)
+        prob = torch.zeros(B, cap, device=dev); reg = torch.zeros(B, cap, 4, device=dev); lmk = torch.zeros(B, cap, 10, device=dev)
+        offs = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        crops = torch.full((n, 3, size, size), float("nan"), device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_cnt, d_pad = cnt.to(dev), pad.to(dev)
+        if net == "rnet":
+            _lib.call("vnfr_rnet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(offs),
+                      P(crops), n, P(status), _lib.stream_ptr())
+        else:
+            _lib.call("vnfr_onet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(lmk),
+                      P(offs), P(crops), n, P(status), _lib.stream_ptr())
+        torch.cuda.synchronize()
+        assert status.item() == 0
+        got = crops.cpu()
+        k = 0
+        for b in range(B):
+            img = torch.from_numpy(fr[b]).permute(2, 0, 1).float()
+            for i in range(int(cnt[b])):
+                x, y, ex, ey = boxes[i]
+                if ey > y - 1 and ex > x - 1:
+                    ref = detect.normalize(detect.area_resize(img[None, :, y - 1:ey, x - 1:ex], (size, size)))[0]
+                else:
+                    ref = torch.zeros(3, size, size)                  # detect_face.py:110 skips empty boxes
+                assert torch.equal(got[k], ref), "%s crop %d of frame %d (box %s) differs: %g" % (
+                    net, i, b, boxes[i], (got[k] - ref).abs().max())
+                k += 1
+
+
 def test_extract_matches_reference_golden(dev, models):
     """MTCNN.extract on the reference's own boxes: bit-exact against the reference's torch.Tensor crop path."""
     from oracle import synth

@@ -10,6 +10,7 @@
 #include <math_constants.h>
 #include <cuda_fp16.h>
 #include <string.h>
+#include <stdlib.h>
 
 extern long long g_vnfr_launches;
 
@@ -400,6 +401,97 @@ __global__ void __launch_bounds__(CROP_THREADS) crop_kernel(const HeadArgs a) {
   }
 }
 
+// Warp-per-output-row variant (the default): the byte gathers above are bound by L1 wavefronts -- a warp-level byte load
+// whose lanes sit kw*3 bytes apart touches 4-5 cache lines, ~600 wavefronts per output row of a 150-pixel box.  Here one
+// warp owns (crop, output row): its lanes read the source span of that row as CONSECUTIVE aligned 32-bit words (one
+// wavefront per 128 bytes), keep exact column sums of their 4 byte columns over the kh window rows in two registers of
+// packed u16 lanes (kh <= 257, checked on the host), park them in the warp's shared-memory slice and then add up the kw
+// column sums of each of the row's 3*S outputs.  No CTA barrier; boxes wider than the slice take the byte-gather path.
+constexpr int CR_WARPS = 8, CR_CAP = 2048;      // warps per CTA, byte columns per warp slice
+
+template <int S>
+__global__ void __launch_bounds__(CR_WARPS * 32) crop_rows_kernel(const HeadArgs a) {
+  __shared__ __align__(16) uint16_t s_col[CR_WARPS][CR_CAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint16_t* col = s_col[warp];
+  const int total_raw = a.offs[a.B];
+  if (total_raw > a.crop_cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.status, 32);
+  const int total = min(total_raw, a.crop_cap);
+  const long long n_tasks = (long long)total * S;
+  const size_t rowbytes = (size_t)a.W * 3;
+  for (long long task = (long long)blockIdx.x * CR_WARPS + warp; task < n_tasks; task += (long long)gridDim.x * CR_WARPS) {
+    const int flat = (int)(task / S), oy = (int)(task - (long long)flat * S);
+    int b, slot;
+    locate(a.offs, a.B, flat, b, slot);
+    const int4 pad = __ldg(a.pad + (size_t)b * a.cap + slot);
+    float* dst = a.crops + (size_t)flat * 3 * S * S + oy * S;
+    const int x0 = pad.x - 1, y0 = pad.y - 1;
+    const int cw = pad.z - x0, ch = pad.w - y0;
+    if (cw <= 0 || ch <= 0) {                               // detect_face.py:110 skips empty boxes: the crop stays zero
+      for (int t = lane; t < 3 * S; t += 32) { const int c = t / S; dst[c * S * S + (t - c * S)] = 0.f; }
+      continue;
+    }
+    const int ys = (oy * ch) / S, ye = ((oy + 1) * ch + S - 1) / S;
+    const float kh = (float)(ye - ys);
+    const uint8_t* row0 = a.frames + ((size_t)b * a.H + (y0 + ys)) * rowbytes + (size_t)x0 * 3;   // first byte of the span
+    const int delta = (int)((uintptr_t)row0 & 3);           // the same for every row: rowbytes % 4 == 0 (host check)
+    const int span = delta + cw * 3;                        // byte columns counted from the aligned start
+    if (span <= CR_CAP) {
+      const uint8_t* base = row0 - delta;
+      const int nwords = (span + 3) >> 2;
+      for (int wi = lane; wi < nwords; wi += 32) {
+        const uint8_t* p = base + 4 * (size_t)wi;
+        uint32_t e = 0, o = 0;
+        int y = ys;
+        for (; y + 4 <= ye; y += 4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(p + u * rowbytes));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { e += w[u] & 0x00FF00FFu; o += (w[u] >> 8) & 0x00FF00FFu; }
+          p += 4 * rowbytes;
+        }
+        for (; y < ye; ++y) {
+          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+          e += w & 0x00FF00FFu; o += (w >> 8) & 0x00FF00FFu;
+          p += rowbytes;
+        }
+        *reinterpret_cast<uint2*>(col + 4 * wi) = make_uint2(__byte_perm(e, o, 0x5410), __byte_perm(e, o, 0x7632));
+      }
+      __syncwarp();
+      for (int t = lane; t < 3 * S; t += 32) {
+        const int c = t / S, ox = t - c * S;
+        const int xs = (ox * cw) / S, xe = ((ox + 1) * cw + S - 1) / S;
+        const uint16_t* cp = col + delta + 3 * xs + c;
+        unsigned sum = 0;
+        for (int x = xs; x < xe; ++x, cp += 3) sum += *cp;
+        dst[c * S * S + ox] = mul_rn(sub_rn(div_rn(div_rn((float)sum, kh), (float)(xe - xs)), 127.5f), 0.0078125f);
+      }
+      __syncwarp();
+    } else {
+      for (int t = lane; t < 3 * S; t += 32) {
+        const int c = t / S, ox = t - c * S;
+        const int xs = (ox * cw) / S, xe = ((ox + 1) * cw + S - 1) / S;
+        unsigned sum = 0;
+        for (int y = ys; y < ye; ++y) {
+          const uint8_t* q = row0 + (size_t)(y - ys) * rowbytes + 3 * xs + c;
+          for (int x = xs; x < xe; ++x, q += 3) sum += __ldg(q);
+        }
+        dst[c * S * S + ox] = mul_rn(sub_rn(div_rn(div_rn((float)sum, kh), (float)(xe - xs)), 127.5f), 0.0078125f);
+      }
+    }
+  }
+}
+
+// crop stage launcher: the warp-per-row kernel when the frame layout allows aligned word loads and u16 column sums
+template <int S>
+void launch_crops(const HeadArgs& a, cudaStream_t st) {
+  static const bool force_gather = getenv("VNFR_CROP_GATHER") != nullptr;
+  const bool rows_ok = ((size_t)a.W * 3) % 4 == 0 && ((uintptr_t)a.frames % 4) == 0 && (a.H + S - 1) / S + 1 <= 257;
+  if (rows_ok && !force_gather) crop_rows_kernel<S><<<148 * 6, CR_WARPS * 32, 0, st>>>(a);
+  else crop_kernel<S><<<148 * 8, CROP_THREADS, 0, st>>>(a);
+}
+
 // ------------------------------------------------------------------------------------------------------- R-Net
 constexpr int RG = 4;     // candidates per CTA pass
 constexpr int R_A = RG * 3 * 24 * 24;        // 6912   input / pool2 / fc4 out
@@ -764,8 +856,8 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
     VNFR_CUDA(cudaFuncSetAttribute(onet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O_SMEM));
     attr = true;
   }
-  if (onet) crop_kernel<48><<<148 * 8, CROP_THREADS, 0, st>>>(a);
-  else crop_kernel<24><<<148 * 8, CROP_THREADS, 0, st>>>(a);
+  if (onet) launch_crops<48>(a, st);
+  else launch_crops<24>(a, st);
   ++g_vnfr_launches;
   // persistent grid: one CTA per SM (shared memory bound), each loops over the flat candidate list
   if (onet) onet_kernel<<<148 * 1, NT, O_SMEM, st>>>(a);
@@ -800,7 +892,7 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
     VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
     attr = true;
   }
-  crop_kernel<48><<<148 * 8, CROP_THREADS, 0, st>>>(a);
+  launch_crops<48>(a, st);
   onet_front_kernel<<<148, NT, OF_SMEM, st>>>(a);
   g_vnfr_launches += 2;
   VNFR_CHECK_LAUNCH();

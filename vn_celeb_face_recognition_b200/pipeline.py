@@ -76,7 +76,8 @@ class FacePipeline:
                 else:
                     # two halves on two streams: the low-occupancy stage kernels of one half overlap the other half's
                     # P-Net / R-Net / O-Net (measured 8.14 -> 7.74 ms for 64 x 1080p)
-                    ws = self.det.detect_device_chunked(frames_u8, None, [(0, B // 2), (B // 2, B)])
+                    n = self.device_chunks
+                    ws = self.det.detect_device_chunked(frames_u8, None, [(i * B // n, (i + 1) * B // n) for i in range(n)])
                 try:
                     return self._embed_classify(ws, mark)
                 except CropWorkspaceOverflow:          # more candidates than the crop workspaces hold: grow and repeat
@@ -113,6 +114,8 @@ class FacePipeline:
                 out["label"], out["prob"] = label, prob
         return out
 
+    #: device-resident frames: the cascade runs as this many sub-batches alternating between two streams
+    device_chunks = int(os.environ.get("VNFR_DEVICE_CHUNKS", "2"))
     #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i)
     sub_batch = 8
     #: the first sub-batch is smaller: nothing can overlap its copy, so it should land quickly
