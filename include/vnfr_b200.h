@@ -112,10 +112,14 @@ int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const
  * VnfrConvOp.split3 = split_mode) over all crops in one launch; the other layers stay on the fp32 FMA path.
  *   split_mode 1: three bf16 parts per fp32 operand, six products.  w2_split: bf16 [64][1728], p1: bf16 [crop_cap][23][23][96]
  *   split_mode 2: two fp16 parts, three products (half the tensor work). w2_split: fp16 [64][896], p1: fp16 [crop_cap][23][23][64]
- * c2: fp32 [crop_cap][441][64] workspace.  Same outputs and semantics as vnfr_onet_forward.                          */
+ * c2: fp32 [crop_cap][441][64] workspace.
+ * w3_split (nullable): conv3 (64 -> 64, 3x3; 18 % of the FLOPs) on the tensor cores as well, always as two fp16 parts:
+ * fp16 [64][1728] (pack_conv_split2, sv_ck 64) with workspaces p3: fp16 [crop_cap][10][10][128] and c3: fp32 [crop_cap][64][64];
+ * NULL keeps conv3 on the FMA path (p3 / c3 are then ignored).  Same outputs and semantics as vnfr_onet_forward.     */
 int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
                          const float* weights, const void* w2_split, int split_mode, float* prob, float* reg, float* lmk,
-                         int32_t* offs, float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream);
+                         int32_t* offs, float* crops, void* p1, float* c2, const void* w3_split, void* p3, float* c3,
+                         int crop_cap, int32_t* status, void* stream);
 
 /* Stage-2 tail (detect_face.py:119-136): score > threshold, NMS(0.7), bbreg, rerec, pad. */
 int vnfr_stage2_boxes(int B, int H, int W, int cap2, const int32_t* s2_count, const float* s2_box, const float* s2_prob,

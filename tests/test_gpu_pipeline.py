@@ -122,7 +122,7 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
             # the same through the tensor-core conv2 path (split precision: 3 x bf16 / 2 x fp16 parts): must agree with the
             # FMA path to fp32 noise
             from vn_celeb_face_recognition_b200 import encoder_plan as ep
-            for mode in (1, 2):
+            for mode, tc3 in ((1, False), (2, False), (2, True)):
                 pack = ep.pack_conv_split2 if mode == 2 else ep.pack_conv_split3
                 w2s = pack(sds[net]["conv2.weight"], sds[net]["conv2.bias"], dev, 32).w
                 prob_t = torch.zeros_like(prob); reg_t = torch.zeros_like(reg); lmk_t = torch.zeros_like(lmk)
@@ -132,13 +132,20 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
                 else:
                     p1 = torch.empty(len(y) * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
                 c2 = torch.empty(len(y) * 441 * 64, device=dev)
+                w3s = p3 = c3 = None
+                if tc3:                                              # conv3 on the tensor cores as well
+                    w3s = ep.pack_conv_split2(sds[net]["conv3.weight"], sds[net]["conv3.bias"], dev, 64).w
+                    p3 = torch.empty(len(y) * 100 * 128, dtype=torch.float16, device=dev)
+                    c3 = torch.empty(len(y) * 64 * 64, device=dev)
                 _lib.call("vnfr_onet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), mode, P(prob_t),
-                          P(reg_t), P(lmk_t), P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), _lib.stream_ptr())
+                          P(reg_t), P(lmk_t), P(offs), P(crops_t), P(p1), P(c2), P(w3s), P(p3), P(c3), len(y), P(status),
+                          _lib.stream_ptr())
                 torch.cuda.synchronize()
                 assert torch.equal(crops_t, crops)
                 errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item(), (lmk_t - lmk).abs().max().item())
-                print("onet tensor-core conv2, split mode %d: max |d prob| %.2e  |d reg| %.2e  |d lmk| %.2e" % ((mode,) + errs))
-                assert errs[0] < 5e-6 and errs[1] < 2e-5 and errs[2] < 2e-5, (mode, errs)
+                print("onet tensor-core conv2 (split mode %d)%s: max |d prob| %.2e  |d reg| %.2e  |d lmk| %.2e" % (
+                    (mode, " + conv3" if tc3 else "") + errs))
+                assert errs[0] < 5e-6 and errs[1] < 2e-5 and errs[2] < 2e-5, (mode, tc3, errs)
         torch.cuda.synchronize()
         assert status.item() == 0
         ref_in = taps[key_in][order]

@@ -347,6 +347,8 @@ struct HeadArgs {
                          // or [crop][23][23][64] fp16 (hi | lo)
   int split_mode;        // 1 = three bf16 parts, 2 = two fp16 parts
   const float* c2;       // O-Net tensor-core path: conv2 + PReLU output [crop][21*21][64] fp32 (written by sv_conv)
+  void* p3;              // O-Net tensor-core conv3: pooled conv2 map as fp16 hi | lo parts [crop][10][10][128] (nullable)
+  const float* c3;       // O-Net tensor-core conv3: conv3 + PReLU output [crop][8*8][64] fp32 (nullable: conv3 on the FMA pipe)
   int crop_cap;          // crops the workspace holds; flat indices beyond it are dropped and flagged in *status (bit 5)
   int* status;
 };
@@ -748,6 +750,32 @@ __global__ void __launch_bounds__(NT, 1) onet_front_kernel(const HeadArgs a) {
 constexpr int OB_A = 64 * 10 * 10 + 512, OB_B = 64 * 8 * 8, OB_C = 16384 + 9216;
 constexpr int OB_SMEM = (OB_A + OB_B + OB_C + O_F) * 4;
 
+// maxpool 3/2 (21 -> 10: every window is complete) of the conv2 output + two-part fp16 split, NHWC [crop][10][10][hi 64 | lo 64]:
+// the input of conv3 on the tensor cores (64 -> 64, 3x3: 18 % of O-Net's FLOPs, 0.6 ms on the FMA pipe)
+__global__ void __launch_bounds__(256) onet_mid_kernel(const HeadArgs a) {
+  const int total = min(a.offs[a.B], a.crop_cap);
+  const long long n = (long long)total * 100 * 64;
+  unsigned short* p3 = reinterpret_cast<unsigned short*>(a.p3);
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < n; idx += (long long)gridDim.x * 256) {
+    const int c = (int)(idx & 63);
+    const long long t = idx >> 6;
+    const int flat = (int)(t / 100), pos = (int)(t - (long long)flat * 100);
+    const int oy = pos / 10, ox = pos - oy * 10;
+    const float* src = a.c2 + (size_t)flat * 441 * 64 + c;
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) m = fmaxf(m, __ldg(src + (size_t)((2 * oy + ky) * 21 + 2 * ox + kx) * 64));
+    const __half hi = __float2half_rn(m);
+    const __half lo = __float2half_rn(m - __half2float(hi));
+    unsigned short* q = p3 + (size_t)t * 128 + c;
+    q[0] = __half_as_ushort(hi); q[64] = __half_as_ushort(lo);
+  }
+}
+
+// TC3: conv3 + PReLU already done on the tensor cores (a.c3); this kernel starts at the 2/2 max-pool
+template <bool TC3>
 __global__ void __launch_bounds__(NT, 1) onet_back_kernel(const HeadArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* A = sm; float* Bf = sm + OB_A; float* Cf = Bf + OB_B; float* F = Cf + OB_C;
@@ -767,23 +795,35 @@ __global__ void __launch_bounds__(NT, 1) onet_back_kernel(const HeadArgs a) {
         const int4 pd = a.pad[(size_t)b * a.cap + slot];
         s_empty[g] = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);
       }
-      // maxpool 3/2 (21 -> 10: every window is complete) straight from the fp32 NHWC conv2 output; channel fastest
-      const float* src = a.c2 + (size_t)flat * 441 * 64;
-      for (int i = threadIdx.x; i < 100 * 64; i += NT) {
-        const int pos = i >> 6, c = i & 63;
-        const int oy = pos / 10, ox = pos - oy * 10;
-        float m = -CUDART_INF_F;
+      if (TC3) {
+        // maxpool 2/2 (8 -> 4) straight from the fp32 NHWC conv3 output; channel fastest
+        const float* src = a.c3 + (size_t)flat * 64 * 64;
+        for (int i = threadIdx.x; i < 16 * 64; i += NT) {
+          const int pos = i >> 6, c = i & 63;
+          const int oy = pos >> 2, ox = pos & 3;
+          const float* q = src + (size_t)((2 * oy) * 8 + 2 * ox) * 64 + c;
+          A[c * 16 + pos] = fmaxf(fmaxf(__ldg(q), __ldg(q + 64)), fmaxf(__ldg(q + 8 * 64), __ldg(q + 9 * 64)));
+        }
+        __syncthreads();
+      } else {
+        // maxpool 3/2 (21 -> 10: every window is complete) straight from the fp32 NHWC conv2 output; channel fastest
+        const float* src = a.c2 + (size_t)flat * 441 * 64;
+        for (int i = threadIdx.x; i < 100 * 64; i += NT) {
+          const int pos = i >> 6, c = i & 63;
+          const int oy = pos / 10, ox = pos - oy * 10;
+          float m = -CUDART_INF_F;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) m = fmaxf(m, __ldg(src + (size_t)((2 * oy + ky) * 21 + 2 * ox + kx) * 64 + c));
-        A[c * 100 + pos] = m;
+            for (int kx = 0; kx < 3; ++kx) m = fmaxf(m, __ldg(src + (size_t)((2 * oy + ky) * 21 + 2 * ox + kx) * 64 + c));
+          A[c * 100 + pos] = m;
+        }
+        __syncthreads();
+        conv_prelu_smem_ws<64, 64, 3, 3, 10, 10, 1, 8, 4, 4, 2>(A, Bf, Cf, Cf + 16384, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);
+        __syncthreads();
+        maxpool_smem<2, 8, 8>(Bf, A, 64);
+        __syncthreads();
       }
-      __syncthreads();
-      conv_prelu_smem_ws<64, 64, 3, 3, 10, 10, 1, 8, 4, 4, 2>(A, Bf, Cf, Cf + 16384, w + OW_::W3, w + OW_::B3, w + OW_::A3, 0, 64);
-      __syncthreads();
-      maxpool_smem<2, 8, 8>(Bf, A, 64);
-      __syncthreads();
       conv_prelu_smem<64, 128, 2, 2, 4, 4, 1, 4, 3, 4>(A, F + g * 1152, Cf, w + OW_::W4, w + OW_::B4, w + OW_::A4, 0, 128);
       __syncthreads();
     }
@@ -849,7 +889,7 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
-  a.p1 = nullptr; a.c2 = nullptr; a.split_mode = 0;
+  a.p1 = nullptr; a.c2 = nullptr; a.split_mode = 0; a.p3 = nullptr; a.c3 = nullptr;
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(rnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
@@ -872,9 +912,13 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
 // 67 712 B per crop; c2: 112 896 B per crop.
 extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
                                     const float* weights, const void* w2_split, int split_mode, float* prob, float* reg, float* lmk,
-                                    int32_t* offs, float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream) {
+                                    int32_t* offs, float* crops, void* p1, float* c2, const void* w3_split, void* p3, float* c3,
+                                    int crop_cap, int32_t* status, void* stream) {
   VNFR_REQUIRE(frames && count && pad && weights && w2_split && prob && reg && lmk && offs && crops && p1 && c2 && status, "null pointer");
   VNFR_REQUIRE(split_mode == 1 || split_mode == 2, "split_mode must be 1 (3 x bf16) or 2 (2 x fp16)");
+  const bool tc3 = w3_split != nullptr;
+  VNFR_REQUIRE(!tc3 || (p3 != nullptr && c3 != nullptr && ((uintptr_t)p3 % 16) == 0 && ((uintptr_t)c3 % 16) == 0),
+               "conv3 on the tensor cores needs the p3 / c3 workspaces (16-byte aligned)");
   VNFR_REQUIRE(crop_cap > 0 && ((uintptr_t)crops % 16) == 0 && ((uintptr_t)p1 % 16) == 0 && ((uintptr_t)c2 % 16) == 0,
                "workspaces must hold at least one crop and be 16-byte aligned");
   if (B == 0) return VNFR_OK;
@@ -885,11 +929,12 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
-  a.p1 = p1; a.c2 = c2; a.split_mode = split_mode;
+  a.p1 = p1; a.c2 = c2; a.split_mode = split_mode; a.p3 = tc3 ? p3 : nullptr; a.c3 = tc3 ? c3 : nullptr;
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(onet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM));
-    VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
     attr = true;
   }
   launch_crops<48>(a, st);
@@ -921,7 +966,35 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
     const int rc = vnfr_conv_run(&op, stream);
     if (rc != VNFR_OK) return rc;
   }
-  onet_back_kernel<<<148, NT, OB_SMEM, st>>>(a);
+  if (tc3) {
+    // conv3 (64 -> 64, 3x3 on the pooled 10x10 map) on the tensor cores, two fp16 parts / three products
+    onet_mid_kernel<<<148 * 8, 256, 0, st>>>(a);
+    ++g_vnfr_launches;
+    VNFR_CHECK_LAUNCH();
+    static VnfrConvOp op3;
+    static const void* key3[4] = {nullptr, nullptr, nullptr, nullptr};
+    static int key3_cap = -1;
+    if (key3[0] != p3 || key3[1] != w3_split || key3[2] != (const void*)c3 || key3[3] != (const void*)weights || key3_cap != crop_cap) {
+      memset(&op3, 0, sizeof(op3));
+      op3.in = p3; op3.weights = w3_split; op3.bias = weights + OW_::B3; op3.prelu_alpha = weights + OW_::A3;
+      op3.out_f32 = c3; op3.out_f32_pitch = 64;
+      op3.n_img = crop_cap; op3.in_h = 10; op3.in_w = 10; op3.cin = 128; op3.in_pitch = 128;
+      op3.kh = 3; op3.kw = 3; op3.stride = 1; op3.pad_h = 0; op3.pad_w = 0; op3.out_h = 8; op3.out_w = 8;
+      op3.cout = 64; op3.cout_pad = 64; op3.k_pad = 1728; op3.block_n = 64; op3.n_split = 64;
+      op3.relu = 0; op3.dtype = 1; op3.reserved[0] = 64; op3.split3 = 2;
+      op3.n_img_dev = offs + B;
+      const int rc = vnfr_conv_prepare(&op3);
+      if (rc != VNFR_OK) return rc;
+      VNFR_REQUIRE(op3.a_mode == 3, "split-precision conv3 did not qualify for the shifted-view kernel");
+      key3[0] = p3; key3[1] = w3_split; key3[2] = c3; key3[3] = weights; key3_cap = crop_cap;
+    }
+    op3.n_img_dev = offs + B;
+    const int rc = vnfr_conv_run(&op3, stream);
+    if (rc != VNFR_OK) return rc;
+    onet_back_kernel<true><<<148, NT, OB_SMEM, st>>>(a);
+  } else {
+    onet_back_kernel<false><<<148, NT, OB_SMEM, st>>>(a);
+  }
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

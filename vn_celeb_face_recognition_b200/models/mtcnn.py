@@ -173,6 +173,11 @@ class DetectWorkspace:
             else:
                 self.op1 = torch.empty(self.ocrop_cap * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
             self.oc2 = torch.empty(self.ocrop_cap * 21 * 21 * 64, **f32)
+            self.op3 = self.oc3 = None
+            if MTCNN.onet_split_mode == 2 and MTCNN.onet_conv3_tensor_cores:
+                # conv3 on the tensor cores too: pooled conv2 map as 2 fp16 parts, conv3 output in fp32
+                self.op3 = torch.empty(self.ocrop_cap * 10 * 10 * 128, dtype=torch.float16, device=dev)
+                self.oc3 = torch.empty(self.ocrop_cap * 8 * 8 * 64, **f32)
         self.out_box = torch.zeros(B, capf, 5, **f32)
         self.out_pts = torch.zeros(B, capf, 10, **f32)
 
@@ -212,6 +217,8 @@ class MTCNN(nn.Module):
     #: split of the fp32 operands of that convolution: 2 = two fp16 parts, three products (default); 1 = three bf16 parts, six
     #: products (VNFR_ONET_SPLIT=1)
     onet_split_mode = int(os.environ.get("VNFR_ONET_SPLIT", "2"))
+    #: O-Net conv3 on the tensor cores as well (needs onet_split_mode 2); VNFR_ONET_CONV3_FMA=1 keeps it on the FMA pipe
+    onet_conv3_tensor_cores = not os.environ.get("VNFR_ONET_CONV3_FMA")
 
     def __init__(self, image_size=160, margin=0, min_face_size=20, thresholds=[0.6, 0.7, 0.7], factor=0.709,
                  post_process=True, select_largest=True, selection_method=None, keep_all=False, device=None):
@@ -268,7 +275,8 @@ class MTCNN(nn.Module):
             osd = self.onet.state_dict()
             pack = encoder_plan.pack_conv_split2 if MTCNN.onet_split_mode == 2 else encoder_plan.pack_conv_split3
             w2s = pack(osd["conv2.weight"], osd["conv2.bias"], dev, 32)
-            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w}
+            w3s = encoder_plan.pack_conv_split2(osd["conv3.weight"], osd["conv3.bias"], dev, 64)
+            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w, "onet_w3s": w3s.w}
             MTCNN._pnet_owner = None
         if MTCNN._pnet_owner is not self._packed:
             # P-Net weights live in __constant__ memory (one set per process): re-upload when another instance used it
@@ -324,7 +332,8 @@ class MTCNN(nn.Module):
         if hasattr(ws, "op1"):
             _lib.call("vnfr_onet_forward_tc", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
                       P(wts["onet_w2s"]), MTCNN.onet_split_mode, P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), P(ws.op1),
-                      P(ws.oc2), ws.ocrop_cap, P(ws.status), st)
+                      P(ws.oc2), P(wts["onet_w3s"] if ws.op3 is not None else None), P(ws.op3), P(ws.oc3), ws.ocrop_cap,
+                      P(ws.status), st)
         else:
             _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
                       P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), ws.ocrop_cap, P(ws.status), st)
