@@ -108,6 +108,14 @@ int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const
                       const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops, int crop_cap,
                       int32_t* status, void* stream);
 
+/* R-Net with conv2 (28 -> 48, 3x3; 64 % of its FLOPs) on the tensor cores in split precision (two fp16 parts per fp32 operand,
+ * three products, fp32 accumulation; vnfr_conv_run with VnfrConvOp.split3 = 2) over all crops in one launch; the other layers
+ * stay on the fp32 FMA path.  w2_split: fp16 [48][896] (split2 layout, sv_ck 32); p1: fp16 [crop_cap][11][11][64] and
+ * c2: fp32 [crop_cap][81][48] workspaces.  Same outputs and semantics as vnfr_rnet_forward.                           */
+int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                         const float* weights, const void* w2_split, float* prob, float* reg, int32_t* offs, float* crops,
+                         void* p1, float* c2, int crop_cap, int32_t* status, void* stream);
+
 /* O-Net with conv2 (63 % of its FLOPs) on the tensor cores in split precision, fp32 accumulation (vnfr_conv_run with
  * VnfrConvOp.split3 = split_mode) over all crops in one launch; the other layers stay on the fp32 FMA path.
  *   split_mode 1: three bf16 parts per fp32 operand, six products.  w2_split: bf16 [64][1728], p1: bf16 [crop_cap][23][23][96]

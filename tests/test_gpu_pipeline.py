@@ -116,6 +116,20 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
         if net == "rnet":
             _lib.call("vnfr_rnet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(offs),
                       P(crops), len(y), P(status), _lib.stream_ptr())
+            # the same with conv2 on the tensor cores (two fp16 parts): must agree with the FMA path to fp32 noise
+            from vn_celeb_face_recognition_b200 import encoder_plan as ep
+            w2s = ep.pack_conv_split2(sds[net]["conv2.weight"], sds[net]["conv2.bias"], dev, 32).w
+            prob_t = torch.zeros_like(prob); reg_t = torch.zeros_like(reg)
+            crops_t = torch.empty_like(crops)
+            p1 = torch.empty(len(y) * 121 * 64, dtype=torch.float16, device=dev)
+            c2 = torch.empty(len(y) * 81 * 48, device=dev)
+            _lib.call("vnfr_rnet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), P(prob_t), P(reg_t),
+                      P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), _lib.stream_ptr())
+            torch.cuda.synchronize()
+            assert torch.equal(crops_t, crops)
+            errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item())
+            print("rnet tensor-core conv2: max |d prob| %.2e  |d reg| %.2e" % errs)
+            assert errs[0] < 5e-6 and errs[1] < 2e-5, errs
         else:
             _lib.call("vnfr_onet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(lmk),
                       P(offs), P(crops), len(y), P(status), _lib.stream_ptr())

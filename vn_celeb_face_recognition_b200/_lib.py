@@ -57,6 +57,7 @@ _SIGS = {
     "vnfr_nms_segments": [_I, _I, _P, _P, _P, _F, _I, _P, _P, _P],
     "vnfr_stage1_boxes": [C.POINTER(Pyramid), _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "vnfr_rnet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
+    "vnfr_rnet_forward_tc": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "vnfr_onet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "vnfr_onet_forward_tc": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "vnfr_stage2_boxes": [_I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P],

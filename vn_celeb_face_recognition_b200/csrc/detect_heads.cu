@@ -592,6 +592,123 @@ __global__ void __launch_bounds__(NT, 1) rnet_kernel(const HeadArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ R-Net, tensor-core conv2
+// conv2 (28 -> 48, 3x3) is 64 % of R-Net's FLOPs and took 40 % of rnet_kernel.  Same scheme as O-Net below: two fp16
+// parts per fp32 operand, three products, fp32 accumulation in TMEM (sv_conv.cu, VnfrConvOp.split3 = 2), all crops of the
+// batch in one launch:
+//   rnet_front_kernel: crop -> conv1 + PReLU -> maxpool 3/2 -> fp16 split, NHWC [crop][11][11][hi 32 | lo 32] (28 real channels)
+//   sv_conv_kernel   : conv2 + bias + PReLU -> fp32 NHWC [crop][81][48]
+//   rnet_back_kernel : maxpool 3/2 -> conv3 -> dense4 -> heads (small buffers: two CTAs per SM)
+__global__ void __launch_bounds__(NT, 1) rnet_front_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm; float* Bf = sm + R_A; float* Cf = Bf + R_B;
+  const int total = min(a.offs[a.B], a.crop_cap);
+  const float* w = a.w;
+  unsigned short* p1 = reinterpret_cast<unsigned short*>(a.p1);
+  for (int base = blockIdx.x * RG; base < total; base += gridDim.x * RG) {
+    __syncthreads();
+    {
+      const int nvalid = min(RG, total - base) * 3 * 576;
+      const float4* src = reinterpret_cast<const float4*>(a.crops + (size_t)base * 3 * 576);
+      for (int i = threadIdx.x; i < RG * 3 * 576 / 4; i += NT)
+        reinterpret_cast<float4*>(A)[i] = 4 * i < nvalid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int c0 = 0; c0 < 28; c0 += 8) {
+      const int c1 = min(28, c0 + 8), cn = c1 - c0;
+      conv_prelu_smem<3, 28, 3, 3, 24, 24, RG, 4, 8, 1>(A, Cf, nullptr, w + RW::W1, w + RW::B1, w + RW::A1, c0, c1);   // Cf [RG][cn][22][22]
+      __syncthreads();
+      for (int g = 0; g < RG; ++g) {
+        constexpr int OH = 11;
+        for (int i = threadIdx.x; i < cn * OH * OH; i += NT) {
+          const int c = i / (OH * OH), r = i - c * (OH * OH);
+          const int oy = r / OH, ox = r - oy * OH;
+          float m = -CUDART_INF_F;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int y = 2 * oy + ky, x = 2 * ox + kx;
+              if (y < 22 && x < 22) m = fmaxf(m, Cf[((g * cn + c) * 22 + y) * 22 + x]);
+            }
+          Bf[((g * 28 + c0 + c) * OH + oy) * OH + ox] = m;
+        }
+      }
+      __syncthreads();
+    }
+    // two-part fp16 split, pixel-major, channel fastest (channels 28..31 of each part are zero padding)
+    const int ng = min(RG, total - base);
+    for (int i = threadIdx.x; i < ng * 121 * 32; i += NT) {
+      const int c = i & 31, t = i >> 5;
+      const int g = t / 121, px = t - g * 121;
+      const float x = c < 28 ? Bf[(g * 28 + c) * 121 + px] : 0.f;
+      const __half hi = __float2half_rn(x);
+      const __half lo = __float2half_rn(x - __half2float(hi));
+      unsigned short* q = p1 + ((size_t)(base + g) * 121 + px) * 64 + c;
+      q[0] = __half_as_ushort(hi); q[32] = __half_as_ushort(lo);
+    }
+  }
+}
+
+constexpr int RB_A = RG * 48 * 16, RB_B = RG * 576, RB_C = 16 * RG * 128;       // pool2 / dense4 out, conv3 out, scratch
+constexpr int RB_SMEM = (RB_A + RB_B + RB_C) * 4;
+
+__global__ void __launch_bounds__(NT, 2) rnet_back_kernel(const HeadArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* A = sm; float* Bf = sm + RB_A; float* Cf = Bf + RB_B;
+  const int total = min(a.offs[a.B], a.crop_cap);
+  const float* w = a.w;
+  for (int base = blockIdx.x * RG; base < total; base += gridDim.x * RG) {
+    __shared__ int s_b[RG], s_slot[RG];
+    __syncthreads();
+    if (threadIdx.x < RG) {
+      int b = 0, slot = 0;
+      if (base + threadIdx.x < total) locate(a.offs, a.B, base + threadIdx.x, b, slot);
+      s_b[threadIdx.x] = (base + threadIdx.x < total) ? b : -1;
+      s_slot[threadIdx.x] = slot;
+    }
+    // maxpool 3/2 (9 -> 4: every window is complete) straight from the fp32 NHWC conv2 output; channel fastest
+    for (int i = threadIdx.x; i < RG * 16 * 48; i += NT) {
+      const int c = i % 48, t = i / 48;
+      const int g = t >> 4, pos = t & 15;
+      const int oy = pos >> 2, ox = pos & 3;
+      float m = 0.f;
+      if (base + g < total) {
+        const float* src = a.c2 + ((size_t)(base + g) * 81 + (2 * oy) * 9 + 2 * ox) * 48 + c;
+        m = -CUDART_INF_F;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) m = fmaxf(m, __ldg(src + (ky * 9 + kx) * 48));
+      }
+      A[(g * 48 + c) * 16 + pos] = m;
+    }
+    __syncthreads();
+    conv_prelu_smem<48, 64, 2, 2, 4, 4, RG, 4, 3, 2>(A, Bf, Cf, w + RW::W3, w + RW::B3, w + RW::A3, 0, 64);   // Bf [RG][64][3][3] = [RG][576]
+    __syncthreads();
+    fc_prelu_smem<576, 128, RG>(Bf, A, Cf, w + RW::W4, w + RW::B4, w + RW::A4);                        // A  [RG][128]
+    __syncthreads();
+    if (threadIdx.x < RG * 8) {
+      const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+      float sacc = __ldg(w + RW::B5 + j);
+      for (int k = 0; k < 128; ++k) sacc = fmaf(__ldg(w + RW::W5 + k * 8 + j), A[g * 128 + k], sacc);
+      Cf[threadIdx.x] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x < RG && s_b[threadIdx.x] >= 0) {
+      const int g = threadIdx.x;
+      const float l0 = Cf[g * 8], l1 = Cf[g * 8 + 1];
+      const float mx = fmaxf(l0, l1);
+      const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+      const size_t o = (size_t)s_b[g] * a.cap + s_slot[g];
+      const int4 pd = a.pad[o];
+      const bool empty = !(pd.w > pd.y - 1 && pd.z > pd.x - 1);      // detect_face.py:110 would skip this crop
+      a.prob[o] = empty ? 0.f : e1 / (e0 + e1);
+      a.reg[o] = make_float4(Cf[g * 8 + 2], Cf[g * 8 + 3], Cf[g * 8 + 4], Cf[g * 8 + 5]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------- O-Net
 constexpr int OG = 4;                        // crops whose dense5 + heads run together (dense5's 1.18 MB of weights are
                                              // then read from L2 once per 4 crops instead of once per crop)
@@ -995,6 +1112,61 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   } else {
     onet_back_kernel<false><<<148, NT, OB_SMEM, st>>>(a);
   }
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+// R-Net with conv2 on the tensor cores (see rnet_front_kernel).  w2_split: fp16 [48][896] (encoder_plan.pack_conv_split2, sv_ck
+// 32); p1: fp16 [crop_cap][11][11][64], c2: fp32 [crop_cap][81][48] workspaces (15 488 B and 15 552 B per crop).
+extern "C" int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
+                                    const float* weights, const void* w2_split, float* prob, float* reg, int32_t* offs,
+                                    float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream) {
+  VNFR_REQUIRE(frames && count && pad && weights && w2_split && prob && reg && offs && crops && p1 && c2 && status, "null pointer");
+  VNFR_REQUIRE(crop_cap > 0 && ((uintptr_t)crops % 16) == 0 && ((uintptr_t)p1 % 16) == 0 && ((uintptr_t)c2 % 16) == 0,
+               "workspaces must hold at least one crop and be 16-byte aligned");
+  if (B == 0) return VNFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  scan_counts_kernel<<<1, 32, 0, st>>>(count, B, cap, offs);
+  ++g_vnfr_launches;
+  HeadArgs a;
+  a.frames = frames; a.B = B; a.H = H; a.W = W; a.cap = cap; a.count = count;
+  a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
+  a.reg = reinterpret_cast<float4*>(reg); a.lmk = nullptr; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
+  a.p1 = p1; a.c2 = c2; a.split_mode = 2; a.p3 = nullptr; a.c3 = nullptr;
+  static bool attr = false;
+  if (!attr) {
+    VNFR_CUDA(cudaFuncSetAttribute(rnet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(rnet_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
+    attr = true;
+  }
+  launch_crops<24>(a, st);
+  rnet_front_kernel<<<148, NT, R_SMEM, st>>>(a);
+  g_vnfr_launches += 2;
+  VNFR_CHECK_LAUNCH();
+  static VnfrConvOp op;
+  static const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+  static int key_cap = -1;
+  if (key[0] != p1 || key[1] != w2_split || key[2] != (const void*)c2 || key[3] != (const void*)weights || key_cap != crop_cap) {
+    memset(&op, 0, sizeof(op));
+    op.in = p1; op.weights = w2_split; op.bias = weights + RW::B2; op.prelu_alpha = weights + RW::A2;
+    op.out_f32 = c2; op.out_f32_pitch = 48;
+    op.n_img = crop_cap; op.in_h = 11; op.in_w = 11; op.cin = 64; op.in_pitch = 64;
+    op.kh = 3; op.kw = 3; op.stride = 1; op.pad_h = 0; op.pad_w = 0; op.out_h = 9; op.out_w = 9;
+    op.cout = 48; op.cout_pad = 48; op.k_pad = 896; op.block_n = 48; op.n_split = 48;
+    op.relu = 0; op.dtype = 1; op.reserved[0] = 32; op.split3 = 2;
+    op.n_img_dev = offs + B;                     // total candidate count, written by scan_counts_kernel
+    const int rc = vnfr_conv_prepare(&op);
+    if (rc != VNFR_OK) return rc;
+    VNFR_REQUIRE(op.a_mode == 3, "split-precision conv2 did not qualify for the shifted-view kernel");
+    key[0] = p1; key[1] = w2_split; key[2] = c2; key[3] = weights; key_cap = crop_cap;
+  }
+  op.n_img_dev = offs + B;
+  {
+    const int rc = vnfr_conv_run(&op, stream);
+    if (rc != VNFR_OK) return rc;
+  }
+  rnet_back_kernel<<<148 * 2, NT, RB_SMEM, st>>>(a);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

@@ -166,6 +166,11 @@ class DetectWorkspace:
         self.ocrop_cap = max(1, min(B * cap3, max(crop_floor[1], B * crop_ws[1])))
         self.rcrops = torch.empty(self.rcrop_cap * 3 * 24 * 24, **f32)
         self.ocrops = torch.empty(self.ocrop_cap * 3 * 48 * 48, **f32)
+        self.rp1 = self.rc2 = None
+        if MTCNN.rnet_tensor_cores:
+            # R-Net conv2 on the tensor cores: pooled conv1 map as 2 fp16 parts, conv2 output in fp32 (vnfr_rnet_forward_tc)
+            self.rp1 = torch.empty(self.rcrop_cap * 11 * 11 * 64, dtype=torch.float16, device=dev)
+            self.rc2 = torch.empty(self.rcrop_cap * 9 * 9 * 48, **f32)
         if MTCNN.onet_tensor_cores:
             # O-Net conv2 on the tensor cores: pooled conv1 map as 2 fp16 / 3 bf16 parts, conv2 output in fp32 (vnfr_onet_forward_tc)
             if MTCNN.onet_split_mode == 2:
@@ -214,6 +219,8 @@ class MTCNN(nn.Module):
     crop_ws_floor = (2048, 512)
     #: run O-Net's conv2 on the tensor cores in split precision (fp32-level accuracy); VNFR_ONET_FMA=1 keeps it on the FMA pipe
     onet_tensor_cores = not os.environ.get("VNFR_ONET_FMA")
+    #: R-Net's conv2 on the tensor cores (two fp16 parts, three products); VNFR_RNET_FMA=1 keeps it on the FMA pipe
+    rnet_tensor_cores = not os.environ.get("VNFR_RNET_FMA")
     #: split of the fp32 operands of that convolution: 2 = two fp16 parts, three products (default); 1 = three bf16 parts, six
     #: products (VNFR_ONET_SPLIT=1)
     onet_split_mode = int(os.environ.get("VNFR_ONET_SPLIT", "2"))
@@ -276,7 +283,10 @@ class MTCNN(nn.Module):
             pack = encoder_plan.pack_conv_split2 if MTCNN.onet_split_mode == 2 else encoder_plan.pack_conv_split3
             w2s = pack(osd["conv2.weight"], osd["conv2.bias"], dev, 32)
             w3s = encoder_plan.pack_conv_split2(osd["conv3.weight"], osd["conv3.bias"], dev, 64)
-            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w, "onet_w3s": w3s.w}
+            rsd = self.rnet.state_dict()
+            rw2s = encoder_plan.pack_conv_split2(rsd["conv2.weight"], rsd["conv2.bias"], dev, 32)
+            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w, "onet_w3s": w3s.w,
+                            "rnet_w2s": rw2s.w}
             MTCNN._pnet_owner = None
         if MTCNN._pnet_owner is not self._packed:
             # P-Net weights live in __constant__ memory (one set per process): re-upload when another instance used it
@@ -323,8 +333,13 @@ class MTCNN(nn.Module):
                   P(ws.cand_reg), P(ws.keep1_count), P(ws.keep1), cap2, P(ws.s2_count), P(ws.s2_box), P(ws.s2_pad),
                   P(ws.status), st)
         mark("stage1_nms")
-        _lib.call("vnfr_rnet_forward", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
-                  P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), P(ws.rcrops), ws.rcrop_cap, P(ws.status), st)
+        if ws.rp1 is not None:
+            _lib.call("vnfr_rnet_forward_tc", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
+                      P(wts["rnet_w2s"]), P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), P(ws.rcrops), P(ws.rp1), P(ws.rc2),
+                      ws.rcrop_cap, P(ws.status), st)
+        else:
+            _lib.call("vnfr_rnet_forward", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
+                      P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), P(ws.rcrops), ws.rcrop_cap, P(ws.status), st)
         mark("rnet")
         _lib.call("vnfr_stage2_boxes", B, H, W, cap2, P(ws.s2_count), P(ws.s2_box), P(ws.s2_prob), P(ws.s2_reg), t1, cap3,
                   P(ws.s3_count), P(ws.s3_box), P(ws.s3_pad), P(ws.status), st)
