@@ -302,6 +302,22 @@ def test_alignment_kernel_matches_cv2_path(dev, models):
                 k += 1
 
 
+#: log-probability tolerance of label parity.  The classifier of the BASELINE configs is RANDOM-INIT: the reference's own top-2
+#: margin can be far below what the allowed embedding tolerance (cosine >= 0.999, i.e. |d emb| <= 0.045) moves a logit by.
+#: A predicted label must be the reference's label, or -- only where the reference itself is that undecided -- a class whose
+#: REFERENCE log-probability lies within this tolerance of the reference's maximum (oracle/add_golden_logp.py).
+LABEL_LOGP_TOL = 0.05
+
+
+def assert_labels_match(got, ref_labels, ref_logp):
+    assert len(got) == len(ref_labels)
+    for k, (lab, ref) in enumerate(zip(got, ref_labels.tolist())):
+        if lab == ref:
+            continue
+        gap = float(ref_logp[k].max() - ref_logp[k][lab])
+        assert gap <= LABEL_LOGP_TOL, "face %d: label %d, reference %d (reference log-prob gap %.4f)" % (k, lab, ref, gap)
+
+
 def test_demo_video_path_matches_reference_golden(dev, models):
     """parallel_detect_and_align + recognize_celeb (demo_video.py:117-129) end to end: aligned faces, boxes, labels."""
     import pandas as pd
@@ -321,12 +337,12 @@ def test_demo_video_path_matches_reference_golden(dev, models):
         # level on identical inputs in test_alignment_kernel_matches_cv2_path
         d = np.abs(np.stack(faces[i]).astype(int) - g["aligned_%d" % i].astype(int))
         assert d.max() <= 16 and (d > 1).mean() < 0.01 and d.mean() < 0.1
-        assert [int(n[2:]) for n in names[i]] == g["labels_%d" % i].tolist()
+        assert_labels_match([int(n[2:]) for n in names[i]], g["labels_%d" % i], g["logp_%d" % i])
     # fused device pipeline == staged API
     fp = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", cp)
     res = fp(fr)
     for i in range(2):
-        assert res[i]["labels"].tolist() == g["labels_%d" % i].tolist()
+        assert_labels_match(res[i]["labels"].tolist(), g["labels_%d" % i], g["logp_%d" % i])
         assert_boxes_match(res[i]["boxes"], g["boxes_%d" % i], 0.99)
     # threshold -> "Unknown" = num_classes (demo_image.py:131-137)
     fp2 = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", cp, threshold=1.1)

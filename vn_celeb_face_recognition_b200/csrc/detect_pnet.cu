@@ -10,8 +10,18 @@
 // x 32 channels per thread).  All 6 632 weights are copied once per CTA into shared memory in K-major order with the
 // output channel innermost, so one 16-byte broadcast load feeds 4 FMAs per cell (the first version kept them in
 // __constant__ memory: 26 KB of indexed constant loads thrashed the constant cache -- 12.7 % issue utilisation, see
-// profiles/).  Arithmetic is fp32 FMA throughout: thresholded decisions must match the fp32 reference.
+// profiles/).  conv1 / conv2 / heads are fp32 FMA: thresholded decisions must match the fp32 reference.
+//
+// conv3 (16 -> 32, 3x3: 57 % of the FLOPs) runs on the tensor cores in split precision (default; VNFR_PNET_FMA=1 keeps it
+// on the FMA pipe): the conv2 epilogue writes the 18x18x16 map pixel-major as two fp16 parts (hi | lo, 32 bytes = one
+// K = 16 slice per pixel, 32-byte swizzle rows) into shared memory; output cell (y, x) is accumulator row r = 18 y + x
+// and tap (ky, kx) reads the SAME buffer from a start address shifted by 18 ky + kx rows (the shifted-view trick of
+// sv_conv.cu), so one elected thread issues 3 row tiles x 9 taps x 3 products (hi*hi, hi*lo, lo*hi) tcgen05.mma of
+// M = 128, N = 32, K = 16 into three 32-column TMEM accumulators; the four warps then read their TMEM lanes back, add
+// bias, PReLU and run the heads / softmax / compaction exactly as before.  The two columns x = 16, 17 of every raster
+// row and rows r >= 288 are computed and discarded (16/18 useful).
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <math_constants.h>
 #include <string.h>
 
@@ -46,9 +56,23 @@ constexpr int D_FLOATS = D_B4 + 8;    // 6796 floats (all offsets are multiples 
 
 __device__ float g_pnet_w[D_FLOATS];  // repacked weights (global, L2-resident; copied into shared memory per CTA)
 
+// tensor-core conv3: B operand = conv3 weights as fp16 hi / lo parts, [tap][part][32 cout rows][16 cin] in the 32-byte
+// swizzled K-major layout (16-byte chunk c of row n at n*32 + ((c ^ ((n >> 2) & 1)) << 4)); A operand = the conv2 map,
+// one 32-byte row per pixel of the 18-wide raster (432 rows: the last accumulator rows reach row 383 + 38)
+constexpr int TC_B_BYTES = 9 * 2 * 1024;
+constexpr int TC_A_PART_BYTES = 432 * 32;
+__device__ uint4 g_pnet_w3h[TC_B_BYTES / 16];
+
 constexpr int S_BUF = 3 * IT * ITP > 16 * C2T * C2T ? 3 * IT * ITP : 16 * C2T * C2T;   // input patch, later conv2 map
+constexpr int S_BUF_BYTES = (S_BUF * 4 > 2 * TC_A_PART_BYTES ? S_BUF * 4 : 2 * TC_A_PART_BYTES);   // ... or the two A parts
 constexpr int S_P = 10 * PT * PT;
-constexpr int PNET_SMEM = (D_FLOATS + S_BUF + S_P) * 4;
+// layout (from a 1024-byte aligned base): B weights | input patch / conv2 map (fp32 or fp16 parts) | weights | pooled conv1
+constexpr int PNET_SMEM = 1024 + TC_B_BYTES + S_BUF_BYTES + (D_FLOATS + S_P) * 4;
+// the tensor-core variant does not keep the fp32 conv3 weights in shared memory: 70 KB per CTA, three CTAs per SM
+constexpr int TC_W_SKIP = 144 * 32;
+constexpr int PNET_SMEM_TC = PNET_SMEM - TC_W_SKIP * 4;
+constexpr int PNET_TC_CTAS = 3;
+static_assert(TC_B_BYTES % 1024 == 0 && S_BUF_BYTES % 1024 == 0, "operand buffers must keep the swizzle phase");
 
 struct PnetParams {
   int B, n_levels;
@@ -59,17 +83,94 @@ struct PnetParams {
 
 __device__ __forceinline__ float prelu(float v, float a) { return v > 0.f ? v : v * a; }
 
-__global__ void __launch_bounds__(NTHR, PNET_MIN_CTAS) pnet_kernel(const __grid_constant__ PnetParams p, const float* __restrict__ levels,
+// heads (1x1 -> 2 logits + 4 regressions) + softmax + `>= thr` + warp-ballot compaction of ONE cell per lane; acc = conv3
+// output before PReLU.  Warp-collective: every lane calls it, `valid` masks the cell.
+__device__ __forceinline__ void pnet_cell_epilogue(const PnetParams& p, const float* __restrict__ s_w, const float (&acc)[32], int b, int l,
+                                                   int gy, int gx, bool valid, int oh, int ow, float thr, int cap,
+                                                   int* __restrict__ cand_count, uint32_t* __restrict__ cand_cell,
+                                                   float* __restrict__ cand_score, float4* __restrict__ cand_reg,
+                                                   float* __restrict__ dense_prob, float* __restrict__ dense_reg) {
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = s_w[D_B4 + j];
+#pragma unroll
+  for (int co = 0; co < 32; ++co) {
+    const float v = prelu(acc[co], s_w[D_A3 + co]);
+    const float4 wa = *reinterpret_cast<const float4*>(s_w + D_W4 + co * 8);
+    const float4 wb = *reinterpret_cast<const float4*>(s_w + D_W4 + co * 8 + 4);
+    o[0] = fmaf(wa.x, v, o[0]); o[1] = fmaf(wa.y, v, o[1]); o[2] = fmaf(wa.z, v, o[2]); o[3] = fmaf(wa.w, v, o[3]);
+    o[4] = fmaf(wb.x, v, o[4]); o[5] = fmaf(wb.y, v, o[5]);
+  }
+  // softmax over the two logits (torch: exp(x - max) / sum)
+  const float mx = fmaxf(o[0], o[1]);
+  const float e0 = expf(o[0] - mx), e1 = expf(o[1] - mx);
+  const float prob = e1 / (e0 + e1);
+  if (valid && dense_prob != nullptr) {
+    const size_t cells = (size_t)oh * ow;
+    const size_t cell = (size_t)gy * ow + gx;
+    dense_prob[p.map_off[l] + (size_t)b * cells + cell] = prob;
+    if (dense_reg != nullptr) {
+      float* dr = dense_reg + 4 * (p.map_off[l] + (size_t)b * cells);
+      dr[cell] = o[2]; dr[cells + cell] = o[3]; dr[2 * cells + cell] = o[4]; dr[3 * cells + cell] = o[5];
+    }
+  }
+  // generateBoundingBox: probs >= thresh (detect_face.py:209) -> warp-ballot stream compaction into the segment
+  const bool pass = valid && prob >= thr;
+  const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+  if (ballot != 0u) {
+    const int seg = b * p.n_levels + l;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(cand_count + seg, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pass) {
+      const int slot = base + __popc(ballot & ((1u << lane) - 1u));
+      if (slot < cap) {
+        const size_t oidx = (size_t)seg * cap + slot;
+        cand_cell[oidx] = ((uint32_t)gy << 16) | (uint32_t)gx;
+        cand_score[oidx] = prob;
+        cand_reg[oidx] = make_float4(o[2], o[3], o[4], o[5]);
+      }
+    }
+  }
+}
+
+template <bool TC>
+__global__ void __launch_bounds__(NTHR, TC ? PNET_TC_CTAS : PNET_MIN_CTAS) pnet_kernel(const __grid_constant__ PnetParams p, const float* __restrict__ levels,
                                                     float thr, int cap, int* __restrict__ cand_count,
                                                     uint32_t* __restrict__ cand_cell, float* __restrict__ cand_score,
                                                     float4* __restrict__ cand_reg, float* __restrict__ dense_prob,
                                                     float* __restrict__ dense_reg) {
-  extern __shared__ __align__(16) float smem[];
-  float* s_w = smem;                                  // weights
-  float* s_buf = smem + D_FLOATS;                     // input patch [3][IT][ITP], then conv2 map [16][C2T][C2T]
-  float* s_p = s_buf + S_BUF;                         // pooled conv1 map [10][PT][PT], then head partials
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar;             // tensor-core path: MMAs of the current tile have completed
+  __shared__ uint32_t s_tmem;
+  uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_bw = smem_al;                                                   // conv3 B operand (tensor-core path)
+  float* s_buf = reinterpret_cast<float*>(smem_al + TC_B_BYTES);             // input patch [3][IT][ITP], then conv2 map:
+                                                                             // fp32 [16][C2T][C2T] or fp16 hi | lo A operand
+  float* s_w = reinterpret_cast<float*>(smem_al + TC_B_BYTES + S_BUF_BYTES); // weights
+  float* s_p = s_w + D_FLOATS - (TC ? TC_W_SKIP : 0);                        // pooled conv1 map [10][PT][PT]
+  const float* s_wt = s_w - (TC ? TC_W_SKIP : 0);     // rows after the conv3 weights (bias / PReLU of conv3, heads): s_wt[D_...]
   const int tid = threadIdx.x;
-  for (int i = tid; i < D_FLOATS / 4; i += NTHR) reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(g_pnet_w)[i];
+  for (int i = tid; i < D_FLOATS / 4; i += NTHR) {
+    if (TC && i >= D_W3 / 4 && i < D_B3 / 4) continue;                       // fp32 conv3 weights: not needed on the tensor-core path
+    reinterpret_cast<float4*>(s_w)[(TC && i >= D_B3 / 4) ? i - TC_W_SKIP / 4 : i] = reinterpret_cast<const float4*>(g_pnet_w)[i];
+  }
+  const uint32_t a_hi = smem_u32(s_buf), a_lo = a_hi + TC_A_PART_BYTES, b_addr = smem_u32(s_bw), bar = smem_u32(&s_bar);
+  uint32_t tmem_base = 0, phase = 0;
+  if (TC) {
+    for (int i = tid; i < TC_B_BYTES / 16; i += NTHR) reinterpret_cast<uint4*>(s_bw)[i] = g_pnet_w3h[i];
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
+    if (tid < 32) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(128u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc::fence_proxy_async_smem();                      // the B operand was written through the generic proxy
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    tmem_base = s_tmem;
+  }
 
   const int tiles_per_img = p.tile_off[p.n_levels];
   const int total_tiles = tiles_per_img * p.B;
@@ -193,12 +294,83 @@ __global__ void __launch_bounds__(NTHR, PNET_MIN_CTAS) pnet_kernel(const __grid_
               for (int co = 0; co < 16; ++co) acc[j][co] = fmaf(w[co], v, acc[j][co]);
             }
           }
+      if (TC) {
+        // fp16 hi | lo parts, one 32-byte swizzled row per pixel: 16-byte chunk c at row*32 + ((c ^ address bit 7) << 4)
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 3; ++j) {
+          uint32_t hw[8], lw[8];
 #pragma unroll
-        for (int co = 0; co < 16; ++co) s_buf[co * C2T * C2T + oo[j]] = prelu(acc[j][co], s_w[D_A2 + co]);
+          for (int q = 0; q < 8; ++q) {
+            const float v0 = prelu(acc[j][2 * q], s_w[D_A2 + 2 * q]), v1 = prelu(acc[j][2 * q + 1], s_w[D_A2 + 2 * q + 1]);
+            const __half2 h = __floats2half2_rn(v0, v1);
+            const __half2 lo = __floats2half2_rn(v0 - __low2float(h), v1 - __high2float(h));
+            hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+            lw[q] = *reinterpret_cast<const uint32_t*>(&lo);
+          }
+          const uint32_t row = a_hi + 32u * (uint32_t)oo[j];
+          const uint32_t sw = ((row >> 7) & 1u) << 4;
+          tc::sts128(row + sw, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+          tc::sts128(row + (sw ^ 16u), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+          tc::sts128(row + TC_A_PART_BYTES + sw, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+          tc::sts128(row + TC_A_PART_BYTES + (sw ^ 16u), make_uint4(lw[4], lw[5], lw[6], lw[7]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int co = 0; co < 16; ++co) s_buf[co * C2T * C2T + oo[j]] = prelu(acc[j][co], s_w[D_A2 + co]);
+      }
     }
+    if (TC) { tc::fence_proxy_async_smem(); tc::tc_fence_before(); }
     __syncthreads();
+
+    if (TC) {
+      // ---- conv3 on the tensor cores: 3 row tiles x 9 taps x 3 products, fp32 accumulation in TMEM
+      if (tid < 32) {
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t idesc = tc::make_idesc_f16(32, 1);
+#pragma unroll 1
+          for (int mt = 0; mt < 3; ++mt) {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t shift = 32u * (uint32_t)(128 * mt + (tap / 3) * C2T + (tap % 3));
+              const uint64_t ah = tc::make_sw_desc(a_hi + shift, 32, 0), al = tc::make_sw_desc(a_lo + shift, 32, 0);
+              const uint64_t bh = tc::make_sw_desc(b_addr + (uint32_t)(tap * 2) * 1024u, 32, 0);
+              const uint64_t bl = tc::make_sw_desc(b_addr + (uint32_t)(tap * 2 + 1) * 1024u, 32, 0);
+              tc::umma_bf16(tmem_base + 32u * mt, ah, bh, idesc, tap != 0);
+              tc::umma_bf16(tmem_base + 32u * mt, ah, bl, idesc, 1);
+              tc::umma_bf16(tmem_base + 32u * mt, al, bh, idesc, 1);
+            }
+          }
+          tc::umma_commit(bar);
+        }
+        __syncwarp();
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc::tc_fence_after();
+      const uint32_t t_lane = tmem_base + ((uint32_t)(tid & ~31) << 16);          // this warp's 32 TMEM lanes
+#pragma unroll 1
+      for (int mt = 0; mt < 3; ++mt) {
+        float acc[32];
+        __syncwarp();
+        tc::tmem_ld16_issue(t_lane + 32u * mt, acc);
+        tc::tmem_ld16_issue(t_lane + 32u * mt + 16u, acc + 16);
+        tc::tmem_ld_wait(acc);
+        tc::tmem_ld_wait(acc + 16);
+#pragma unroll
+        for (int co = 0; co < 32; ++co) acc[co] += s_wt[D_B3 + co];
+        const int r = 128 * mt + tid;                   // accumulator row = raster index in the 18-wide conv2 map
+        const int cy = r / C2T, cx = r - cy * C2T;
+        const int gy = ty0 + cy, gx = tx0 + cx;
+        const bool valid = cy < T && cx < T && gy < oh && gx < ow;
+        pnet_cell_epilogue(p, s_wt, acc, b, l, gy, gx, valid, oh, ow, thr, cap, cand_count, cand_cell, cand_score, cand_reg,
+                           dense_prob, dense_reg);
+      }
+      tc::tc_fence_before();                            // TMEM reads are ordered before the next tile's MMAs (barrier at loop top)
+      continue;
+    }
 
     // ---- conv3 (16->32, 3x3) + PReLU + heads: thread = cells (y, x) and (y + 8, x), 32 channels each in registers
     const int y = tid >> 4, x = tid & 15;
@@ -241,51 +413,17 @@ __global__ void __launch_bounds__(NTHR, PNET_MIN_CTAS) pnet_kernel(const __grid_
       }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = s_w[D_B4 + j];
-#pragma unroll
-      for (int co = 0; co < 32; ++co) {
-        const float v = prelu(acc[h][co], s_w[D_A3 + co]);
-        const float4 wa = *reinterpret_cast<const float4*>(s_w + D_W4 + co * 8);
-        const float4 wb = *reinterpret_cast<const float4*>(s_w + D_W4 + co * 8 + 4);
-        o[0] = fmaf(wa.x, v, o[0]); o[1] = fmaf(wa.y, v, o[1]); o[2] = fmaf(wa.z, v, o[2]); o[3] = fmaf(wa.w, v, o[3]);
-        o[4] = fmaf(wb.x, v, o[4]); o[5] = fmaf(wb.y, v, o[5]);
-      }
-      // softmax over the two logits (torch: exp(x - max) / sum)
-      const float mx = fmaxf(o[0], o[1]);
-      const float e0 = expf(o[0] - mx), e1 = expf(o[1] - mx);
-      const float prob = e1 / (e0 + e1);
       const int gy = ty0 + y + 8 * h, gx = tx0 + x;
-      const bool valid = gy < oh && gx < ow;
-      if (valid && dense_prob != nullptr) {
-        const size_t cells = (size_t)oh * ow;
-        const size_t cell = (size_t)gy * ow + gx;
-        dense_prob[p.map_off[l] + (size_t)b * cells + cell] = prob;
-        if (dense_reg != nullptr) {
-          float* dr = dense_reg + 4 * (p.map_off[l] + (size_t)b * cells);
-          dr[cell] = o[2]; dr[cells + cell] = o[3]; dr[2 * cells + cell] = o[4]; dr[3 * cells + cell] = o[5];
-        }
-      }
-      // generateBoundingBox: probs >= thresh (detect_face.py:209) -> warp-ballot stream compaction into the segment
-      const bool pass = valid && prob >= thr;
-      const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-      if (ballot != 0u) {
-        const int seg = b * p.n_levels + l;
-        const int lane = tid & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cand_count + seg, __popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) {
-          const int slot = base + __popc(ballot & ((1u << lane) - 1u));
-          if (slot < cap) {
-            const size_t oidx = (size_t)seg * cap + slot;
-            cand_cell[oidx] = ((uint32_t)gy << 16) | (uint32_t)gx;
-            cand_score[oidx] = prob;
-            cand_reg[oidx] = make_float4(o[2], o[3], o[4], o[5]);
-          }
-        }
-      }
+      pnet_cell_epilogue(p, s_wt, acc[h], b, l, gy, gx, gy < oh && gx < ow, oh, ow, thr, cap, cand_count, cand_cell, cand_score,
+                         cand_reg, dense_prob, dense_reg);
+    }
+  }
+  if (TC) {
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+      tc::tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
     }
   }
 }
@@ -307,6 +445,21 @@ extern "C" int vnfr_pnet_set_weights(const float* packed_host, int n_floats, voi
   d[D_B4 + 0] = h[B41]; d[D_B4 + 1] = h[B41 + 1];
   for (int j = 0; j < 4; ++j) d[D_B4 + 2 + j] = h[B42 + j];
   VNFR_CUDA(cudaMemcpyToSymbolAsync(g_pnet_w, d, sizeof(d), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  // conv3 weights as fp16 hi / lo parts in the swizzled B-operand layout of the tensor-core path
+  static uint16_t bw[TC_B_BYTES / 2];
+  memset(bw, 0, sizeof(bw));
+  for (int tap = 0; tap < 9; ++tap)
+    for (int n = 0; n < 32; ++n)
+      for (int ci = 0; ci < 16; ++ci) {
+        const float wv = h[W3 + n * 144 + ci * 9 + tap];
+        const __half hi = __float2half_rn(wv);
+        const __half lo = __float2half_rn(wv - __half2float(hi));
+        const int c = ci >> 3, e = ci & 7;
+        const int off = n * 32 + ((c ^ ((n >> 2) & 1)) << 4) + 2 * e;          // bytes inside the (tap, part) block
+        bw[((tap * 2 + 0) * 1024 + off) / 2] = __half_as_ushort(hi);
+        bw[((tap * 2 + 1) * 1024 + off) / 2] = __half_as_ushort(lo);
+      }
+  VNFR_CUDA(cudaMemcpyToSymbolAsync(g_pnet_w3h, bw, sizeof(bw), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return VNFR_OK;
 }
 
@@ -325,14 +478,21 @@ extern "C" int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr, const float* leve
   }
   p.tile_off[pyr->n_levels] = tiles;
   static bool attr = false;
+  static const bool fma_conv3 = getenv("VNFR_PNET_FMA") != nullptr;
   if (!attr) {
-    VNFR_CUDA(cudaFuncSetAttribute(pnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PNET_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(pnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PNET_SMEM_TC));
+    VNFR_CUDA(cudaFuncSetAttribute(pnet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PNET_SMEM));
     attr = true;
   }
   const int total = pyr->B * tiles;
-  const int grid = total < 148 * PNET_MIN_CTAS ? total : 148 * PNET_MIN_CTAS;      // persistent CTAs
-  pnet_kernel<<<grid, NTHR, PNET_SMEM, (cudaStream_t)stream>>>(p, levels, threshold, cap, cand_count, cand_cell, cand_score,
-                                                              reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg);
+  const int per_sm = fma_conv3 ? PNET_MIN_CTAS : PNET_TC_CTAS;
+  const int grid = total < 148 * per_sm ? total : 148 * per_sm;      // persistent CTAs
+  if (fma_conv3)
+    pnet_kernel<false><<<grid, NTHR, PNET_SMEM, (cudaStream_t)stream>>>(p, levels, threshold, cap, cand_count, cand_cell, cand_score,
+                                                                       reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg);
+  else
+    pnet_kernel<true><<<grid, NTHR, PNET_SMEM_TC, (cudaStream_t)stream>>>(p, levels, threshold, cap, cand_count, cand_cell, cand_score,
+                                                                      reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;
