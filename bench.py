@@ -357,10 +357,21 @@ def run_ours(args):
         if enc_ms > 0:
             flops = faces_step_rank * ENC_FLOP_PER_FACE
             achieved = flops / (enc_ms * 1e-3) / 1e12
-            roof = {"kernel": "tcgen05 convolutions (sv_conv_kernel + igemm_conv_kernel): all 106 conv launches of the "
+            # DRAM bytes of those launches from the committed ncu pass (profiles/): same command, same workload
+            traffic, traffic_note = None, None
+            tp = os.path.join(ROOT, "profiles", "r1_encoder_traffic.json")
+            if os.path.exists(tp) and faces_step_rank > 0:
+                tj = json.load(open(tp))
+                if tj.get("faces") == faces_step_rank:
+                    traffic = tj["dram_bytes_per_step"]
+                    traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the %d conv launches of one step "
+                                    "(%.1f MB per launch), %s" % (tj["conv_launches_per_step"], tj["dram_bytes_per_launch"] / 1e6,
+                                                                  tj["source"]))
+            roof = {"kernel": "tcgen05 convolutions (sv_conv_kernel + igemm_conv_kernel): all 105 conv launches of the "
                               "InceptionResnetV1 stage of one step", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                    "traffic": None, "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
+                    "traffic": traffic, "traffic_note": traffic_note,
+                    "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
                     "stage_ms": enc_ms, "share_of_step": enc_ms / sum(stage_ms.values()),
                     "note": "stage times come from instrumented single-stream passes; the timed loop overlaps the two "
                             "detection half-batches on two streams, so ms_per_step < sum(stage_ms)"}
