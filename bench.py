@@ -220,7 +220,9 @@ def run_ours(args):
         ev_log.append((name, e))
 
     def step_device(timed):
-        out = fp.run_device(frames_dev, mark=mark if timed else None)
+        # production path: a stream of batches (the cascade of step i+1 may start under the encoder of step i; every step
+        # still runs all of its own work); the instrumented passes run one batch at a time on one stream
+        out = fp.run_device(frames_dev, mark=mark if timed else None, pipelined=not timed and not args.no_pipeline)
         if world > 1:
             if os.environ.get("VNFR_RAGGED_GATHER"):
                 vdist.all_gather_faces(out["emb"], out["label"], out["prob"])
@@ -273,14 +275,28 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host frames in, host results out (`e2e`)
     e2e_steps = 1 if args.skip_e2e else args.steps
-    for _ in range(0 if args.skip_e2e else 2):
+    for _ in range(0 if args.skip_e2e else 3):
         fp(frames_pinned)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     faces_e2e, d2h = 0, 0
     e0.record()
-    for _ in range(e2e_steps):
-        res = fp(frames_pinned)
+    if args.no_pipeline:
+        for _ in range(e2e_steps):
+            res = fp(frames_pinned)
+            faces_e2e += sum(len(r["labels"]) for r in res)
+    else:
+        # the streaming form of the public call: two batches in flight -- batch i+1 is submitted (its H2D copy and cascade
+        # start under the encoder of batch i), then the results of batch i are collected on the host.  Every step's
+        # frames are copied from pinned host memory and every step's results are read back inside the timed region.
+        pending = None
+        for _ in range(e2e_steps):
+            nxt = fp.submit(frames_pinned)
+            if pending is not None:
+                res = pending.result()
+                faces_e2e += sum(len(r["labels"]) for r in res)
+            pending = nxt
+        res = pending.result()
         faces_e2e += sum(len(r["labels"]) for r in res)
     e1.record()
     barrier()
@@ -383,9 +399,11 @@ def run_ours(args):
                            "encoder": "InceptionResnetV1 random-init", "classifier": "MLPModel(512,1001) random-init",
                            "detector_weights": "bundled MTCNN", "detector_dtype": "f32", "encoder_chunk": enc.chunk,
                            "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (frames_np.nbytes / 1e6),
-                           "work_per_frame": work, "collective": "all_gather(emb,label,prob)" if world > 1 else "none"},
+                           "batches_in_flight": 1 if args.no_pipeline else 2, "work_per_frame": work, "collective": "all_gather(emb,label,prob)" if world > 1 else "none"},
                 "e2e": {"value": faces_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_np.nbytes),
-                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps},
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps,
+                        "api": "FacePipeline.__call__ (one batch at a time)" if args.no_pipeline else
+                               "FacePipeline.submit / PendingResult.result, two batches in flight"},
                 "gpu_launches": int(launches), "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
                 "roofline": roof, "clocks": clocks, "embed": embed, "gallery_topk": topk}
         if world == 1 and not args.no_cpu_baseline:
@@ -421,6 +439,7 @@ def main():
     ap.add_argument("--embed-batch", type=int, default=1024, help="crops per rank of the embeds/s measurement (config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")
+    ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time: no overlap between consecutive steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -393,6 +393,55 @@ def test_host_frame_path_overlapped_copy_equals_device_path(dev, models):
     assert sum(len(r["labels"]) for r in ref) > 0
 
 
+def test_pipelined_batches_equal_one_at_a_time(dev, models):
+    """Two batches in flight (FacePipeline.submit / PendingResult.result on pinned host frames, run_device(pipelined=True)
+    on device frames): the copy and the cascade of batch i+1 overlap the encoder of batch i through alternating frame
+    buffers / workspace slots.  Every batch must come out exactly as when it is run alone, also when batches of
+    different content alternate and when results are collected late."""
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import pipeline
+    A = np.concatenate([synth.frames("small", 18, first_seed=0), synth.frames("small", 16, first_seed=40)])      # 34 frames
+    Bf = np.ascontiguousarray(A[::-1])
+    Cf = np.concatenate([A[5:], A[:5]])
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    fp = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity")
+    alone = {k: fp(torch.from_numpy(v).to(dev)) for k, v in (("A", A), ("B", Bf), ("C", Cf))}
+    assert sum(len(r["labels"]) for r in alone["A"]) > 30
+
+    def same(got, ref):
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a["boxes"], b["boxes"])
+            np.testing.assert_array_equal(a["labels"], b["labels"])
+            np.testing.assert_array_equal(a["emb"], b["emb"])
+
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in (("A", A), ("B", Bf), ("C", Cf))}
+    order = ["A", "B", "C", "A", "A", "C", "B"]
+    pend = []
+    for k in order:                                          # depth-2 pipeline, results collected one batch late
+        pend.append((k, fp.submit(pinned[k])))
+        if len(pend) == 2:
+            kk, h = pend.pop(0)
+            same(h.result(), alone[kk])
+    kk, h = pend.pop(0)
+    same(h.result(), alone[kk])
+    # device-resident frames, pipelined: outputs are device tensors, checked after the NEXT batch has been enqueued
+    dframes = {k: torch.from_numpy(v).to(dev) for k, v in (("A", A), ("B", Bf), ("C", Cf))}
+    prev = None
+    for k in order + ["A"]:
+        out = fp.run_device(dframes[k], pipelined=True)
+        if prev is not None:
+            pk, po = prev
+            ref = alone[pk]
+            lab = po["label"].cpu().numpy()
+            emb = po["emb"].cpu().numpy()
+            cnt = po["count"].cpu().numpy()
+            assert cnt.tolist() == [len(r["labels"]) for r in ref]
+            np.testing.assert_array_equal(lab, np.concatenate([r["labels"] for r in ref]))
+            np.testing.assert_array_equal(emb, np.concatenate([r["emb"] for r in ref]))
+        prev = (k, out)
+
+
 def test_crop_workspace_overflow_grows_and_repeats(dev, models):
     """More R-/O-Net candidates than the crop workspaces hold (crowded frames): the status word flags it, the host grows
     the workspaces and repeats the pass -- results equal the amply sized run, nothing is silently dropped."""

@@ -51,6 +51,8 @@ class InceptionResnetV1(nn.Module):
     #: late layers (8x8 / 3x3 maps) only fill the 148 SMs at several hundred crops (measured 768 crops: 4.8 ms in one
     #: chunk vs 10 ms in six chunks of 128)
     chunk = 1024
+    #: batch-size granularity of the cached plans of the fused pipeline path (embed_s2d)
+    plan_bucket = 64
 
     def __init__(self, pretrained=None, classify=False, num_classes=None, dropout_prob=0.6, device=None):
         super().__init__()
@@ -140,8 +142,10 @@ class InceptionResnetV1(nn.Module):
         emb16 = torch.empty(n, 512, dtype=x_s2d.dtype, device=dev)
         for s in range(0, n, self.chunk):
             m = min(self.chunk, n - s)
-            plan = self._plan(m, h, w, dev)
-            plan.x0.copy_(x_s2d[s:s + m])
+            # plans (activation buffers + captured graph) are cached per batch size: face counts vary from batch to batch,
+            # so round up to a bucket of 64 crops (rows are independent; the padding rows are computed and ignored)
+            plan = self._plan(min(self.chunk, -(-m // self.plan_bucket) * self.plan_bucket), h, w, dev)
+            plan.x0[:m].copy_(x_s2d[s:s + m])
             plan.run()
             _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(emb[s:s + m]),
                       _lib.ptr(emb16[s:s + m]), encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())

@@ -359,24 +359,37 @@ class MTCNN(nn.Module):
         ws.frames = frames_u8
         return ws
 
-    def detect_device_chunked(self, frames_dev, ready_events, bounds):
+    def detect_device_chunked(self, frames_dev, ready_events, bounds, slot=0, wait_current=True):
         """The cascade over the sub-batches ``bounds`` = [(b0, b1), ...] of ``frames_dev`` (CUDA u8 (B,H,W,3)); sub-batch
         i starts as soon as ``ready_events[i]`` (recorded on the copy stream after its H2D) has fired.  Returns a
-        ResultWorkspace with the detections of the whole batch."""
+        ResultWorkspace with the detections of the whole batch.
+
+        ``slot`` selects one of two ResultWorkspaces and ``wait_current=False`` drops the dependency of the cascade on the
+        work already enqueued on the current stream (only ``ready_events`` gate it): together they let the cascade of
+        batch i+1 run while the encoder of batch i is still busy on the current stream (FacePipeline pipelining).  The
+        caller then guarantees that the previous user of this slot has finished (its face crops have been read)."""
         B, H, W, _ = frames_dev.shape
         dev = frames_dev.device
-        key = ("result", B, H, W, tuple(self.caps), dev)
+        key = ("result", B, H, W, tuple(self.caps), dev, slot)
         full = self._ws.get(key)
         if full is None:
             full = self._ws[key] = ResultWorkspace(B, H, W, tuple(self.caps), dev)
-        full.status.zero_()
         cur = torch.cuda.current_stream(dev)
         # consecutive sub-batches run on two alternating streams (each with its own workspace): the low-occupancy stage
         # kernels of one sub-batch (one CTA per image NMS, persistent-kernel tails) overlap the P-Net / R-Net of the next
         if getattr(self, "_chunk_streams", None) is None or self._chunk_streams[0].device != dev:
             self._chunk_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-        for s_ in self._chunk_streams:
-            s_.wait_stream(cur)
+        s0, s1 = self._chunk_streams
+        if wait_current:
+            s0.wait_stream(cur)
+            s1.wait_stream(cur)
+        with torch.cuda.stream(s0):
+            if ready_events is not None and not wait_current:
+                s0.wait_event(ready_events[0])            # orders the reset after the previous user of this slot
+            full.status.zero_()
+            zeroed = torch.cuda.Event()
+            zeroed.record(s0)
+        s1.wait_event(zeroed)
         for i, (b0, b1) in enumerate(bounds):
             st = self._chunk_streams[i & 1]
             with torch.cuda.stream(st):

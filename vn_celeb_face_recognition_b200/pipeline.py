@@ -61,10 +61,16 @@ class FacePipeline:
         self.max_faces_per_frame = max_faces_per_frame
         self.return_faces_u8 = return_faces_u8
 
-    def run_device(self, frames_u8, mark=None):
+    def run_device(self, frames_u8, mark=None, pipelined=False):
         """frames_u8: CUDA uint8 (B,H,W,3).  Returns a dict of DEVICE tensors + the face count (one tiny sync to size
         the encoder batch): count (B,), boxes (B,capf,5), points (B,capf,10), faces_u8 (F,S,S,3), emb (F,512),
-        label (F,), prob (F,), face_img (F,)."""
+        label (F,), prob (F,), face_img (F,).
+
+        ``pipelined=True`` (a stream of batches): the detection cascade of this call does not wait for the work the
+        previous call left on the current stream (its encoder / classifier), only for that call's face crops -- cascade
+        i+1 and encoder i then share the GPU.  The caller asserts that ``frames_u8`` was complete before the previous
+        call returned (e.g. frames resident on the device); results alternate between two workspace slots, so the
+        ``count`` / ``boxes`` / ``points`` tensors of a call stay valid until the call after the next one."""
         from .models.mtcnn import CropWorkspaceOverflow
         marked = mark is not None                      # stage markers need the single-stream cascade
         mark = mark or (lambda name: None)
@@ -77,21 +83,34 @@ class FacePipeline:
                     # two halves on two streams: the low-occupancy stage kernels of one half overlap the other half's
                     # P-Net / R-Net / O-Net (measured 8.14 -> 7.74 ms for 64 x 1080p)
                     n = self.device_chunks
-                    ws = self.det.detect_device_chunked(frames_u8, None, [(i * B // n, (i + 1) * B // n) for i in range(n)])
+                    bounds = [(i * B // n, (i + 1) * B // n) for i in range(n)]
+                    prev = getattr(self, "_dev_crops_done", None)
+                    if pipelined and attempt == 0 and prev is not None:
+                        self._dev_slot = 1 - getattr(self, "_dev_slot", 0)
+                        ws = self.det.detect_device_chunked(frames_u8, [prev] * n, bounds, slot=self._dev_slot, wait_current=False)
+                    else:
+                        ws = self.det.detect_device_chunked(frames_u8, None, bounds, slot=getattr(self, "_dev_slot", 0))
                 try:
-                    return self._embed_classify(ws, mark)
+                    return self._embed_classify(ws, mark, crops_event="_dev_crops_done" if (pipelined and not marked) else None)
                 except CropWorkspaceOverflow:          # more candidates than the crop workspaces hold: grow and repeat
                     if attempt == 5:
                         raise
                     self.det.grow_crop_workspace()
+                    self._dev_crops_done = None
 
-    def _embed_classify(self, ws, mark):
-        """detections (DetectWorkspace / ResultWorkspace) -> aligned crops -> encoder -> classifier, on the device."""
+    def _embed_classify(self, ws, mark, crops_event=None):
+        """detections (DetectWorkspace / ResultWorkspace) -> aligned crops -> encoder -> classifier, on the device.
+        ``crops_event``: attribute name under which an event recorded right after the face-crop kernel is stored (the
+        last reader of the frames and of the detection workspace: what a pipelined next batch has to wait for)."""
         with torch.no_grad():
             dt = self.enc.half_dtype or encoder_plan.HALF
             u8, half, fimg, cap = self.det.face_crops_device(ws, self.mode, self.S, self.det.margin, self.template, dt,
                                                             ws.B * self.max_faces_per_frame, want_u8=self.return_faces_u8)
             mark("face_crops")
+            if crops_event is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                setattr(self, crops_event, ev)
             host = ws.counters[-(ws.B + 1):].cpu().numpy()       # out_count (B) + status: the only mid-pipeline read-back
             self.det.check_status(int(host[-1]))
             F = int(host[:-1].sum())
@@ -132,16 +151,27 @@ class FacePipeline:
 
     def _run_host_frames(self, t, dev):
         """Pinned host frames -> device in sub-batches on a copy stream, the detection cascade of each sub-batch
-        starting as soon as its frames have landed; crops / encoder / classifier then run once over all faces."""
+        starting as soon as its frames have landed; crops / encoder / classifier then run once over all faces.
+
+        Two frame buffers / workspace slots alternate between calls and nothing here waits for the work an earlier call
+        left on the current stream: the H2D copy and the cascade of batch i+1 overlap the encoder of batch i when the
+        caller keeps two batches in flight (``submit``)."""
         B, H, W, _ = t.shape
         key = (B, H, W, dev)
         if getattr(self, "_fbuf_key", None) != key:
-            self._fbuf = torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
+            self._fbufs = [torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
             self._fbuf_key = key
             self._copy_stream = torch.cuda.Stream(dev)
-        buf, cs = self._fbuf, self._copy_stream
+            self._host_crops_done = [None, None]
+            self._host_slot = 0
+        slot = self._host_slot
+        self._host_slot = 1 - slot
+        buf, cs = self._fbufs[slot], self._copy_stream
         cur = torch.cuda.current_stream(dev)
-        cs.wait_stream(cur)                                  # the previous call's kernels are done reading the buffer
+        if self._host_crops_done[slot] is not None:
+            cs.wait_event(self._host_crops_done[slot])       # the batch that used this slot two calls ago has read its frames
+        else:
+            cs.wait_stream(cur)
         events = []
         bounds = self._sub_batches(B)
         with torch.cuda.stream(cs):
@@ -153,18 +183,23 @@ class FacePipeline:
         from .models.mtcnn import CropWorkspaceOverflow
         for attempt in range(6):
             with torch.no_grad():
-                ws = self.det.detect_device_chunked(buf, events if attempt == 0 else None, bounds)
+                ws = self.det.detect_device_chunked(buf, events if attempt == 0 else None, bounds, slot=slot,
+                                                    wait_current=attempt > 0)
             try:
-                return self._embed_classify(ws, lambda name: None)
+                out = self._embed_classify(ws, lambda name: None, crops_event="_host_crops_tmp")
+                self._host_crops_done[slot] = self._host_crops_tmp
+                return out
             except CropWorkspaceOverflow:
                 if attempt == 5:
                     raise
                 self.det.grow_crop_workspace()
 
-    def __call__(self, frames):
-        """frames: (B,H,W,3) uint8 numpy / torch (host or device).  Returns per-frame lists (boxes (n,4) numpy, labels,
-        probs) plus the (F,512) embeddings -- the H2D of the frames (overlapped with compute when the host tensor is
-        pinned), one D2H of the results."""
+    def submit(self, frames):
+        """Asynchronous form of ``__call__`` for a stream of batches: enqueues the whole path for ``frames`` ((B,H,W,3)
+        uint8, pinned host memory for overlap) plus the device->host copy of the results and returns a PendingResult;
+        ``.result()`` waits for that batch only.  With two batches in flight (submit batch i+1, then collect batch i) the
+        H2D copy and the detection cascade of batch i+1 run under the encoder of batch i.  (The one host wait inside
+        ``submit`` is the face count of the batch, which sizes its encoder launch.)"""
         dev = self.det._cuda_device()
         t = torch.as_tensor(frames)
         if t.is_cuda:
@@ -173,19 +208,65 @@ class FacePipeline:
             out = self._run_host_frames(t, dev)
         else:
             out = self.run_device(t.to(dev, non_blocking=True))
-        cnt = out["count_host"]
-        F = out["n_faces"]
-        nmax = int(cnt.max()) if len(cnt) else 0
-        boxes = out["boxes"][:, :max(nmax, 1)].cpu().numpy()
-        lab = out["label"].cpu().numpy() if "label" in out else np.zeros(F, np.int64)
-        prob = out["prob"].cpu().numpy() if "prob" in out else np.zeros(F, np.float32)
-        emb = out["emb"].cpu().numpy()
+        return PendingResult(self, out)
+
+    def __call__(self, frames):
+        """frames: (B,H,W,3) uint8 numpy / torch (host or device).  Returns per-frame lists (boxes (n,4) numpy, labels,
+        probs) plus the (F,512) embeddings -- the H2D of the frames (overlapped with compute when the host tensor is
+        pinned), one D2H of the results."""
+        return self.submit(frames).result()
+
+
+class PendingResult:
+    """Results of one FacePipeline.submit(): the device->host copies are enqueued at construction (pinned staging buffers,
+    two sets alternating per pipeline), ``result()`` waits for them and builds the per-frame lists."""
+
+    def __init__(self, fp, out):
+        self.cnt = out["count_host"]
+        self.F = F = out["n_faces"]
+        B = len(self.cnt)
+        nmax = max(int(self.cnt.max()) if B else 0, 1)
+        dev = out["boxes"].device
+        key = (B, out["boxes"].shape[1], out["emb"].shape[1], fp.max_faces_per_frame)
+        if getattr(fp, "_stage_key", None) != key:
+            cap = max(B * fp.max_faces_per_frame, 1)
+            pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype).pin_memory()
+            fp._stage = [dict(boxes=pin(B, out["boxes"].shape[1], 5, dtype=torch.float32), emb=pin(cap, out["emb"].shape[1], dtype=torch.float32),
+                              label=pin(cap, dtype=torch.int64), prob=pin(cap, dtype=torch.float32)) for _ in range(2)]
+            fp._stage_key, fp._stage_slot = key, 0
+        st = fp._stage[fp._stage_slot]
+        fp._stage_slot = 1 - fp._stage_slot
+        # contiguous -> contiguous pinned copies only: a strided device->host copy goes through a pageable temporary and
+        # blocks the host until everything enqueued before it (the encoder of this batch) has finished
+        st["boxes"].copy_(out["boxes"], non_blocking=True)
+        self.boxes = st["boxes"][:, :nmax]
+        if F > st["emb"].shape[0]:
+            raise _lib.VnfrError("more faces than max_faces_per_frame allows")
+        self.emb, self.label, self.prob = st["emb"][:F], st["label"][:F], st["prob"][:F]
+        self.has_cls = "label" in out
+        if F:
+            self.emb.copy_(out["emb"], non_blocking=True)
+            if self.has_cls:
+                self.label.copy_(out["label"], non_blocking=True)
+                self.prob.copy_(out["prob"], non_blocking=True)
+        self.done = torch.cuda.Event()
+        self.done.record(torch.cuda.current_stream(dev))
+        self.out = out                                   # keeps the device tensors alive until the copies have run
+
+    def result(self):
+        self.done.synchronize()
+        cnt, F = self.cnt, self.F
+        boxes = self.boxes.numpy()
+        lab = self.label.numpy().copy() if self.has_cls else np.zeros(F, np.int64)
+        prob = self.prob.numpy().copy() if self.has_cls else np.zeros(F, np.float32)
+        emb = self.emb.numpy().copy()
         res, o = [], 0
         for b in range(len(cnt)):
             n = int(cnt[b])
-            res.append({"boxes": boxes[b, :n, :4].copy(), "det_prob": boxes[b, :n, 4].copy(), "labels": lab[o:o + n].copy(),
-                        "probs": prob[o:o + n].copy(), "emb": emb[o:o + n]})
+            res.append({"boxes": boxes[b, :n, :4].copy(), "det_prob": boxes[b, :n, 4].copy(), "labels": lab[o:o + n],
+                        "probs": prob[o:o + n], "emb": emb[o:o + n]})
             o += n
+        self.out = None
         return res
 
 
