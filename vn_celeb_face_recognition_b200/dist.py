@@ -37,16 +37,25 @@ def all_gather_faces(emb, label, prob, group=None):
     return allp[:, :D].contiguous(), allp[:, D].long(), allp[:, D + 1].contiguous(), counts
 
 
-def all_gather_faces_padded(emb, label, prob, cap, group=None):
+def all_gather_faces_padded(emb, label, prob, cap, group=None, stream=None):
     """The same exchange without any host synchronisation: ONE collective over a fixed-capacity payload, so the host
     keeps enqueueing the next step while this one drains (the ragged variant above reads the counts back twice).
     ``cap`` = rows reserved per rank, identical on every rank (e.g. frames_per_rank * max_faces_per_frame).
     Returns (payload (world, cap + 1, D + 2) fp32 on device, D): rank r's faces are payload[r, :n_r] with columns
     [:D] embedding, [D] label, [D + 1] probability; n_r rides in payload[r, cap, 0] (exact: counts < 2^24).
-    ``compact_faces`` turns it into the ragged concatenation when the consumer needs it on the host side."""
+    ``compact_faces`` turns it into the ragged concatenation when the consumer needs it on the host side.
+    ``stream`` (CUDA only): run the exchange on that side stream, ordered after what is enqueued on the current stream so
+    far; the current stream does NOT wait for it, so the next batch's kernels are not held up by the collective (which also
+    waits for the slowest rank).  The result is then valid on ``stream``: make the consumer wait for it."""
     n, D = emb.shape
     if n > cap:
         raise ValueError("all_gather_faces_padded: %d faces on this rank exceed the per-rank capacity %d" % (n, cap))
+    if stream is not None:
+        stream.wait_stream(torch.cuda.current_stream(emb.device))
+        for t in (emb, label, prob):
+            t.record_stream(stream)                     # allocated on the current stream, read on the side stream
+        with torch.cuda.stream(stream):
+            return all_gather_faces_padded(emb, label, prob, cap, group=group)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     mine = torch.zeros(cap + 1, D + 2, dtype=torch.float32, device=emb.device)
     mine[:n, :D] = emb
