@@ -53,7 +53,12 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   const uint32_t smem_bias = smem_c + (uint32_t)p.c_bufs * c_buf_bytes;     // 2 x 256 floats
   const uint32_t bars = smem_bias + 2048u;
   const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bar_tfull + 16u,
-                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 16u, bar_bres = bar_cfree + 16u, tmem_slot = bar_bres + 8u;
+                 bar_res = bar_tempty + 16u, bar_cfree = bar_res + 16u, bar_bres = bar_cfree + 16u, tmem_slot = bar_bres + 8u,
+                 bar_cready = bar_bres + 16u;      // [2]: all epilogue threads have written their rows of C buffer cb
+  // TMA-fed A (1x1 convs): warps 0-7 have no gather work, so thread 0 becomes a dedicated C-store thread -- the epilogue
+  // warps then never wait for a store to drain and need no CTA-level barrier before it (ncu: "barrier" was the top stall
+  // of the projection convs: 5-10 stalled warps per issue)
+  const bool store_thread = p.epi_mode && p.a_mode == 1;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x;
@@ -79,7 +84,9 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       mbar_init(bar_tfull + 8u * i, 1);
       mbar_init(bar_tempty + 8u * i, NUM_EPILOGUE_THREADS);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_res + 8u * i, 1); mbar_init(bar_cfree + 8u * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_res + 8u * i, 1); mbar_init(bar_cfree + 8u * i, 1); mbar_init(bar_cready + 8u * i, NUM_EPILOGUE_THREADS);
+    }
     mbar_init(bar_bres, 1);
     fence_barrier_init();
   }
@@ -158,7 +165,24 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       }
     }
     cp_async_wait<0>();                        // nothing may be in flight when the CTA retires
-    }  // a_mode == 0 (with TMA-fed A these warps are idle)
+    }  // a_mode == 0
+    else if (store_thread && tid == 0) {
+      // ================================================= dedicated C-store thread (TMA-fed A: these warps are otherwise idle)
+      int tcount = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++tcount) {
+        const int cb = p.c_bufs == 2 ? (tcount & 1) : 0;
+        const uint32_t rph = p.c_bufs == 2 ? (uint32_t)((tcount >> 1) & 1) : (uint32_t)(tcount & 1);
+        const int n0 = (tile % n_tiles_n) * p.block_n, m0 = (tile / n_tiles_n) * BLOCK_M;
+        const int n_valid = min(p.block_n, p.cout - n0);
+        const uint32_t smem_cb = smem_c + (uint32_t)cb * c_buf_bytes;
+        mbar_wait(bar_cready + 8u * cb, rph);
+        for (int j = 0; j * 64 < n_valid; ++j) tma_store_2d(&tmap_c, smem_cb + (uint32_t)j * 16384u, n0 + j * 64, m0);
+        tma_store_commit();
+        tma_store_wait_read();                 // the panels have been read: hand the buffer back to the producer
+        mbar_arrive(bar_cfree + 8u * cb);
+      }
+      tma_store_wait_all();
+    }
   } else if (warp < 16) {
     // ================================================= epilogue: TMEM -> registers -> bias/residual/ReLU -> global
     const int q = warp & 3;                    // TMEM lane quarter of this warp
@@ -187,6 +211,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         const int cb = p.c_bufs == 2 ? (tcount & 1) : 0;
         const uint32_t cph = p.c_bufs == 2 ? (uint32_t)((tcount >> 1) & 1) : (uint32_t)(tcount & 1);
         const uint32_t smem_cb = smem_c + (uint32_t)cb * c_buf_bytes;
+        if (store_thread) {
+          mbar_wait(bar_res + 8u * cb, cph);
+          epilogue_row_staged<F16>(p, sb, t_row, smem_cb, r, n_valid, chalf, p.residual != nullptr);
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8u * ab);     // accumulator drained: the MMA warp may reuse it
+          fence_proxy_async_smem();              // generic-proxy writes of this row -> visible to the TMA store
+          mbar_arrive(bar_cready + 8u * cb);
+          continue;
+        }
         if (p.c_bufs == 2 && et == 0 && tcount > 0) {
           // the store of the previous tile (other buffer) was issued a whole tile ago: once it has read its panels the
           // buffer goes back to the producer, which refills it with the NEXT tile's residual while this tile is processed
@@ -311,7 +344,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
     }
   }
 
-  if (p.epi_mode && tid == NUM_PRODUCER_THREADS) tma_store_wait_all();     // the storing thread: writes have landed
+  if (p.epi_mode && !store_thread && tid == NUM_PRODUCER_THREADS) tma_store_wait_all();     // the storing thread: writes have landed
   __syncthreads();
   if (dbg && tid == 0) dbg[0] += clock64() - t_kernel;
   if (warp == 17) {
