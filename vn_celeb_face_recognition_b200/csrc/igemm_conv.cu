@@ -101,9 +101,13 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();       // the next kernel may start its prologue on SMs this grid has left
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above touched no global data: now wait for the producer of our inputs (the TMA producer warp waits after it
+  // has put the resident weight slab in flight: weights do not depend on the previous kernel)
+  if (warp != 16) pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -263,6 +267,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
         mbar_arrive_expect_tx(bar_bres, (uint32_t)KB * b_stage_bytes);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_b + (uint32_t)kb * b_stage_bytes, &tmap_w, bar_bres, kb * BLOCK_K, n0);
       }
+      pdl_wait();
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % n_tiles_n) * p.block_n;
         const int m0 = (tile / n_tiles_n) * BLOCK_M;
@@ -537,9 +542,11 @@ extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   dim3 grid(total_tiles < g_num_sms ? total_tiles : g_num_sms);
   if (p.b_res) grid = dim3((g_num_sms / p.n_tiles_n) * p.n_tiles_n);
   if (op->dtype == 1)
-    igemm_conv_kernel<true><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode, b_res_kb), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
+    VNFR_CUDA(launch_pdl(igemm_conv_kernel<true>, (int)grid.x, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode, b_res_kb),
+                         (cudaStream_t)stream, tm, ta, tc_, tr, p));
   else
-    igemm_conv_kernel<false><<<grid, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode, b_res_kb), (cudaStream_t)stream>>>(tm, ta, tc_, tr, p);
+    VNFR_CUDA(launch_pdl(igemm_conv_kernel<false>, (int)grid.x, NUM_THREADS, smem_bytes_for(op->block_n, p.stages, op->epi_mode, b_res_kb),
+                         (cudaStream_t)stream, tm, ta, tc_, tr, p));
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

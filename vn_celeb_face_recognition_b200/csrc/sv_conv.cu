@@ -108,9 +108,11 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   }
   // bias is the same for every tile (single N tile): stage it once
   for (int i = tid; i < 256; i += SV_THREADS) s_bias[i] = i < p.cout ? __ldg(p.bias + i) : 0.f;
+  pdl_launch_dependents();       // the next kernel may start its prologue on SMs this grid has left
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                    // nothing above read or wrote global data: now wait for the producer of our inputs
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -546,14 +548,14 @@ int vnfr_sv_run(const VnfrConvOp* op, void* stream) {
   const int grid = q.n_bands < 148 ? q.n_bands : 148;
   cudaStream_t st = (cudaStream_t)stream;
   if (q.ck == 16) {
-    if (op->dtype == 1) sv_conv_kernel<true, 1><<<grid, SV_THREADS, smem, st>>>(tm, ta, q);
-    else sv_conv_kernel<false, 1><<<grid, SV_THREADS, smem, st>>>(tm, ta, q);
+    if (op->dtype == 1) VNFR_CUDA(launch_pdl(sv_conv_kernel<true, 1>, grid, SV_THREADS, smem, st, tm, ta, q));
+    else VNFR_CUDA(launch_pdl(sv_conv_kernel<false, 1>, grid, SV_THREADS, smem, st, tm, ta, q));
   } else if (q.ck == 32) {
-    if (op->dtype == 1) sv_conv_kernel<true, 2><<<grid, SV_THREADS, smem, st>>>(tm, ta, q);
-    else sv_conv_kernel<false, 2><<<grid, SV_THREADS, smem, st>>>(tm, ta, q);
+    if (op->dtype == 1) VNFR_CUDA(launch_pdl(sv_conv_kernel<true, 2>, grid, SV_THREADS, smem, st, tm, ta, q));
+    else VNFR_CUDA(launch_pdl(sv_conv_kernel<false, 2>, grid, SV_THREADS, smem, st, tm, ta, q));
   } else {
-    if (op->dtype == 1) sv_conv_kernel<true, 4><<<grid, SV_THREADS, smem, st>>>(tm, ta, q);
-    else sv_conv_kernel<false, 4><<<grid, SV_THREADS, smem, st>>>(tm, ta, q);
+    if (op->dtype == 1) VNFR_CUDA(launch_pdl(sv_conv_kernel<true, 4>, grid, SV_THREADS, smem, st, tm, ta, q));
+    else VNFR_CUDA(launch_pdl(sv_conv_kernel<false, 4>, grid, SV_THREADS, smem, st, tm, ta, q));
   }
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();

@@ -72,6 +72,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (globaltimer_ns() - t0 > 2000000000ull) __trap();
   }
 }
+// Programmatic dependent launch: `launch_dependents` lets the NEXT kernel of the stream (launched with the programmatic
+// stream-serialisation attribute, see launch_pdl) start its prologue -- barrier init, tensor-map prefetch, TMEM allocation,
+// weight loads -- on SMs this grid has already left; `wait` blocks until every prerequisite grid has completed and its
+// memory is visible.  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -386,6 +393,19 @@ inline EncodeTiledFn get_encode_tiled() {
       fn = reinterpret_cast<EncodeTiledFn>(sym);
   }
   return fn;
+}
+
+// Kernel launch with (pdl = true) or without the programmatic stream-serialisation attribute.  VNFR_NO_PDL=1 disables it.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool pdl = getenv("VNFR_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace tc
