@@ -651,38 +651,53 @@ __global__ void __launch_bounds__(NT, 1) rnet_front_kernel(const HeadArgs a) {
   }
 }
 
-// ---- R-Net front with conv1 (3 -> 28, 3x3) on the tensor cores as well (default; VNFR_RNET_FRONT_FMA=1 = rnet_front_kernel).
-// The FMA version is bound by shared-memory loads (ncu: 72 % LSU wavefronts, 29 % FMA): K = 27 gives every loaded
-// activation only 4-8 FMAs.  Here the crop becomes an "x-im2col" A operand in shared memory: one 32-byte swizzled row per
-// pixel (y, x) holding k = 3 dx + c -> crop[c][y][x + dx] (9 of 16 fp16, hi and lo parts in two buffers); tap ky reads the
-// SAME buffer from a start address shifted by 24 ky rows (the shifted-view trick), so one crop is 5 row tiles x 3 taps x 3
-// products (hi*hi, hi*lo, lo*hi) = 45 tcgen05.mma of M 128, N 32, K 16 into five TMEM accumulators.  The 8 warps read
-// their TMEM lanes back (+ bias, PReLU) into a shared-memory map (aliasing the A buffers), max-pool 3/2 and write the
-// two-part fp16 split that conv2's shifted-view convolution reads.  Two CTAs per SM (256 TMEM columns each).
+// ---- R-Net / O-Net front with conv1 (3 -> 28 / 32, 3x3) on the tensor cores as well (default; VNFR_RNET_FRONT_FMA=1 /
+// VNFR_ONET_FRONT_FMA=1 select the FMA front kernels).  The FMA versions are bound by shared-memory loads (ncu: 70 % LSU
+// wavefronts, 30 % FMA): K = 27 gives every loaded activation only 4-8 FMAs.  Here the crop becomes an "x-im2col" A
+// operand in shared memory: one 32-byte swizzled row per pixel (y, x) holding k = 3 dx + c -> crop[c][y][x + dx] (9 of 16
+// fp16, hi and lo parts in two buffers); tap ky reads the SAME buffer from a start address shifted by S ky rows (the
+// shifted-view trick), so a band of conv rows is MT row tiles x 3 taps x 3 products (hi*hi, hi*lo, lo*hi) tcgen05.mma of
+// M 128, N 32, K 16 into MT TMEM accumulators.  The 8 warps read their TMEM lanes back (+ bias, PReLU) into a
+// shared-memory map (aliasing the A buffers), max-pool 3/2 and write the two-part fp16 split that conv2's shifted-view
+// convolution reads.  R-Net: the whole 22x22 map is one band (5 tiles); O-Net: bands of 4 pooled rows = 9 conv rows (4
+// tiles, one conv row recomputed per band).  Two CTAs per SM.
 constexpr int RT_THREADS = 256;
-constexpr int RT_A_ROWS = 688;                       // 576 pixels + the rows the last accumulator rows reach (639 + 48)
-constexpr int RT_A_PART = RT_A_ROWS * 32;            // 22 016 B per part (multiple of 256: same swizzle phase for hi / lo)
-constexpr int RT_REGION = 62464;                     // max(two A parts 44 032 B, conv1 map 484 px x 32 ch fp32 61 952 B)
-constexpr int RT_B_BYTES = 3 * 2 * 1024;             // [ky][part][32 cout rows][16 k] fp16, 32-byte swizzled rows
-constexpr int RT_SMEM = 1024 + RT_B_BYTES + RT_REGION + 3 * 576 * 4;
 
-__global__ void __launch_bounds__(RT_THREADS, 2) rnet_front_tc_kernel(const HeadArgs a) {
+template <int S, int COUT, int PB, int W1, int B1, int A1>
+struct FrontTc {
+  static constexpr int OH = S - 2;                             // conv1 output edge
+  static constexpr int PH = (OH - 3 + 1) / 2 + 1;              // pooled edge (3/2, ceil mode)
+  static constexpr int CB = (2 * PB + 1 < OH) ? 2 * PB + 1 : OH;   // conv rows per band
+  static constexpr int MT = ((CB - 1) * S + OH + 127) / 128;   // accumulator row tiles per band (raster of width S)
+  static constexpr int A_ROWS = MT * 128 + 2 * S;              // rows the last accumulator rows reach through the ky shifts
+  static constexpr int A_PART = (A_ROWS * 32 + 255) / 256 * 256;
+  static constexpr int MAP_BYTES = CB * OH * 32 * 4;
+  static constexpr int REGION = ((2 * A_PART > MAP_BYTES ? 2 * A_PART : MAP_BYTES) + 1023) / 1024 * 1024;
+  static constexpr int B_BYTES = 3 * 2 * 1024;                 // [ky][part][32 cout rows][16 k] fp16, 32-byte swizzled rows
+  static constexpr int SMEM = 1024 + B_BYTES + REGION + 3 * S * S * 4;
+  static constexpr unsigned TCOLS = MT * 32 <= 128 ? 128u : 256u;
+};
+
+template <int S, int COUT, int PB, int W1, int B1, int A1>
+__global__ void __launch_bounds__(RT_THREADS, 2) head_front_tc_kernel(const HeadArgs a) {
+  using F = FrontTc<S, COUT, PB, W1, B1, A1>;
+  constexpr int OH = F::OH, PH = F::PH, MT = F::MT;
   extern __shared__ __align__(16) uint8_t rt_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
   uint8_t* base = rt_raw + ((1024u - (smem_u32(rt_raw) & 1023u)) & 1023u);
   uint8_t* s_b = base;                                           // B operand
-  uint8_t* s_reg = base + RT_B_BYTES;                            // A parts, later the conv1 map [484][32] fp32
-  float* s_crop = reinterpret_cast<float*>(base + RT_B_BYTES + RT_REGION);   // [3][24][24]
+  uint8_t* s_reg = base + F::B_BYTES;                            // A parts, later the conv1 map [rows][OH][32] fp32
+  float* s_crop = reinterpret_cast<float*>(base + F::B_BYTES + F::REGION);   // [3][S][S]
   float* s_map = reinterpret_cast<float*>(s_reg);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_hi = smem_u32(s_reg), a_lo = a_hi + RT_A_PART, b_addr = smem_u32(s_b), bar = smem_u32(&s_bar);
+  const uint32_t a_hi = smem_u32(s_reg), a_lo = a_hi + F::A_PART, b_addr = smem_u32(s_b), bar = smem_u32(&s_bar);
   const float* w = a.w;
   // ---- once per CTA: B operand (conv1 weights as fp16 hi / lo, k = 3 dx + c), barrier, TMEM
   for (int i = tid; i < 3 * 32 * 16; i += RT_THREADS) {
     const int k = i & 15, n = (i >> 4) & 31, ky = i >> 9;
     float wv = 0.f;
-    if (k < 9 && n < 28) { const int dx = k / 3, c = k - 3 * dx; wv = __ldg(w + RW::W1 + ((c * 3 + ky) * 3 + dx) * 28 + n); }
+    if (k < 9 && n < COUT) { const int dx = k / 3, c = k - 3 * dx; wv = __ldg(w + W1 + ((c * 3 + ky) * 3 + dx) * COUT + n); }
     const __half hi = __float2half_rn(wv);
     const __half lo = __float2half_rn(wv - __half2float(hi));
     const int off = n * 32 + (((k >> 3) ^ ((n >> 2) & 1)) << 4) + 2 * (k & 7);
@@ -691,7 +706,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rnet_front_tc_kernel(const Head
   }
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(F::TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc::fence_proxy_async_smem();
@@ -705,118 +720,129 @@ __global__ void __launch_bounds__(RT_THREADS, 2) rnet_front_tc_kernel(const Head
   for (int flat = blockIdx.x; flat < total; flat += gridDim.x) {
     // ---- crop -> shared memory
     {
-      const float4* src = reinterpret_cast<const float4*>(a.crops + (size_t)flat * 3 * 576);
-      for (int i = tid; i < 3 * 576 / 4; i += RT_THREADS) reinterpret_cast<float4*>(s_crop)[i] = __ldg(src + i);
+      const float4* src = reinterpret_cast<const float4*>(a.crops + (size_t)flat * 3 * S * S);
+      for (int i = tid; i < 3 * S * S / 4; i += RT_THREADS) reinterpret_cast<float4*>(s_crop)[i] = __ldg(src + i);
     }
     __syncthreads();
-    // ---- x-im2col A operand: pixel p = 24 y + x -> 16 halves, k = 3 dx + c (k >= 9 and x + dx > 23: zero)
-    for (int pix = tid; pix < 576; pix += RT_THREADS) {
-      const int x = pix % 24;
-      uint32_t hw[8], lw[8];
-      float v[16];
+    for (int P0 = 0; P0 < PH; P0 += PB) {
+      const int P1 = min(PH, P0 + PB);
+      const int y0 = 2 * P0, y1 = min(OH, 2 * (P1 - 1) + 3), ncr = y1 - y0;      // conv rows [y0, y1) of this band
+      // ---- x-im2col A operand: band pixel p = S yy + x -> 16 halves, k = 3 dx + c (k >= 9 and x + dx >= S: zero)
+      for (int pix = tid; pix < (ncr + 2) * S; pix += RT_THREADS) {
+        const int x = pix % S;
+        const float* src = s_crop + y0 * S + pix;
+        float v[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int dx = k / 3, c = k - 3 * dx;
-        v[k] = (k < 9 && x + dx < 24) ? s_crop[c * 576 + pix + dx] : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const __half2 h = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-        const __half2 l = __floats2half2_rn(v[2 * q] - __low2float(h), v[2 * q + 1] - __high2float(h));
-        hw[q] = *reinterpret_cast<const uint32_t*>(&h);
-        lw[q] = *reinterpret_cast<const uint32_t*>(&l);
-      }
-      const uint32_t row = a_hi + 32u * (uint32_t)pix;
-      const uint32_t sw = ((row >> 7) & 1u) << 4;
-      tc::sts128(row + sw, make_uint4(hw[0], hw[1], hw[2], hw[3]));
-      tc::sts128(row + (sw ^ 16u), make_uint4(hw[4], hw[5], hw[6], hw[7]));
-      tc::sts128(row + RT_A_PART + sw, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-      tc::sts128(row + RT_A_PART + (sw ^ 16u), make_uint4(lw[4], lw[5], lw[6], lw[7]));
-    }
-    tc::fence_proxy_async_smem();
-    tc::tc_fence_before();
-    __syncthreads();
-    // ---- conv1 on the tensor cores
-    if (warp == 0) {
-      tc::tc_fence_after();
-      if (tc::elect_one()) {
-        const uint32_t idesc = tc::make_idesc_f16(32, 1);
-#pragma unroll 1
-        for (int mt = 0; mt < 5; ++mt) {
-#pragma unroll 1
-          for (int ky = 0; ky < 3; ++ky) {
-            const uint32_t shift = 32u * (uint32_t)(128 * mt + 24 * ky);
-            const uint64_t ah = tc::make_sw_desc(a_hi + shift, 32, 0), al = tc::make_sw_desc(a_lo + shift, 32, 0);
-            const uint64_t bh = tc::make_sw_desc(b_addr + (uint32_t)(ky * 2) * 1024u, 32, 0);
-            const uint64_t bl = tc::make_sw_desc(b_addr + (uint32_t)(ky * 2 + 1) * 1024u, 32, 0);
-            tc::umma_bf16(tmem_base + 32u * mt, ah, bh, idesc, ky != 0);
-            tc::umma_bf16(tmem_base + 32u * mt, ah, bl, idesc, 1);
-            tc::umma_bf16(tmem_base + 32u * mt, al, bh, idesc, 1);
-          }
+        for (int k = 0; k < 16; ++k) {
+          const int dx = k / 3, c = k - 3 * dx;
+          v[k] = (k < 9 && x + dx < S) ? src[c * S * S + dx] : 0.f;
         }
-        tc::umma_commit(bar);
+        uint32_t hw[8], lw[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const __half2 h = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+          const __half2 l = __floats2half2_rn(v[2 * q] - __low2float(h), v[2 * q + 1] - __high2float(h));
+          hw[q] = *reinterpret_cast<const uint32_t*>(&h);
+          lw[q] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint32_t row = a_hi + 32u * (uint32_t)pix;
+        const uint32_t sw = ((row >> 7) & 1u) << 4;
+        tc::sts128(row + sw, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+        tc::sts128(row + (sw ^ 16u), make_uint4(hw[4], hw[5], hw[6], hw[7]));
+        tc::sts128(row + F::A_PART + sw, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+        tc::sts128(row + F::A_PART + (sw ^ 16u), make_uint4(lw[4], lw[5], lw[6], lw[7]));
       }
-      __syncwarp();
-    }
-    tc::mbar_wait(bar, phase);
-    phase ^= 1u;
-    tc::tc_fence_after();
-    __syncthreads();                 // every thread has seen the MMAs complete: the A buffers may be overwritten by the map
-    // ---- TMEM -> + bias, PReLU -> conv1 map [22*22][32] fp32 (warp group g = warp >> 2 takes row tiles g, g + 2, g + 4)
-    {
-      const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      for (int mt = warp >> 2; mt < 5; mt += 2) {
-        float acc[32];
+      tc::fence_proxy_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      // ---- conv1 of the band on the tensor cores
+      if (warp == 0) {
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t idesc = tc::make_idesc_f16(32, 1);
+#pragma unroll 1
+          for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t shift = 32u * (uint32_t)(128 * mt + S * ky);
+              const uint64_t ah = tc::make_sw_desc(a_hi + shift, 32, 0), al = tc::make_sw_desc(a_lo + shift, 32, 0);
+              const uint64_t bh = tc::make_sw_desc(b_addr + (uint32_t)(ky * 2) * 1024u, 32, 0);
+              const uint64_t bl = tc::make_sw_desc(b_addr + (uint32_t)(ky * 2 + 1) * 1024u, 32, 0);
+              tc::umma_bf16(tmem_base + 32u * mt, ah, bh, idesc, ky != 0);
+              tc::umma_bf16(tmem_base + 32u * mt, ah, bl, idesc, 1);
+              tc::umma_bf16(tmem_base + 32u * mt, al, bh, idesc, 1);
+            }
+          }
+          tc::umma_commit(bar);
+        }
         __syncwarp();
-        tc::tmem_ld16_issue(t_lane + 32u * mt, acc);
-        tc::tmem_ld16_issue(t_lane + 32u * mt + 16u, acc + 16);
-        tc::tmem_ld_wait(acc);
-        tc::tmem_ld_wait(acc + 16);
-        const int r = 128 * mt + (warp & 3) * 32 + lane;
-        const int y = r / 24, x = r - 24 * y;
-        if (y < 22 && x < 22) {
-          float4* dst = reinterpret_cast<float4*>(s_map + (y * 22 + x) * 32);
+      }
+      tc::mbar_wait(bar, phase);
+      phase ^= 1u;
+      tc::tc_fence_after();
+      __syncthreads();               // every thread has seen the MMAs complete: the A buffers may be overwritten by the map
+      // ---- TMEM -> + bias, PReLU -> conv1 map [ncr][OH][32] fp32 (warp group g = warp >> 2 takes row tiles g, g + 2, ...)
+      {
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int mt = warp >> 2; mt < MT; mt += 2) {
+          float acc[32];
+          __syncwarp();
+          tc::tmem_ld16_issue(t_lane + 32u * mt, acc);
+          tc::tmem_ld16_issue(t_lane + 32u * mt + 16u, acc + 16);
+          tc::tmem_ld_wait(acc);
+          tc::tmem_ld_wait(acc + 16);
+          const int r = 128 * mt + (warp & 3) * 32 + lane;
+          const int yy = r / S, x = r - S * yy;
+          if (yy < ncr && x < OH) {
+            float4* dst = reinterpret_cast<float4*>(s_map + (yy * OH + x) * 32);
 #pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            float o[4];
+            for (int q = 0; q < COUT / 4; ++q) {
+              float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = prelu(acc[4 * q + e] + __ldg(w + RW::B1 + 4 * q + e), __ldg(w + RW::A1 + 4 * q + e));
-            dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+              for (int e = 0; e < 4; ++e) o[e] = prelu(acc[4 * q + e] + __ldg(w + B1 + 4 * q + e), __ldg(w + A1 + 4 * q + e));
+              dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+            }
           }
         }
       }
-    }
-    tc::tc_fence_before();
-    __syncthreads();
-    // ---- maxpool 3/2 (ceil: windows clipped at 22) + two-part fp16 split -> p1 [crop][121][hi 32 | lo 32] (28 real channels)
-    for (int i = tid; i < 121 * 32; i += RT_THREADS) {
-      const int c = i & 31, pp = i >> 5;
-      const int oy = pp / 11, ox = pp - 11 * oy;
-      float m = 0.f;
-      if (c < 28) {
-        m = -CUDART_INF_F;
+      tc::tc_fence_before();
+      __syncthreads();
+      // ---- maxpool 3/2 (ceil: windows clipped at OH) of pooled rows [P0, P1) + two-part fp16 split
+      //      -> p1 [crop][PH*PH][hi 32 | lo 32] (COUT real channels)
+      for (int i = tid; i < (P1 - P0) * PH * 32; i += RT_THREADS) {
+        const int c = i & 31, pp = i >> 5;
+        const int oyl = pp / PH, ox = pp - PH * oyl;
+        const int oy = P0 + oyl;
+        float m = 0.f;
+        if (c < COUT) {
+          m = -CUDART_INF_F;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+          for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int y = 2 * oy + ky, x = 2 * ox + kx;
-            if (y < 22 && x < 22) m = fmaxf(m, s_map[(y * 22 + x) * 32 + c]);
-          }
+            for (int kx = 0; kx < 3; ++kx) {
+              const int y = 2 * oy + ky, x = 2 * ox + kx;
+              if (y < OH && x < OH) m = fmaxf(m, s_map[((y - y0) * OH + x) * 32 + c]);
+            }
+        }
+        const __half hi = __float2half_rn(m);
+        const __half lo = __float2half_rn(m - __half2float(hi));
+        unsigned short* q = p1 + ((size_t)flat * (PH * PH) + oy * PH + ox) * 64 + c;
+        q[0] = __half_as_ushort(hi); q[32] = __half_as_ushort(lo);
       }
-      const __half hi = __float2half_rn(m);
-      const __half lo = __float2half_rn(m - __half2float(hi));
-      unsigned short* q = p1 + ((size_t)flat * 121 + pp) * 64 + c;
-      q[0] = __half_as_ushort(hi); q[32] = __half_as_ushort(lo);
+      __syncthreads();               // the map region is rebuilt as the A operand of the next band / crop
     }
-    __syncthreads();                 // the map / crop buffers are reused by the next crop
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc::tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(F::TCOLS) : "memory");
   }
 }
+
+// R-Net: 24x24 crops, 28 channels, one band; O-Net: 48x48 crops, 32 channels, bands of 4 pooled rows
+#define RNET_FRONT_TC 24, 28, 11, RW::W1, RW::B1, RW::A1
+#define ONET_FRONT_TC 48, 32, 4, OW_::W1, OW_::B1, OW_::A1
 
 constexpr int RB_A = RG * 48 * 16, RB_B = RG * 576, RB_C = 16 * RG * 128;       // pool2 / dense4 out, conv3 out, scratch
 constexpr int RB_SMEM = (RB_A + RB_B + RB_C) * 4;
@@ -1218,12 +1244,17 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(onet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(head_front_tc_kernel<ONET_FRONT_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   FrontTc<ONET_FRONT_TC>::SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
     attr = true;
   }
   launch_crops<48>(a, st);
-  onet_front_kernel<<<148, NT, OF_SMEM, st>>>(a);
+  static const bool front_fma = getenv("VNFR_ONET_FRONT_FMA") != nullptr;
+  // (the tensor-core front writes the two-part fp16 split only: split_mode 1 keeps the FMA front)
+  if (front_fma || split_mode != 2) onet_front_kernel<<<148, NT, OF_SMEM, st>>>(a);
+  else head_front_tc_kernel<ONET_FRONT_TC><<<148 * 2, RT_THREADS, FrontTc<ONET_FRONT_TC>::SMEM, st>>>(a);
   g_vnfr_launches += 2;
   VNFR_CHECK_LAUNCH();
   // conv2 on the tensor cores; the tensor maps are re-encoded only when a pointer or the capacity changes
@@ -1305,14 +1336,15 @@ extern "C" int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   static bool attr = false;
   if (!attr) {
     VNFR_CUDA(cudaFuncSetAttribute(rnet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
-    VNFR_CUDA(cudaFuncSetAttribute(rnet_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
+    VNFR_CUDA(cudaFuncSetAttribute(head_front_tc_kernel<RNET_FRONT_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   FrontTc<RNET_FRONT_TC>::SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(rnet_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
     attr = true;
   }
   launch_crops<24>(a, st);
   static const bool front_fma = getenv("VNFR_RNET_FRONT_FMA") != nullptr;
   if (front_fma) rnet_front_kernel<<<148, NT, R_SMEM, st>>>(a);
-  else rnet_front_tc_kernel<<<148 * 2, RT_THREADS, RT_SMEM, st>>>(a);
+  else head_front_tc_kernel<RNET_FRONT_TC><<<148 * 2, RT_THREADS, FrontTc<RNET_FRONT_TC>::SMEM, st>>>(a);
   g_vnfr_launches += 2;
   VNFR_CHECK_LAUNCH();
   static VnfrConvOp op;
