@@ -135,10 +135,11 @@ class FacePipeline:
 
     #: device-resident frames: the cascade runs as this many sub-batches alternating between two streams
     device_chunks = int(os.environ.get("VNFR_DEVICE_CHUNKS", "2"))
-    #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i)
-    sub_batch = 8
-    #: the first sub-batch is smaller: nothing can overlap its copy, so it should land quickly
-    first_sub_batch = 4
+    #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i).  Measured for
+    #: 64 x 1080p with two batches in flight (tools/e2e_pipe_probe.py): 8/4 10.94 ms, 16/8 10.45, 16/16 10.43, 32/32 11.15
+    sub_batch = 16
+    #: the first sub-batch is smaller: with a single batch in flight nothing can overlap its copy, so it should land quickly
+    first_sub_batch = 8
 
     def _sub_batches(self, B):
         bounds, b0 = [], 0
