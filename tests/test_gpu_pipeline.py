@@ -425,6 +425,12 @@ def test_pipelined_batches_equal_one_at_a_time(dev, models):
             same(h.result(), alone[kk])
     kk, h = pend.pop(0)
     same(h.result(), alone[kk])
+    # three submits before the first collect: the staging slot of the first batch is reused by the third, which must
+    # materialise the first batch's results before overwriting them
+    h1, h2, h3 = fp.submit(pinned["A"]), fp.submit(pinned["B"]), fp.submit(pinned["C"])
+    same(h3.result(), alone["C"])
+    same(h1.result(), alone["A"])
+    same(h2.result(), alone["B"])
     # device-resident frames, pipelined: outputs are device tensors, checked after the NEXT batch has been enqueued
     dframes = {k: torch.from_numpy(v).to(dev) for k, v in (("A", A), ("B", Bf), ("C", Cf))}
     prev = None

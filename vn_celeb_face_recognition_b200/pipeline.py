@@ -230,13 +230,25 @@ class PendingResult:
         dev = out["boxes"].device
         key = (B, out["boxes"].shape[1], out["emb"].shape[1], fp.max_faces_per_frame)
         if getattr(fp, "_stage_key", None) != key:
+            for o in fp.__dict__.get("_stage_owner", []):          # geometry changed: collect what still uses the old buffers
+                if o is not None and o._res is None:
+                    o.result()
+            fp._stage_owner = [None, None]
             cap = max(B * fp.max_faces_per_frame, 1)
             pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype).pin_memory()
             fp._stage = [dict(boxes=pin(B, out["boxes"].shape[1], 5, dtype=torch.float32), emb=pin(cap, out["emb"].shape[1], dtype=torch.float32),
                               label=pin(cap, dtype=torch.int64), prob=pin(cap, dtype=torch.float32)) for _ in range(2)]
             fp._stage_key, fp._stage_slot = key, 0
-        st = fp._stage[fp._stage_slot]
-        fp._stage_slot = 1 - fp._stage_slot
+        slot = fp._stage_slot
+        st = fp._stage[slot]
+        fp._stage_slot = 1 - slot
+        # the staging buffers alternate: a third submit() before the first result() has been collected would overwrite them,
+        # so the previous owner of this slot is materialised first (that wait only costs when more than two are in flight)
+        owners = fp.__dict__.setdefault("_stage_owner", [None, None])
+        if owners[slot] is not None and owners[slot]._res is None:
+            owners[slot].result()
+        owners[slot] = self
+        self._res = None
         # contiguous -> contiguous pinned copies only: a strided device->host copy goes through a pageable temporary and
         # blocks the host until everything enqueued before it (the encoder of this batch) has finished
         st["boxes"].copy_(out["boxes"], non_blocking=True)
@@ -255,6 +267,8 @@ class PendingResult:
         self.out = out                                   # keeps the device tensors alive until the copies have run
 
     def result(self):
+        if self._res is not None:
+            return self._res
         self.done.synchronize()
         cnt, F = self.cnt, self.F
         boxes = self.boxes.numpy()
@@ -268,6 +282,7 @@ class PendingResult:
                         "probs": prob[o:o + n], "emb": emb[o:o + n]})
             o += n
         self.out = None
+        self._res = res
         return res
 
 
