@@ -64,15 +64,18 @@ int vnfr_pyramid_plan(int B, int H, int W, int min_face_size, double factor, Vnf
  * levels: fp32, layout given by VnfrPyramid.level_off.                                                             */
 int vnfr_pyramid_resize_norm(const VnfrPyramid* pyr_host, const uint8_t* frames, float* levels, void* stream);
 
-/* Upload P/R/O-Net weights.  `packed_host` layouts are produced by models/mtcnn.py:_pack_* (documented there).     */
-int vnfr_pnet_set_weights(const float* packed_host, int n_floats, void* stream);
+/* P-Net weights: `packed_host` (6632 floats, layout produced by models/mtcnn.py:_pack_pnet) -> the kernel's layout, written
+ * to the HOST buffer out_host (vnfr_pnet_packed_bytes() bytes).  The caller uploads it to a 16-byte aligned device buffer it
+ * owns and passes that to vnfr_pnet_sweep_compact: the library keeps no weights of its own (no hidden state).            */
+int vnfr_pnet_packed_bytes(void);
+int vnfr_pnet_pack_weights(const float* packed_host, int n_floats, void* out_host, int out_bytes);
 
 /* PNet.forward over every level + generateBoundingBox's threshold, fused (mtcnn.py:38-49; detect_face.py:73-75,
  * :203-218).  Candidates of image b / level l go to segment seg = b*n_levels + l with capacity `cap`:
  *   cand_count[seg]; cand_cell[seg][i] = (y<<16)|x; cand_score[seg][i]; cand_reg[seg][i][4].
  * dense_prob / dense_reg (nullable, layout VnfrPyramid.map_off: prob [cell], reg [4][cell] per (l,b)) are for parity
  * tests only.                                                                                                      */
-int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr_host, const float* levels, float threshold, int cap,
+int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr_host, const float* levels, const void* pnet_weights, float threshold, int cap,
                             int32_t* cand_count, uint32_t* cand_cell, float* cand_score, float* cand_reg,
                             float* dense_prob, float* dense_reg, void* stream);
 
@@ -228,6 +231,60 @@ int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* 
  * cosine top-k against a gallery shard (BASELINE.json config 5; the reference itself has no gallery search). */
 int vnfr_topk_rows(const float* scores, int n, int g, int pitch, int k, int col_offset, int accumulate, float* out_val,
                    int32_t* out_idx, void* stream);
+
+/* ---- fused tail: pool -> bottleneck -> L2-normalise -> MLP -> log-softmax/argmax in ONE cooperative kernel --------------
+ * Replaces avgpool_1a + last_linear + last_bn + F.normalize (models/inception_resnet_v1.py:294-302; `logits` +
+ * log_softmax :298-300 when classify), MLPModel.forward (models/mlp_model.py:10-15) and the argmax / exp / threshold of
+ * identify_person (demo_image.py:113-137).  Up to three linear layers, each followed by a row operation; every
+ * contraction runs on the tensor cores in split precision (two fp16 parts per fp32 operand, three products, fp32
+ * accumulation: fp32-level accuracy, so the predicted label equals the fp32 reference's).
+ * Weights of a layer: fp16 [2*N_pad][K] = rows [0,N_pad) the hi parts fp16(W), rows [N_pad,2*N_pad) the lo parts
+ * fp16(W - hi) (rows >= N zero); bias fp32 [N_pad].  a_in: fp16 [2*n_pad][K] scratch (hi rows, then lo rows), written by
+ * the kernel; layer l+1's a_in must be layer l's a_next.  partial: fp32 [split_k][n_pad][N_pad] scratch.               */
+typedef struct {
+  int32_t K, N, N_pad;            /* K multiple of 64; N_pad multiple of 128, N <= 8192                              */
+  int32_t split_k;                /* K ranges per output tile (partials are summed in a fixed order)                 */
+  int32_t rowop;                  /* after the layer: 0 identity, 1 ReLU, 2 L2-normalise (F.normalize), 3 log_softmax + argmax */
+  int32_t out_vec_pitch;
+  const void* weights;
+  const float* bias;
+  float* partial;
+  void* a_in;
+  void* a_next;                   /* nullable (last layer)                                                           */
+  float* out_vec;                 /* nullable: fp32 [n][out_vec_pitch] row-operation output (embedding / log-probs)   */
+} VnfrTailLayer;
+
+typedef struct {
+  unsigned char tmap_a[3][128];   /* filled by vnfr_tail_prepare                                                     */
+  unsigned char tmap_w[3][128];
+  int32_t n_layers, n_pad;        /* n_pad: row capacity of the scratch buffers, multiple of 128                     */
+  int32_t in_mode;                /* 0: x = 16-bit NHWC [n][hw][x_pitch] (first layer[0].K channels), mean over hw;
+                                     1: x_f32 = fp32 [n][x_f32_pitch], first x_f32_cols columns                      */
+  int32_t hw, x_pitch, x_dtype;   /* x_dtype: 0 = bf16, 1 = fp16                                                     */
+  int32_t x_f32_pitch;
+  int32_t x_f32_cols;             /* valid columns of x_f32 (<= layer[0].K; the rest of K is zero padding)           */
+  int32_t emb_half_dtype;
+  int32_t reserved;
+  const void* x;
+  const float* x_f32;
+  VnfrTailLayer layer[3];
+  void* emb_half;                 /* nullable: 16-bit [n][N] copy of the L2-normalised row (rowop 2)                 */
+  int64_t* label;                 /* nullable outputs of rowop 3: argmax (or n_classes when prob < threshold)        */
+  float* prob;                    /*   exp(max log-prob)                                                             */
+  float* label_f;                 /* nullable: the same two values as floats with row pitch lp_pitch -- the label /  */
+  float* prob_f;                  /*   probability columns of the all-gather send buffer (dist.py payload)           */
+  int32_t lp_pitch;
+  int32_t n_classes;
+  const float* thr_class;         /* nullable: per-class thresholds [n_classes] (demo_image.py:118-124)              */
+  float thr;                      /* scalar threshold otherwise (0 = keep every label)                               */
+  int32_t count_value;            /* value written to *count_cell (the caller's total row count when it runs chunks) */
+  float* count_cell;              /* nullable: receives (float)count_value -- the count cell of the send buffer     */
+  unsigned int* grid_barrier;     /* one zero-initialisable device word                                              */
+} VnfrTailOp;
+
+int vnfr_tail_prepare(VnfrTailOp* op_host);
+/* n <= n_pad rows; launches ONE cooperative kernel (plus a 4-byte memset of the barrier word) on `stream`.         */
+int vnfr_tail_run(const VnfrTailOp* op_host, int n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -171,38 +171,7 @@ def mlp_forward(sd, x):
 # --------------------------------------------------------------------------------------------------------------------
 # Encoder / MLP architecture table + seeded, well-conditioned random init
 # --------------------------------------------------------------------------------------------------------------------
-def encoder_conv_specs():
-    """(prefix, cin, cout, (kh,kw), has_bn) for every conv in construction order of inception_resnet_v1.py:219-254."""
-    specs = []
-
-    def b(p, cin, cout, k):
-        k = (k, k) if isinstance(k, int) else k
-        specs.append((p, cin, cout, k, True))
-
-    b("conv2d_1a", 3, 32, 3); b("conv2d_2a", 32, 32, 3); b("conv2d_2b", 32, 64, 3)
-    b("conv2d_3b", 64, 80, 1); b("conv2d_4a", 80, 192, 3); b("conv2d_4b", 192, 256, 3)
-    for i in range(5):
-        p = "repeat_1.%d" % i
-        b(p + ".branch0", 256, 32, 1)
-        b(p + ".branch1.0", 256, 32, 1); b(p + ".branch1.1", 32, 32, 3)
-        b(p + ".branch2.0", 256, 32, 1); b(p + ".branch2.1", 32, 32, 3); b(p + ".branch2.2", 32, 32, 3)
-        specs.append((p + ".conv2d", 96, 256, (1, 1), False))
-    b("mixed_6a.branch0", 256, 384, 3)
-    b("mixed_6a.branch1.0", 256, 192, 1); b("mixed_6a.branch1.1", 192, 192, 3); b("mixed_6a.branch1.2", 192, 256, 3)
-    for i in range(10):
-        p = "repeat_2.%d" % i
-        b(p + ".branch0", 896, 128, 1)
-        b(p + ".branch1.0", 896, 128, 1); b(p + ".branch1.1", 128, 128, (1, 7)); b(p + ".branch1.2", 128, 128, (7, 1))
-        specs.append((p + ".conv2d", 256, 896, (1, 1), False))
-    b("mixed_7a.branch0.0", 896, 256, 1); b("mixed_7a.branch0.1", 256, 384, 3)
-    b("mixed_7a.branch1.0", 896, 256, 1); b("mixed_7a.branch1.1", 256, 256, 3)
-    b("mixed_7a.branch2.0", 896, 256, 1); b("mixed_7a.branch2.1", 256, 256, 3); b("mixed_7a.branch2.2", 256, 256, 3)
-    for i in list(range(5)) + [None]:
-        p = "repeat_3.%d" % i if i is not None else "block8"
-        b(p + ".branch0", 1792, 192, 1)
-        b(p + ".branch1.0", 1792, 192, 1); b(p + ".branch1.1", 192, 192, (1, 3)); b(p + ".branch1.2", 192, 192, (3, 1))
-        specs.append((p + ".conv2d", 384, 1792, (1, 1), False))
-    return specs
+from vn_celeb_face_recognition_b200.synthetic import encoder_conv_specs  # noqa: E402,F401  (seeded weight DATA lives in the package)
 
 
 def make_encoder_state_dict(seed=0, calibrate=True, calib_batch=None):
@@ -210,30 +179,12 @@ def make_encoder_state_dict(seed=0, calibrate=True, calib_batch=None):
 
     Default PyTorch init + eval-mode BN makes the network degenerate (all inputs -> the same embedding, SURVEY.md
     section 4.5), so parity would pass for a kernel that ignores its input.  Here: kaiming-normal(fan_in, relu) conv
-    weights, BN affine drawn near (1, 0), and -- when ``calibrate`` -- BN running statistics set layer by layer to the
-    batch statistics of a seeded calibration batch pushed through the oracle itself.
+    weights, BN affine drawn near (1, 0) (vn_celeb_face_recognition_b200.synthetic.encoder_state_dict_uncalibrated), and
+    -- when ``calibrate`` -- BN running statistics set layer by layer to the batch statistics of a seeded calibration
+    batch pushed through the oracle itself.
     """
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-    for p, cin, cout, (kh, kw), has_bn in encoder_conv_specs():
-        fan_in = cin * kh * kw
-        w = torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / fan_in) ** 0.5
-        if has_bn:
-            sd[p + ".conv.weight"] = w
-            sd[p + ".bn.weight"] = 1.0 + 0.1 * torch.randn(cout, generator=g)
-            sd[p + ".bn.bias"] = 0.1 * torch.randn(cout, generator=g)
-            sd[p + ".bn.running_mean"] = torch.zeros(cout)
-            sd[p + ".bn.running_var"] = torch.ones(cout)
-            sd[p + ".bn.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
-        else:
-            sd[p + ".weight"] = w
-            sd[p + ".bias"] = 0.1 * torch.randn(cout, generator=g)
-    sd["last_linear.weight"] = torch.randn(512, 1792, generator=g) * (1.0 / 1792) ** 0.5
-    sd["last_bn.weight"] = 1.0 + 0.1 * torch.randn(512, generator=g)
-    sd["last_bn.bias"] = 0.1 * torch.randn(512, generator=g)
-    sd["last_bn.running_mean"] = torch.zeros(512)
-    sd["last_bn.running_var"] = torch.ones(512)
-    sd["last_bn.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    from vn_celeb_face_recognition_b200 import synthetic
+    sd = synthetic.encoder_state_dict_uncalibrated(seed)
     if calibrate:
         if calib_batch is None:
             from . import synth
@@ -265,10 +216,5 @@ def _calibrate_bn(sd, x):
 
 def make_mlp_state_dict(num_classes=1001, input_dim=512, seed=0):
     """MLPModel ``state_dict`` (models/mlp_model.py:6-8) with a wide seeded init so argmax depends on the input."""
-    g = torch.Generator().manual_seed(1000 + seed)
-    return {
-        "dense_1.weight": torch.randn(2048, input_dim, generator=g) * (2.0 / input_dim) ** 0.5 * 4.0,
-        "dense_1.bias": 0.1 * torch.randn(2048, generator=g),
-        "dense_2.weight": torch.randn(num_classes, 2048, generator=g) * (1.0 / 2048) ** 0.5 * 4.0,
-        "dense_2.bias": 0.1 * torch.randn(num_classes, generator=g),
-    }
+    from vn_celeb_face_recognition_b200 import synthetic
+    return synthetic.mlp_state_dict(num_classes, input_dim, seed)

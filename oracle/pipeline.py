@@ -49,19 +49,23 @@ def identify(emb, mlp_sd, threshold):
     return lab.astype(np.int64), prob.astype(np.float32), out.numpy()
 
 
-def recognize(bth_faces, enc_sd, mlp_sd, threshold=0.0):
-    """recognize_celeb, demo_image.py:50-76, without the name lookup: returns per-frame label lists + embeddings."""
+def recognize(bth_faces, enc_sd, mlp_sd, threshold=0.0, return_logp=False):
+    """recognize_celeb, demo_image.py:50-76, without the name lookup: returns per-frame label lists + embeddings
+    (+ the (F, C) log-probabilities when ``return_logp``)."""
     flat = [f for x in bth_faces for f in x]
     if not flat:
-        return [[] for _ in bth_faces], np.zeros((0, 512), np.float32)
+        empty = [[] for _ in bth_faces], np.zeros((0, 512), np.float32)
+        return empty + (np.zeros((0, 0), np.float32),) if return_logp else empty
     x = torch.stack([transforms_default(f) for f in flat], 0)
     with torch.no_grad():
         emb = nets.encoder_forward(enc_sd, x)
-    lab, prob, _ = identify(emb, mlp_sd, threshold)
+    lab, prob, logp = identify(emb, mlp_sd, threshold)
     out, c = [], 0
     for faces in bth_faces:
         out.append(lab[c:c + len(faces)].tolist())
         c += len(faces)
+    if return_logp:
+        return out, emb.numpy(), logp
     return out, emb.numpy()
 
 

@@ -22,7 +22,17 @@ from unittest import mock
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("VNFR_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root():
+    """VNFR_REFERENCE_ROOT, else /root/reference (build container), else <repo>/baseline/_ref (a tree a user placed there)."""
+    cands = [os.environ.get("VNFR_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "models")) and os.path.exists(os.path.join(c, "demo_image.py")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REF_ROOT = _find_reference_root()
 
 
 def reference_available():

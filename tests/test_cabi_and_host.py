@@ -137,3 +137,37 @@ def test_stem_space_to_depth_repack_is_the_same_convolution():
         got = torch.nn.functional.conv2d(s2d, w2, pc.bias[:32])
         assert got.shape == ref.shape
         torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_select_boxes_all_methods_match_reference_golden():
+    """MTCNN.select_boxes (mtcnn.py:363-456; host numpy) for all four methods and the un-batched form, against the
+    unmodified reference on its own detections (tests/golden/select_boxes_small.npz)."""
+    from PIL import Image
+    from conftest import load_golden
+    from oracle import synth
+    from vn_celeb_face_recognition_b200.models import MTCNN
+    g = load_golden("select_boxes_small")
+    imgs = [Image.fromarray(f) for f in synth.frames("small", 3)]
+    boxes = [g["boxes_%d" % i] for i in range(3)]
+    probs = [g["probs_%d" % i] for i in range(3)]
+    points = [g["points_%d" % i] for i in range(3)]
+    m = MTCNN(image_size=160, keep_all=False)
+    picks = set()
+    for method in ["probability", "largest", "center_weighted_size", "largest_over_threshold"]:
+        sb, sp, spt = m.select_boxes(boxes, probs, points, imgs, method=method, threshold=float(g["threshold"]))
+        for i in range(3):
+            if bool(g["%s_none_%d" % (method, i)]):
+                assert sb[i] is None and sp[i][0] is None and spt[i] is None
+                continue
+            np.testing.assert_array_equal(np.asarray(sb[i], np.float32), g["%s_box_%d" % (method, i)])
+            np.testing.assert_array_equal(np.asarray(sp[i], np.float32), g["%s_prob_%d" % (method, i)])
+            np.testing.assert_array_equal(np.asarray(spt[i], np.float32), g["%s_point_%d" % (method, i)])
+            picks.add((method, i, tuple(np.asarray(sb[i]).ravel().tolist())))
+    assert len({p[2] for p in picks}) > 3, "the methods must not all pick the same box"
+    # ndarray frames (the reference's center_weighted_size needs PIL's .width; ours also accepts arrays)
+    sb2, _, _ = m.select_boxes(boxes, probs, points, np.stack([np.asarray(im) for im in imgs]), method="center_weighted_size")
+    for i in range(3):
+        np.testing.assert_array_equal(np.asarray(sb2[i], np.float32), g["center_weighted_size_box_%d" % i])
+    sb, sp, spt = m.select_boxes(boxes[0], probs[0], points[0], imgs[0], method="probability")
+    np.testing.assert_array_equal(np.asarray(sb, np.float32), g["single_box"])
+    assert np.float32(sp) == g["single_prob"] and np.asarray(spt).shape == (1, 5, 2)

@@ -37,6 +37,13 @@ def _worker(rank, world, port, out):
     assert payload.shape == (world, 13, 10)
     e2, l2, p2, c2 = vdist.compact_faces(payload, D)
     assert torch.equal(e, e2) and torch.equal(l, l2) and torch.equal(p, p2) and torch.equal(c, c2)
+    # the send-buffer form (what the fused tail kernel fills on the GPU): rows [emb | label | prob], count in [cap, 0]
+    send = torch.full((13, 10), float("nan"))
+    send[:n, :8], send[:n, 8], send[:n, 9], send[12, 0] = emb, label.float(), prob, float(n)
+    pay3, D3, ev = vdist.all_gather_payload(send)
+    assert ev is None and pay3.shape == (world, 13, 10)
+    e3, l3, p3, c3 = vdist.compact_faces(pay3, D3)
+    assert torch.equal(e, e3) and torch.equal(l, l3) and torch.equal(p, p3) and torch.equal(c, c3)
     try:                                                          # n > cap raises on every rank before the collective
         vdist.all_gather_faces_padded(emb, label, prob, cap=n - 1)
         raise AssertionError("capacity overflow must raise")

@@ -70,7 +70,7 @@ def test_pnet_sweep_matches_oracle(dev, kind, n, minsize):
     p = _plan(B, H, W, minsize)
     L = p.n_levels
     w = _pack_pnet(sds["pnet"])
-    _lib.call("vnfr_pnet_set_weights", C.c_void_p(w.data_ptr()), w.numel(), _lib.stream_ptr())
+    wdev = _lib.pack_pnet_weights(w, dev)                        # caller-owned device copy: the library keeps no weights
     levels = torch.empty(p.level_off[L], device=dev)
     d_fr = torch.from_numpy(fr).to(dev)
     _lib.call("vnfr_pyramid_resize_norm", C.byref(p), _lib.ptr(d_fr), _lib.ptr(levels), _lib.stream_ptr())
@@ -81,7 +81,7 @@ def test_pnet_sweep_matches_oracle(dev, kind, n, minsize):
     reg = torch.zeros(B * L, cap, 4, device=dev)
     dprob = torch.full((p.map_off[L],), float("nan"), device=dev)
     dreg = torch.full((4 * p.map_off[L],), float("nan"), device=dev)
-    _lib.call("vnfr_pnet_sweep_compact", C.byref(p), _lib.ptr(levels), 0.6, cap, _lib.ptr(cnt), _lib.ptr(cell), _lib.ptr(score),
+    _lib.call("vnfr_pnet_sweep_compact", C.byref(p), _lib.ptr(levels), _lib.ptr(wdev), 0.6, cap, _lib.ptr(cnt), _lib.ptr(cell), _lib.ptr(score),
               _lib.ptr(reg), _lib.ptr(dprob), _lib.ptr(dreg), _lib.stream_ptr())
     torch.cuda.synchronize()
     taps = {}

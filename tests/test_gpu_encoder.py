@@ -161,12 +161,13 @@ def test_pool_norm_softmax_kernels(dev, dt):
     torch.testing.assert_close(pr, ref.max(1)[0].exp(), atol=1e-6, rtol=1e-5)
 
 
-@pytest.mark.parametrize("dt,min_cos,margin_thr", [(torch.float16, 0.999, 0.02), (torch.bfloat16, 0.995, 0.15)])
+@pytest.mark.parametrize("dt,min_cos,margin_thr", [(torch.float16, 0.999, 1e-3), (torch.bfloat16, 0.995, 0.15)])
 def test_encoder_and_mlp_match_oracle_and_golden(dev, dt, min_cos, margin_thr):
     """North-star tolerances: embedding cosine >= 0.999 and identical labels -- met by the default fp16 storage type
-    (fp32 accumulation).  The optional bf16 storage type is covered at the accuracy it actually delivers (measured
-    0.9977-0.9997 over 130 layers), which is why it is not the default.  Labels are compared wherever the fp32
-    oracle's top-2 log-prob margin exceeds what 16-bit rounding can move."""
+    (fp32 accumulation) with the tail (bottleneck, L2 norm, MLP) at fp32-level accuracy.  The optional bf16 storage type is
+    covered at the accuracy it actually delivers (measured 0.9977-0.9997 over 130 layers), which is why it is not the
+    default.  A label may differ from the fp32 oracle's only where the oracle's own top-2 log-prob margin is below
+    ``margin_thr`` (fp16: 1e-3); every such face is printed."""
     from oracle import nets, synth
     from vn_celeb_face_recognition_b200.models import InceptionResnetV1, MLPModel
     sd = golden_encoder_state_dict()
@@ -175,7 +176,6 @@ def test_encoder_and_mlp_match_oracle_and_golden(dev, dt, min_cos, margin_thr):
     enc.half_dtype = dt
     enc.load_state_dict(sd)
     mlp = MLPModel(512, 1001).to(dev).eval()
-    mlp.half_dtype = dt
     mlp.load_state_dict(mlp_sd)
     x = synth.crops_160(24, seed=1)
     with torch.no_grad():
@@ -186,10 +186,10 @@ def test_encoder_and_mlp_match_oracle_and_golden(dev, dt, min_cos, margin_thr):
         lp = mlp(e)
     torch.cuda.synchronize()
     # per-stage taps first: a failure names the first broken stage
-    plan = enc._plans[(24, 160, 160)]
+    plan = enc._plans[(enc._bucket(24), 160, 160)]             # plans are bucketed: the first 24 rows are ours
     for name, key in [("conv2d_1a", "conv2d_1a"), ("conv2d_2b", "conv2d_2b"), ("conv2d_4b_repeat_1", "repeat_1.4"),
                       ("repeat_2", "repeat_2.9"), ("block8", "block8")]:
-        got = plan.taps[name].float().permute(0, 3, 1, 2).cpu()
+        got = plan.taps[name][:24].float().permute(0, 3, 1, 2).cpu()
         ref = taps[key]
         rel = (got - ref).norm() / ref.norm()
         print("stage %-12s relative error %.4f" % (key, rel))
@@ -206,13 +206,16 @@ def test_encoder_and_mlp_match_oracle_and_golden(dev, dt, min_cos, margin_thr):
     margin = top2[:, 0] - top2[:, 1]
     lab, lab_ref = lp.argmax(1).cpu(), lp_ref.argmax(1)
     sure = margin > margin_thr
-    assert sure.sum() >= 8
+    for k in (lab != lab_ref).nonzero().flatten().tolist():
+        print("face %d: label %d, oracle %d, oracle margin %.3e" % (k, lab[k], lab_ref[k], margin[k]))
+    assert sure.sum() >= 20 or dt != torch.float16
     assert torch.equal(lab[sure], lab_ref[sure]), "labels differ where the oracle margin is > %g" % margin_thr
     print("label agreement %d/24 (margin>%g: %d), min cosine %.5f" % ((lab == lab_ref).sum(), margin_thr, sure.sum(), cos.min()))
-    # MLP alone on identical inputs: log-probs within bf16 GEMM tolerance
+    # MLP alone on identical inputs: fp32-level accuracy (split-precision contractions), identical labels
     with torch.no_grad():
         lp_same = mlp(e_ref.to(dev)).cpu()
-    assert (lp_same - lp_ref).abs().max().item() < 0.08
+    assert (lp_same - lp_ref).abs().max().item() < 2e-5
+    assert torch.equal(lp_same.argmax(1), lab_ref)
     # 112x112 crops (demo_video default target size) also run
     with torch.no_grad():
         x112 = torch.nn.functional.interpolate(x[:2], size=(112, 112), mode="bilinear", align_corners=False)

@@ -235,12 +235,22 @@ def test_extract_matches_reference_golden(dev, models):
     fr = synth.frames("small", 2)
     m = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
     faces = m.extract(torch.from_numpy(fr), [g["boxes_0"], g["boxes_1"]], None)
+    # crop_resize picks its resampler by input type (detect_face.py:309-325): ndarray -> cv2.resize(INTER_AREA),
+    # PIL -> Image.resize(BILINEAR); vnfr_face_crops modes 2 / 3 restate both: at most 1 grey level off, almost everywhere 0
+    from PIL import Image
+    faces_nd = m.extract(fr, [g["boxes_0"], g["boxes_1"]], None)
+    faces_pil = m.extract([Image.fromarray(f) for f in fr], [g["boxes_0"], g["boxes_1"]], None)
     for i in range(2):
-        np.testing.assert_array_equal(faces[i].cpu().numpy(), g["faces_tensor_%d" % i])
-        # ndarray inputs use cv2.INTER_AREA in the reference (fractional-coverage weights / bilinear when enlarging):
-        # the same crop through a different resampler -- close on average, not pixel-identical
-        d = np.abs(faces[i].cpu().numpy() - g["faces_ndarray_%d" % i]) * 128.0
-        assert d.mean() < 2.0
+        assert not faces[i].is_cuda                                  # the reference returns CPU tensors
+        np.testing.assert_array_equal(faces[i].numpy(), g["faces_tensor_%d" % i])
+        for got, key in ((faces_nd[i], "faces_ndarray_%d" % i), (faces_pil[i], "faces_pil_%d" % i)):
+            d = np.abs(got.numpy() - g[key]) * 128.0
+            print("%s: max %.1f grey levels, %.4f %% of the values differ" % (key, d.max(), 100.0 * (d > 0.5).mean()))
+            assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 0.01, (key, d.max(), (d > 0.5).mean())
+    # forward() on ndarray frames = detection + INTER_AREA extraction (what every demo script passes)
+    f_nd, b_nd = m(fr)
+    for i in range(2):
+        assert (np.abs(f_nd[i].numpy() - g["faces_ndarray_%d" % i]) * 128.0 > 1.5).mean() < 0.01
     # forward(): detection + extraction, keep_all and single-face (+margin) variants
     f, b = m(torch.from_numpy(fr))
     for i in range(2):
@@ -302,20 +312,89 @@ def test_alignment_kernel_matches_cv2_path(dev, models):
                 k += 1
 
 
-#: log-probability tolerance of label parity.  The classifier of the BASELINE configs is RANDOM-INIT: the reference's own top-2
-#: margin can be far below what the allowed embedding tolerance (cosine >= 0.999, i.e. |d emb| <= 0.045) moves a logit by.
-#: A predicted label must be the reference's label, or -- only where the reference itself is that undecided -- a class whose
-#: REFERENCE log-probability lies within this tolerance of the reference's maximum (oracle/add_golden_logp.py).
-LABEL_LOGP_TOL = 0.05
+#: Label parity (north star: "predicted labels are identical").  The tail (bottleneck, L2 norm, MLP, log-softmax) runs at
+#: fp32-level accuracy (split-precision tensor-core contractions, csrc/tail_fused.cu), so a label can only differ from the
+#: reference's where the reference's own top-2 log-probability margin is below what the fp16 convolutions upstream move a
+#: logit by.  Every differing face is printed with the reference's margin, and that margin must be below this bound
+#: (random-init classifier: BASELINE.json configs; the margins of the goldens are stored beside the labels).
+#: Measured on the 96 config-3 faces with IDENTICAL crops: 95 labels identical; one face whose reference margin is 2.7e-3
+#: differs (its embedding is at cosine 0.999993 of the reference's: fp16 storage of the 130 convolution layers).
+LABEL_FLIP_MAX_MARGIN = 5e-3
 
 
-def assert_labels_match(got, ref_labels, ref_logp):
+def assert_labels_match(got, ref_labels, ref_logp, what=""):
     assert len(got) == len(ref_labels)
+    flips = []
     for k, (lab, ref) in enumerate(zip(got, ref_labels.tolist())):
-        if lab == ref:
-            continue
-        gap = float(ref_logp[k].max() - ref_logp[k][lab])
-        assert gap <= LABEL_LOGP_TOL, "face %d: label %d, reference %d (reference log-prob gap %.4f)" % (k, lab, ref, gap)
+        if lab != ref:
+            flips.append((k, lab, ref, float(ref_logp[k].max() - ref_logp[k][lab])))
+    for k, lab, ref, gap in flips:
+        print("%s face %d: label %d, reference %d, reference log-prob margin %.3e" % (what, k, lab, ref, gap))
+    assert all(gap < LABEL_FLIP_MAX_MARGIN for _, _, _, gap in flips), flips
+    return len(flips)
+
+
+def test_config3_labels_identical_to_reference(dev, models):
+    """BASELINE config 3 (1080p, min_face_size 50, demo_video alignment, random-init encoder + MLP): 8 frames = 96 faces vs
+    the UNMODIFIED reference's boxes, embeddings and labels (tests/golden/pipeline_1080p_labels.npz,
+    oracle/make_golden_labels.py).
+
+    (a) embed + classify on IDENTICAL aligned crops (the oracle's, which reproduce the reference's): labels must be
+        identical -- a face may differ only where the reference's own top-2 log-prob margin is < 5e-3 (at most 2 of the
+        96), and is printed with that margin.
+    (b) the fused pipeline end to end: identical face counts, boxes at IoU >= 0.99, embeddings at cosine >= 0.999.  Its
+        aligned crops differ from the reference's in ~0.1 % of the pixels by a few grey levels: landmarks agree to ~1e-4 px
+        (fp32 summation order of the detector), and cv2.warpAffine's 1/32-px fixed-point coordinates flip at that level.
+        The RANDOM-INIT encoder amplifies such a crop difference ~20x (measured: cosine 0.9997-0.99999 end to end vs
+        >= 0.99996 on identical crops), which moves some faces whose reference margin is ~1e-2 across the decision boundary.
+        These flips are a property of the input perturbation, not of the encoder / classifier arithmetic: every one of them
+        must have a crop that differs from the oracle's (or be one of the faces of (a)); they are printed with the reference
+        margin and bounded in number."""
+    from oracle import synth, align, pipeline as opipe
+    from vn_celeb_face_recognition_b200 import pipeline
+    g = load_golden("pipeline_1080p_labels")
+    fr = synth.frames("1080p", 8)
+    cnt = g["count"].tolist()
+    F = sum(cnt)
+    assert F >= 96
+    # ---- (a) identical crops
+    faces, _ = opipe.parallel_detect_and_align(list(fr), synth.mtcnn_state_dicts(), align.CENTER_POINTS[(160, 160)], (160, 160),
+                                               min_face_size=50)
+    assert [len(x) for x in faces] == cnt
+    flat = np.stack([f for x in faces for f in x])
+    x = torch.stack([pipeline.transforms_default(f) for f in flat]).to(dev)
+    with torch.no_grad():
+        e_a = models["enc"](x)
+        lab_a = models["mlp"](e_a).argmax(1).cpu().numpy()
+    e_a = e_a.cpu().numpy()
+    cos_a = (e_a * g["emb"]).sum(1)
+    flips_a = assert_labels_match(lab_a.tolist(), g["labels"], g["logp"], "(a) identical crops:")
+    print("(a) identical crops: %d faces, %d label flips, min cosine vs reference %.6f, smallest reference margin %.2e"
+          % (F, flips_a, cos_a.min(), float(g["margin"].min())))
+    assert cos_a.min() >= 0.9999 and flips_a <= 2
+    # ---- (b) end to end
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    fp = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", return_faces_u8=True)
+    out = fp.run_device(torch.from_numpy(fr).to(dev))
+    assert out["count"].cpu().tolist() == cnt
+    boxes = out["boxes"].cpu().numpy()
+    o = 0
+    for i, n in enumerate(cnt):
+        assert_boxes_match(boxes[i, :n, :4], g["boxes"][o:o + n], 0.99)
+        o += n
+    lab_b, emb_b, u8_b = out["label"].cpu().numpy(), out["emb"].cpu().numpy(), out["faces_u8"].cpu().numpy()
+    cos_b = (emb_b * g["emb"]).sum(1)
+    flips_b = np.nonzero(lab_b != g["labels"])[0]
+    for k in flips_b:
+        d = np.abs(u8_b[k].astype(int) - flat[k].astype(int))
+        print("(b) end to end: face %d: label %d, reference %d, reference margin %.3e, cosine %.6f, crop differs from the "
+              "reference's in %.3f %% of the values (max %d levels)" % (k, lab_b[k], g["labels"][k], g["margin"][k], cos_b[k],
+                                                                        100.0 * (d > 0).mean(), d.max()))
+        assert d.max() > 0 or lab_a[k] != g["labels"][k], "face %d differs although its crop and its identical-crop label do not" % k
+    print("(b) end to end: %d faces, %d label flips (all on crops that differ from the reference's), min cosine %.6f"
+          % (F, len(flips_b), cos_b.min()))
+    assert cos_b.min() >= 0.999
+    assert len(flips_b) <= F // 10
 
 
 def test_demo_video_path_matches_reference_golden(dev, models):
@@ -461,3 +540,42 @@ def test_crop_workspace_overflow_grows_and_repeats(dev, models):
     for a, b in zip(got, ref):
         for x, y in zip(a, b):
             np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+
+
+def test_classify_head_and_per_class_thresholds_match_reference_golden(dev, models):
+    """InceptionResnetV1(classify=True) (inception_resnet_v1.py:298-300) and identify_person with the per-class threshold
+    dict of local_thresholds.json (demo_image.py:113-147) against the unmodified reference (tests/golden/heads_seed0.npz)."""
+    import pandas as pd
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import pipeline
+    from vn_celeb_face_recognition_b200.models import InceptionResnetV1
+    h = load_golden("heads_seed0")
+    sd = golden_encoder_state_dict()
+    sd["logits.weight"], sd["logits.bias"] = torch.from_numpy(h["logits_weight"]), torch.from_numpy(h["logits_bias"])
+    enc = InceptionResnetV1(pretrained=None, classify=True, num_classes=10, device=dev).eval()
+    enc.load_state_dict(sd)
+    with torch.no_grad():
+        out = enc(synth.crops_160(4, seed=2).to(dev)).cpu().numpy()
+    assert out.shape == (4, 10)
+    # un-normalised bottleneck output -> logits: fp16 convolutions upstream (the head itself is fp32-accurate, test_gpu_tail.py)
+    assert np.abs(out - h["classify_logp"]).max() < 0.05 and (out.argmax(1) == h["classify_logp"].argmax(1)).all()
+    # identify_person on the reference's own embeddings: per-class dict and scalar thresholds
+    emb = torch.from_numpy(load_golden("encoder_seed0")["emb"]).to(dev)
+    name_df = pd.DataFrame({"label": np.arange(1001), "name": ["id%d" % i for i in range(1001)]})
+    thr_dict = {str(i): float(v) for i, v in enumerate(h["thr_vals"])}
+    assert pipeline.identify_person(emb, models["mlp"], name_df, thr_dict) == [str(n) for n in h["names_per_class_thr"]]
+    assert pipeline.identify_person(emb, models["mlp"], name_df, float(h["scalar_thr"])) == [str(n) for n in h["names_scalar_thr"]]
+    # the fused pipeline applies the same per-class thresholds inside the tail kernel
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    fr = synth.frames("small", 2, first_seed=3)
+    base = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity")(fr)
+    probs = np.concatenate([r["probs"] for r in base])
+    labels = np.concatenate([r["labels"] for r in base])
+    thr = {str(i): 0.0 for i in range(1001)}
+    for k in range(0, len(labels), 2):
+        thr[str(int(labels[k]))] = 2.0                                   # every other face's class becomes unreachable
+    got = np.concatenate([r["labels"] for r in pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity",
+                                                                      threshold=thr)(fr)])
+    exp = np.array([1001 if thr[str(int(l))] > p else int(l) for l, p in zip(labels, probs)])
+    np.testing.assert_array_equal(got, exp)
+    assert (got == 1001).any() and (got != 1001).any()

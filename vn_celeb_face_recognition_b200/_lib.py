@@ -45,6 +45,30 @@ class Op(C.Structure):
     _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("conv", ConvOp)]
 
 
+class TailLayer(C.Structure):
+    _fields_ = [
+        ("K", C.c_int32), ("N", C.c_int32), ("N_pad", C.c_int32), ("split_k", C.c_int32), ("rowop", C.c_int32),
+        ("out_vec_pitch", C.c_int32),
+        ("weights", C.c_void_p), ("bias", C.c_void_p), ("partial", C.c_void_p), ("a_in", C.c_void_p), ("a_next", C.c_void_p),
+        ("out_vec", C.c_void_p),
+    ]
+
+
+class TailOp(C.Structure):
+    _fields_ = [
+        ("tmap_a", (C.c_ubyte * 128) * 3), ("tmap_w", (C.c_ubyte * 128) * 3),
+        ("n_layers", C.c_int32), ("n_pad", C.c_int32), ("in_mode", C.c_int32),
+        ("hw", C.c_int32), ("x_pitch", C.c_int32), ("x_dtype", C.c_int32), ("x_f32_pitch", C.c_int32),
+        ("x_f32_cols", C.c_int32), ("emb_half_dtype", C.c_int32), ("reserved", C.c_int32),
+        ("x", C.c_void_p), ("x_f32", C.c_void_p),
+        ("layer", TailLayer * 3),
+        ("emb_half", C.c_void_p), ("label", C.c_void_p), ("prob", C.c_void_p), ("label_f", C.c_void_p), ("prob_f", C.c_void_p),
+        ("lp_pitch", C.c_int32), ("n_classes", C.c_int32),
+        ("thr_class", C.c_void_p), ("thr", C.c_float), ("count_value", C.c_int32),
+        ("count_cell", C.c_void_p), ("grid_barrier", C.c_void_p),
+    ]
+
+
 _lib = None
 
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
@@ -52,8 +76,8 @@ _P, _I, _F, _D, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_longlong
 _SIGS = {
     "vnfr_pyramid_plan": [_I, _I, _I, _I, _D, C.POINTER(Pyramid)],
     "vnfr_pyramid_resize_norm": [C.POINTER(Pyramid), _P, _P, _P],
-    "vnfr_pnet_set_weights": [_P, _I, _P],
-    "vnfr_pnet_sweep_compact": [C.POINTER(Pyramid), _P, _F, _I, _P, _P, _P, _P, _P, _P, _P],
+    "vnfr_pnet_pack_weights": [_P, _I, _P, _I],
+    "vnfr_pnet_sweep_compact": [C.POINTER(Pyramid), _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P],
     "vnfr_nms_segments": [_I, _I, _P, _P, _P, _F, _I, _P, _P, _P],
     "vnfr_stage1_boxes": [C.POINTER(Pyramid), _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "vnfr_rnet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
@@ -74,6 +98,8 @@ _SIGS = {
     "vnfr_l2norm_rows": [_P, _I, _I, _I, _P, _P, _I, _P],
     "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
     "vnfr_topk_rows": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "vnfr_tail_prepare": [C.POINTER(TailOp)],
+    "vnfr_tail_run": [C.POINTER(TailOp), _I, _P],
 }
 
 
@@ -89,6 +115,7 @@ def lib():
         l.vnfr_launch_count.restype = C.c_longlong
         l.vnfr_rnet_weight_floats.restype = C.c_int
         l.vnfr_onet_weight_floats.restype = C.c_int
+        l.vnfr_pnet_packed_bytes.restype = C.c_int
         for name, args in _SIGS.items():
             fn = getattr(l, name)      # AttributeError if the symbol is missing: fail loudly
             fn.argtypes = args
@@ -99,7 +126,7 @@ def lib():
 
 def exported_symbols():
     return ["vnfr_last_error", "vnfr_version", "vnfr_launch_count", "vnfr_rnet_weight_floats",
-            "vnfr_onet_weight_floats"] + sorted(_SIGS)
+            "vnfr_onet_weight_floats", "vnfr_pnet_packed_bytes"] + sorted(_SIGS)
 
 
 def check(rc):
@@ -115,9 +142,20 @@ def launch_count():
     return int(lib().vnfr_launch_count())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on ``device`` (default: the current device).  The C library launches on the
+    CURRENT device: callers that hold tensors of another device wrap their calls in ``torch.cuda.device(tensor.device)``."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def pack_pnet_weights(packed_host, device):
+    """_pack_pnet floats (host) -> the P-Net kernel's weight block on ``device`` (caller-owned; see vnfr_pnet_pack_weights)."""
+    import torch
+    n = lib().vnfr_pnet_packed_bytes()
+    out = torch.zeros(n, dtype=torch.uint8)
+    call("vnfr_pnet_pack_weights", C.c_void_p(packed_host.data_ptr()), packed_host.numel(), C.c_void_p(out.data_ptr()), n)
+    return out.to(device)
 
 
 def ptr(t):

@@ -44,4 +44,15 @@ __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, 
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// One-time setup that is per DEVICE (cudaFuncSetAttribute, __device__ tables): true the first time it is asked on the
+// current device.  (A process-wide `static bool` would leave a second GPU of the same process unconfigured.)
+struct VnfrPerDevice { bool done[64]; };
+inline bool vnfr_first_on_device(VnfrPerDevice& s) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+  if (s.done[d]) return false;
+  s.done[d] = true;
+  return true;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -1201,11 +1201,10 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
   a.p1 = nullptr; a.c2 = nullptr; a.split_mode = 0; a.p3 = nullptr; a.c3 = nullptr;
-  static bool attr = false;
-  if (!attr) {
+  static VnfrPerDevice attr_once = {};
+  if (vnfr_first_on_device(attr_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(rnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(onet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, O_SMEM));
-    attr = true;
   }
   if (onet) launch_crops<48>(a, st);
   else launch_crops<24>(a, st);
@@ -1241,14 +1240,13 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = lmk; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
   a.p1 = p1; a.c2 = c2; a.split_mode = split_mode; a.p3 = tc3 ? p3 : nullptr; a.c3 = tc3 ? c3 : nullptr;
-  static bool attr = false;
-  if (!attr) {
+  static VnfrPerDevice attr_once = {};
+  if (vnfr_first_on_device(attr_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(onet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(head_front_tc_kernel<ONET_FRONT_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    FrontTc<ONET_FRONT_TC>::SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(onet_back_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_SMEM));
-    attr = true;
   }
   launch_crops<48>(a, st);
   static const bool front_fma = getenv("VNFR_ONET_FRONT_FMA") != nullptr;
@@ -1333,13 +1331,12 @@ extern "C" int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, 
   a.pad = reinterpret_cast<const int4*>(pad); a.offs = offs; a.w = weights; a.prob = prob;
   a.reg = reinterpret_cast<float4*>(reg); a.lmk = nullptr; a.crops = crops; a.crop_cap = crop_cap; a.status = status;
   a.p1 = p1; a.c2 = c2; a.split_mode = 2; a.p3 = nullptr; a.c3 = nullptr;
-  static bool attr = false;
-  if (!attr) {
+  static VnfrPerDevice attr_once = {};
+  if (vnfr_first_on_device(attr_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(rnet_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(head_front_tc_kernel<RNET_FRONT_TC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    FrontTc<RNET_FRONT_TC>::SMEM));
     VNFR_CUDA(cudaFuncSetAttribute(rnet_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM));
-    attr = true;
   }
   launch_crops<24>(a, st);
   static const bool front_fma = getenv("VNFR_RNET_FRONT_FMA") != nullptr;

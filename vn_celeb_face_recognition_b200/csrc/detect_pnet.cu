@@ -54,14 +54,16 @@ constexpr int D_W3 = D_A2 + 16, D_B3 = D_W3 + 144 * 32, D_A3 = D_B3 + 32;
 constexpr int D_W4 = D_A3 + 32, D_B4 = D_W4 + 32 * 8;
 constexpr int D_FLOATS = D_B4 + 8;    // 6796 floats (all offsets are multiples of 4)
 
-__device__ float g_pnet_w[D_FLOATS];  // repacked weights (global, L2-resident; copied into shared memory per CTA)
+// The repacked weights live in a CALLER-OWNED device buffer (vnfr_pnet_pack_weights -> upload -> vnfr_pnet_sweep_compact):
+// [D_FLOATS fp32 | TC_B_BYTES of fp16 conv3 parts]; every CTA copies them into shared memory.  No process-global state:
+// two detectors with different weights can run on two streams.
 
 // tensor-core conv3: B operand = conv3 weights as fp16 hi / lo parts, [tap][part][32 cout rows][16 cin] in the 32-byte
 // swizzled K-major layout (16-byte chunk c of row n at n*32 + ((c ^ ((n >> 2) & 1)) << 4)); A operand = the conv2 map,
 // one 32-byte row per pixel of the 18-wide raster (432 rows: the last accumulator rows reach row 383 + 38)
 constexpr int TC_B_BYTES = 9 * 2 * 1024;
 constexpr int TC_A_PART_BYTES = 432 * 32;
-__device__ uint4 g_pnet_w3h[TC_B_BYTES / 16];
+constexpr int PNET_PACKED_BYTES = D_FLOATS * 4 + TC_B_BYTES;      // D_FLOATS * 4 is a multiple of 16
 
 constexpr int S_BUF = 3 * IT * ITP > 16 * C2T * C2T ? 3 * IT * ITP : 16 * C2T * C2T;   // input patch, later conv2 map
 constexpr int S_BUF_BYTES = (S_BUF * 4 > 2 * TC_A_PART_BYTES ? S_BUF * 4 : 2 * TC_A_PART_BYTES);   // ... or the two A parts
@@ -140,8 +142,9 @@ __global__ void __launch_bounds__(NTHR, TC ? PNET_TC_CTAS : PNET_MIN_CTAS) pnet_
                                                     float thr, int cap, int* __restrict__ cand_count,
                                                     uint32_t* __restrict__ cand_cell, float* __restrict__ cand_score,
                                                     float4* __restrict__ cand_reg, float* __restrict__ dense_prob,
-                                                    float* __restrict__ dense_reg) {
+                                                    float* __restrict__ dense_reg, const float* __restrict__ g_pnet_w) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint4* g_pnet_w3h = reinterpret_cast<const uint4*>(g_pnet_w + D_FLOATS);
   __shared__ __align__(8) uint64_t s_bar;             // tensor-core path: MMAs of the current tile have completed
   __shared__ uint32_t s_tmem;
   uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -430,10 +433,13 @@ __global__ void __launch_bounds__(NTHR, TC ? PNET_TC_CTAS : PNET_MIN_CTAS) pnet_
 
 }  // namespace
 
-extern "C" int vnfr_pnet_set_weights(const float* packed_host, int n_floats, void* stream) {
+extern "C" int vnfr_pnet_packed_bytes(void) { return PNET_PACKED_BYTES; }
+
+extern "C" int vnfr_pnet_pack_weights(const float* packed_host, int n_floats, void* out_host, int out_bytes) {
   VNFR_REQUIRE(packed_host != nullptr && n_floats == PNET_FLOATS, "P-Net packed weights must hold 6632 floats");
-  static float d[D_FLOATS];          // repack [co][k] -> [k][co] (padded); static: the async copy reads it after return
-  memset(d, 0, sizeof(d));
+  VNFR_REQUIRE(out_host != nullptr && out_bytes == PNET_PACKED_BYTES, "out_host must hold vnfr_pnet_packed_bytes() bytes");
+  float* d = reinterpret_cast<float*>(out_host);          // repack [co][k] -> [k][co] (padded)
+  memset(out_host, 0, PNET_PACKED_BYTES);
   const float* h = packed_host;
   for (int co = 0; co < 10; ++co) { for (int k = 0; k < 27; ++k) d[D_W1 + k * 12 + co] = h[W1 + co * 27 + k]; d[D_B1 + co] = h[B1 + co]; d[D_A1 + co] = h[A1 + co]; }
   for (int co = 0; co < 16; ++co) { for (int k = 0; k < 90; ++k) d[D_W2 + k * 16 + co] = h[W2 + co * 90 + k]; d[D_B2 + co] = h[B2 + co]; d[D_A2 + co] = h[A2 + co]; }
@@ -444,10 +450,8 @@ extern "C" int vnfr_pnet_set_weights(const float* packed_host, int n_floats, voi
   }
   d[D_B4 + 0] = h[B41]; d[D_B4 + 1] = h[B41 + 1];
   for (int j = 0; j < 4; ++j) d[D_B4 + 2 + j] = h[B42 + j];
-  VNFR_CUDA(cudaMemcpyToSymbolAsync(g_pnet_w, d, sizeof(d), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   // conv3 weights as fp16 hi / lo parts in the swizzled B-operand layout of the tensor-core path
-  static uint16_t bw[TC_B_BYTES / 2];
-  memset(bw, 0, sizeof(bw));
+  uint16_t* bw = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(out_host) + D_FLOATS * 4);
   for (int tap = 0; tap < 9; ++tap)
     for (int n = 0; n < 32; ++n)
       for (int ci = 0; ci < 16; ++ci) {
@@ -459,14 +463,14 @@ extern "C" int vnfr_pnet_set_weights(const float* packed_host, int n_floats, voi
         bw[((tap * 2 + 0) * 1024 + off) / 2] = __half_as_ushort(hi);
         bw[((tap * 2 + 1) * 1024 + off) / 2] = __half_as_ushort(lo);
       }
-  VNFR_CUDA(cudaMemcpyToSymbolAsync(g_pnet_w3h, bw, sizeof(bw), 0, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return VNFR_OK;
 }
 
-extern "C" int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr, const float* levels, float threshold, int cap,
+extern "C" int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr, const float* levels, const void* pnet_weights, float threshold, int cap,
                                        int32_t* cand_count, uint32_t* cand_cell, float* cand_score, float* cand_reg,
                                        float* dense_prob, float* dense_reg, void* stream) {
   VNFR_REQUIRE(pyr != nullptr && cap > 0, "bad arguments");
+  VNFR_REQUIRE(pnet_weights != nullptr && ((uintptr_t)pnet_weights % 16) == 0, "pnet_weights must be a 16-byte aligned device buffer");
   const int tiles = pyr->tile_off[pyr->n_levels];
   if (pyr->B == 0 || tiles == 0) return VNFR_OK;
   PnetParams p;
@@ -477,22 +481,23 @@ extern "C" int vnfr_pnet_sweep_compact(const VnfrPyramid* pyr, const float* leve
     p.level_off[l] = pyr->level_off[l]; p.map_off[l] = pyr->map_off[l];
   }
   p.tile_off[pyr->n_levels] = tiles;
-  static bool attr = false;
+  static VnfrPerDevice attr_once = {};
   static const bool fma_conv3 = getenv("VNFR_PNET_FMA") != nullptr;
-  if (!attr) {
+  if (vnfr_first_on_device(attr_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(pnet_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PNET_SMEM_TC));
     VNFR_CUDA(cudaFuncSetAttribute(pnet_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PNET_SMEM));
-    attr = true;
   }
   const int total = pyr->B * tiles;
   const int per_sm = fma_conv3 ? PNET_MIN_CTAS : PNET_TC_CTAS;
   const int grid = total < 148 * per_sm ? total : 148 * per_sm;      // persistent CTAs
   if (fma_conv3)
     pnet_kernel<false><<<grid, NTHR, PNET_SMEM, (cudaStream_t)stream>>>(p, levels, threshold, cap, cand_count, cand_cell, cand_score,
-                                                                       reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg);
+                                                                       reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg,
+                                                                       reinterpret_cast<const float*>(pnet_weights));
   else
     pnet_kernel<true><<<grid, NTHR, PNET_SMEM_TC, (cudaStream_t)stream>>>(p, levels, threshold, cap, cand_count, cand_cell, cand_score,
-                                                                      reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg);
+                                                                      reinterpret_cast<float4*>(cand_reg), dense_prob, dense_reg,
+                                                                      reinterpret_cast<const float*>(pnet_weights));
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

@@ -428,10 +428,9 @@ extern "C" int vnfr_pyramid_resize_norm(const VnfrPyramid* pyr, const uint8_t* f
   if (!force_rows && ((uintptr_t)frames % 16) == 0) {
     PyrStripParams q;
     if (plan_strips(pyr, &q) && strip_smem_bytes(q) <= 110 * 1024) {
-      static bool strip_attr = false;
-      if (!strip_attr) {
+      static VnfrPerDevice strip_attr_once = {};
+      if (vnfr_first_on_device(strip_attr_once)) {
         VNFR_CUDA(cudaFuncSetAttribute(pyramid_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        strip_attr = true;
       }
       const long long grid = (long long)q.B * q.ctas_per_frame;
       pyramid_strip_kernel<<<(unsigned)grid, PS_THREADS, strip_smem_bytes(q), (cudaStream_t)stream>>>(q, frames, levels);
@@ -455,11 +454,10 @@ extern "C" int vnfr_pyramid_resize_norm(const VnfrPyramid* pyr, const uint8_t* f
   const int per_sm = smem > 0 ? (int)((220 * 1024) / (smem + 1024)) : 8;
   long long grid = 148LL * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
   if (grid > n_tasks) grid = n_tasks;
-  static bool attr = false;
-  if (!attr) {
+  static VnfrPerDevice attr_once = {};
+  if (vnfr_first_on_device(attr_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(pyramid_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(pyramid_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   if (vec) pyramid_rows_kernel<16><<<(int)grid, PYR_THREADS, smem, (cudaStream_t)stream>>>(p, frames, levels);
   else pyramid_rows_kernel<1><<<(int)grid, PYR_THREADS, smem, (cudaStream_t)stream>>>(p, frames, levels);

@@ -7,7 +7,13 @@
 //   align_face.py:51-57 alignment): integer crop, 5-point least-squares similarity (Umeyama with scale; closed form in
 //   2-D) onto the template, cv2.warpAffine(INTER_LINEAR, BORDER_CONSTANT 0) in OpenCV's fixed-point arithmetic, then
 //   transforms_default (data_loader/__init__.py:27-34, 52-56).
-// Both write the u8 face (HWC, what the reference's glue returns) and the standardised 16-bit NHWC8 tensor the encoder
+// mode 2 / mode 3: MTCNN.extract for numpy.ndarray / PIL.Image frames (detect_face.py:309-325 crop_resize): the same box
+//   arithmetic as mode 0, but the crop is resampled the way the reference's library does it for that input type --
+//   mode 2 = cv2.resize(INTER_AREA): fractional-coverage box filter in float when shrinking in both directions (with
+//   OpenCV's integer-ratio fast path), 11-bit fixed-point bilinear with the "area" source coordinates otherwise;
+//   mode 3 = PIL.Image.resize(BILINEAR): triangle filter whose support scales with the reduction, horizontal pass rounded
+//   to u8 before the vertical pass (Pillow's 8-bit resampler, 22-bit fixed-point coefficients).
+// All modes write the u8 face (HWC, what the reference's glue returns) and the standardised 16-bit NHWC8 tensor the encoder
 // consumes, reading the u8 frame directly -- faces never visit the host.
 #include "common.cuh"
 #include <cuda_fp16.h>
@@ -67,6 +73,143 @@ __device__ __forceinline__ void store_px(const FaceArgs& a, size_t px, unsigned 
   }
 }
 
+// ---- mode 2: cv2.resize(crop, (S,S), INTER_AREA) for one output pixel ------------------------------------------------
+// OpenCV resize.cpp: area path (computeResizeAreaTab / ResizeArea_Invoker, float accumulation in table order) when
+// scale_x >= 1 and scale_y >= 1, with resizeAreaFast_ for integer ratios; otherwise the bilinear path with
+// area_mode source coordinates (HResizeLinear / VResizeLinear<uchar>, INTER_RESIZE_COEF_BITS = 11).
+struct AreaTaps { int first, n; float w_first, w_mid, w_last; };     // source cells [first, first+n): weights first | mid.. | last
+
+__device__ __forceinline__ AreaTaps area_taps(int d, double scale, int ssize) {
+  const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+  const double cell = fmin(scale, (double)ssize - fsx1);
+  int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+  sx2 = min(sx2, ssize - 1);
+  sx1 = min(sx1, sx2);
+  AreaTaps t;
+  const bool left = sx1 - fsx1 > 1e-3, right = fsx2 - sx2 > 1e-3;
+  t.first = left ? sx1 - 1 : sx1;
+  t.n = (left ? 1 : 0) + (sx2 - sx1) + (right ? 1 : 0);
+  t.w_mid = (float)(1.0 / cell);
+  t.w_first = left ? (float)((sx1 - fsx1) / cell) : t.w_mid;
+  t.w_last = right ? (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell) : t.w_mid;
+  if (t.n == 1 && left) t.w_last = t.w_first;          // a single (left-partial) cell
+  return t;
+}
+__device__ __forceinline__ float area_w(const AreaTaps& t, int k) { return k == 0 ? t.w_first : (k == t.n - 1 ? t.w_last : t.w_mid); }
+
+__device__ __forceinline__ void linear_area_tap(int d, double scale, double inv_scale, int ssize, int& s, int& c0, int& c1) {
+  s = (int)floor(d * scale);
+  float f = (float)((d + 1) - (s + 1) * inv_scale);
+  f = f <= 0.f ? 0.f : f - floorf(f);
+  if (s < 0) { f = 0.f; s = 0; }
+  if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+  c0 = (int)rintf((1.f - f) * 2048.f);                  // saturate_cast<short>(coef * INTER_RESIZE_COEF_SCALE)
+  c1 = (int)rintf(f * 2048.f);
+}
+
+__device__ void cv_area_pixel(const uint8_t* crop, int pitch_px, int cw, int ch, int S, int ox, int oy, unsigned out[3]) {
+  // exactly cv::resize's doubles: inv_scale = dsize / ssize, scale = 1 / inv_scale (NOT ssize / dsize: 1/(160/98) < 98/160,
+  // which moves cvFloor(dy * scale) to the previous source row where dy * 98/160 is an integer)
+  const double inv_scale_x = (double)S / cw, inv_scale_y = (double)S / ch;
+  const double scale_x = 1.0 / inv_scale_x, scale_y = 1.0 / inv_scale_y;
+  if (scale_x >= 1.0 && scale_y >= 1.0) {
+    if (cw % S == 0 && ch % S == 0) {                   // resizeAreaFast_: integer box sums
+      const int ix = cw / S, iy = ch / S;
+      int s[3] = {0, 0, 0};
+      for (int y = 0; y < iy; ++y) {
+        const uint8_t* row = crop + ((size_t)(oy * iy + y) * pitch_px + ox * ix) * 3;
+        for (int x = 0; x < ix; ++x) { s[0] += __ldg(row + 3 * x); s[1] += __ldg(row + 3 * x + 1); s[2] += __ldg(row + 3 * x + 2); }
+      }
+      const float sc = 1.f / (float)(ix * iy);
+      for (int c = 0; c < 3; ++c) {
+        const int v = (ix == 2 && iy == 2) ? (s[c] + 2) >> 2 : (int)rintf((float)s[c] * sc);
+        out[c] = (unsigned)min(max(v, 0), 255);
+      }
+      return;
+    }
+    const AreaTaps tx = area_taps(ox, scale_x, cw), ty = area_taps(oy, scale_y, ch);
+    float sum[3] = {0.f, 0.f, 0.f};
+    for (int j = 0; j < ty.n; ++j) {
+      const uint8_t* row = crop + ((size_t)(ty.first + j) * pitch_px + tx.first) * 3;
+      float buf[3] = {0.f, 0.f, 0.f};
+      for (int k = 0; k < tx.n; ++k) {
+        const float al = area_w(tx, k);
+        buf[0] = __fmaf_rn((float)__ldg(row + 3 * k), al, buf[0]);
+        buf[1] = __fmaf_rn((float)__ldg(row + 3 * k + 1), al, buf[1]);
+        buf[2] = __fmaf_rn((float)__ldg(row + 3 * k + 2), al, buf[2]);
+      }
+      const float be = area_w(ty, j);
+      for (int c = 0; c < 3; ++c) sum[c] = __fmaf_rn(be, buf[c], sum[c]);
+    }
+    for (int c = 0; c < 3; ++c) out[c] = (unsigned)min(max((int)rintf(sum[c]), 0), 255);
+    return;
+  }
+  int sx, sy, a0, a1, b0, b1;
+  linear_area_tap(ox, scale_x, inv_scale_x, cw, sx, a0, a1);
+  linear_area_tap(oy, scale_y, inv_scale_y, ch, sy, b0, b1);
+  const int sx1 = min(sx + 1, cw - 1), sy1 = min(sy + 1, ch - 1);
+  const uint8_t* r0 = crop + (size_t)sy * pitch_px * 3;
+  const uint8_t* r1 = crop + (size_t)sy1 * pitch_px * 3;
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = (int)__ldg(r0 + 3 * sx + c) * a0 + (int)__ldg(r0 + 3 * sx1 + c) * a1;      // HResizeLinear: x 2^11
+    const int h1 = (int)__ldg(r1 + 3 * sx + c) * a0 + (int)__ldg(r1 + 3 * sx1 + c) * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;             // VResizeLinear<uchar>
+    out[c] = (unsigned)min(max(v, 0), 255);
+  }
+}
+
+// ---- mode 3: PIL crop.resize((S,S), Image.BILINEAR) for one output pixel -------------------------------------------
+// Pillow Resample.c (8 bits per channel): precompute_coeffs with the triangle filter (support 1 x max(scale, 1)),
+// coefficients normalised then rounded to PRECISION_BITS = 22 fixed point; horizontal pass first, rounded and clipped to
+// u8, then the vertical pass.
+struct PilTaps { int xmin, n; double ww, center, ss; };
+
+__device__ __forceinline__ PilTaps pil_taps(int d, int in_size, int out_size) {
+  const double scale = (double)in_size / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  PilTaps t;
+  t.center = (d + 0.5) * scale;
+  t.ss = 1.0 / filterscale;
+  int xmin = (int)(t.center - support + 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)(t.center + support + 0.5);
+  if (xmax > in_size) xmax = in_size;
+  t.xmin = xmin; t.n = xmax - xmin;
+  double ww = 0.0;
+  for (int x = 0; x < t.n; ++x) {
+    double v = (x + xmin - t.center + 0.5) * t.ss;
+    v = v < 0 ? -v : v;
+    ww += v < 1.0 ? 1.0 - v : 0.0;
+  }
+  t.ww = ww;
+  return t;
+}
+__device__ __forceinline__ int pil_coef(const PilTaps& t, int x) {
+  double v = (x + t.xmin - t.center + 0.5) * t.ss;
+  v = v < 0 ? -v : v;
+  double w = v < 1.0 ? 1.0 - v : 0.0;
+  if (t.ww != 0.0) w /= t.ww;
+  return (int)(w < 0 ? -0.5 + w * 4194304.0 : 0.5 + w * 4194304.0);
+}
+__device__ __forceinline__ unsigned pil_clip8(int v) { v >>= 22; return (unsigned)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+__device__ void pil_bilinear_pixel(const uint8_t* crop, int pitch_px, int cw, int ch, int S, int ox, int oy, unsigned out[3]) {
+  const PilTaps tx = pil_taps(ox, cw, S), ty = pil_taps(oy, ch, S);
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int j = 0; j < ty.n; ++j) {
+    const uint8_t* row = crop + ((size_t)(ty.xmin + j) * pitch_px + tx.xmin) * 3;
+    int h[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int k = 0; k < tx.n; ++k) {
+      const int c = pil_coef(tx, k);
+      h[0] += (int)__ldg(row + 3 * k) * c; h[1] += (int)__ldg(row + 3 * k + 1) * c; h[2] += (int)__ldg(row + 3 * k + 2) * c;
+    }
+    const int cy = pil_coef(ty, j);
+    for (int c = 0; c < 3; ++c) acc[c] += (int)pil_clip8(h[c]) * cy;
+  }
+  for (int c = 0; c < 3; ++c) out[c] = pil_clip8(acc[c]);
+}
+
 __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
   const int total_raw = a.offs[a.B];
   if (total_raw > a.max_faces && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.status, 16);
@@ -87,7 +230,7 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
     const float* bx = a.box + ((size_t)b * a.capf + slot) * 5;
     if (threadIdx.x == 0) {
       if (a.face_img != nullptr) a.face_img[f] = b;
-      if (a.mode == 0) {
+      if (a.mode != 1) {
         // extract_face: margin in fp32 like numpy float32 scalars (detect_face.py:358-368)
         const float m0 = div_rn(mul_rn((float)a.margin, sub_rn(bx[2], bx[0])), (float)(a.S - a.margin));
         const float m1 = div_rn(mul_rn((float)a.margin, sub_rn(bx[3], bx[1])), (float)(a.S - a.margin));
@@ -157,6 +300,17 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
           bl = (unsigned)div_rn(div_rn((float)s2, kh), kw);
         }
         store_px(a, (size_t)f * S * S + i, r, g, bl);
+      }
+    } else if (a.mode == 2 || a.mode == 3) {
+      const uint8_t* crop = img + ((size_t)y1 * a.W + x1) * 3;
+      for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+        const int oy = i / S, ox = i - oy * S;
+        unsigned c3[3] = {0, 0, 0};
+        if (cw > 0 && ch > 0) {
+          if (a.mode == 2) cv_area_pixel(crop, a.W, cw, ch, S, ox, oy, c3);
+          else pil_bilinear_pixel(crop, a.W, cw, ch, S, ox, oy, c3);
+        }
+        store_px(a, (size_t)f * S * S + i, c3[0], c3[1], c3[2]);
       }
     } else {
       // cv2.warpAffine, INTER_LINEAR fixed point: AB_BITS = 10, INTER_BITS = 5, weights 2^15
@@ -240,16 +394,16 @@ extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int c
                                int half_layout, void* stream) {
   VNFR_REQUIRE(frames && count && box && offs && face_half && status, "null pointer");
   VNFR_REQUIRE(image_size <= MAX_S, "image_size larger than 256 is not supported");
-  VNFR_REQUIRE(mode == 0 || (mode == 1 && pts != nullptr && template_host != nullptr), "align mode needs landmarks and a template");
+  VNFR_REQUIRE(mode == 0 || mode == 2 || mode == 3 || (mode == 1 && pts != nullptr && template_host != nullptr),
+               "mode must be 0 / 2 / 3 (extract: tensor / ndarray / PIL resampler) or 1 (align: needs landmarks and a template)");
   VNFR_REQUIRE(image_size > 0 && margin >= 0 && margin < image_size, "bad image_size / margin");
   if (B == 0 || max_faces == 0) return VNFR_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool tab_set = false;
-  if (!tab_set) {
+  static VnfrPerDevice tab_set_once = {};
+  if (vnfr_first_on_device(tab_set_once)) {
     static unsigned short tab[32 * 32 * 4];
     build_bilinear_table(tab);
     VNFR_CUDA(cudaMemcpyToSymbolAsync(g_bilin, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st));
-    tab_set = true;
   }
   scan_counts_kernel2<<<1, 32, 0, st>>>(count, B, capf, offs);
   ++g_vnfr_launches;

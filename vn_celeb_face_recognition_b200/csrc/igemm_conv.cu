@@ -495,11 +495,10 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
 extern "C" int vnfr_conv_run(const VnfrConvOp* op, void* stream) {
   VNFR_REQUIRE(op != nullptr, "op is null");
   if (op->a_mode == 3) return vnfr_sv_run(op, stream);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static VnfrPerDevice attr_set_once = {};
+  if (vnfr_first_on_device(attr_set_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(igemm_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   ConvParams p;
   p.in = (const __nv_bfloat16*)op->in;

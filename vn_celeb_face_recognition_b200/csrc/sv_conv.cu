@@ -509,15 +509,14 @@ int vnfr_sv_run(const VnfrConvOp* op, void* stream) {
     vnfr_set_error(__FILE__, __LINE__, "op prepared for the shifted-view kernel no longer qualifies");
     return VNFR_ERR_ARG;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static VnfrPerDevice attr_set_once = {};
+  if (vnfr_first_on_device(attr_set_once)) {
     VNFR_CUDA(cudaFuncSetAttribute(sv_conv_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(sv_conv_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(sv_conv_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(sv_conv_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(sv_conv_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     VNFR_CUDA(cudaFuncSetAttribute(sv_conv_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
   }
   ConvParams& p = q.p;
   p.in = (const __nv_bfloat16*)op->in;

@@ -69,6 +69,32 @@ def all_gather_faces_padded(emb, label, prob, cap, group=None, stream=None):
     return out.view(world, cap + 1, D + 2), D
 
 
+def all_gather_payload(payload, group=None, stream=None, out=None):
+    """The step's exchange on the send buffer the fused tail kernel filled (FacePipeline: ``out["payload"]``, (cap + 1, D + 2)
+    fp32 -- rows [0, n) = [embedding | label | prob], n in [cap, 0]): ONE ``all_gather_into_tensor`` straight from that
+    buffer, no packing ops, no host synchronisation.  Returns ((world, cap + 1, D + 2) fp32, D, event) -- the same layout
+    ``all_gather_faces_padded`` produces, so ``compact_faces`` applies.
+    ``stream`` (CUDA): run the exchange on that side stream, ordered after what is enqueued on the current stream so far;
+    the current stream does not wait for it (the collective waits for the slowest rank, the next batch's kernels need
+    not).  ``event`` fires when the exchange has read ``payload``: the producer of the batch that reuses this send buffer
+    (FacePipeline alternates two) must wait for it.  ``out``: preallocated result buffer."""
+    D = payload.shape[1] - 2
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return payload.unsqueeze(0), D, None
+    if out is None:
+        out = torch.empty(world * payload.shape[0], payload.shape[1], dtype=payload.dtype, device=payload.device)
+    if stream is not None and payload.is_cuda:
+        stream.wait_stream(torch.cuda.current_stream(payload.device))
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(out.view(-1, payload.shape[1]), payload, group=group)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return out.view(world, payload.shape[0], payload.shape[1]), D, ev
+    dist.all_gather_into_tensor(out.view(-1, payload.shape[1]), payload, group=group)
+    return out.view(world, payload.shape[0], payload.shape[1]), D, None
+
+
 def compact_faces(payload, D):
     """(payload, D) of all_gather_faces_padded -> (emb, label, prob, counts) exactly as all_gather_faces returns them
     (rank-order concatenation).  Reads the per-rank counts back: this is the one synchronising step."""

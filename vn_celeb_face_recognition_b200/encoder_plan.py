@@ -383,9 +383,12 @@ class EncoderWeights:
         g, b = sd["last_bn.weight"].float(), sd["last_bn.bias"].float()
         m, v = sd["last_bn.running_mean"].float(), sd["last_bn.running_var"].float()
         s = g / torch.sqrt(v + BN_EPS)
-        P["last"] = pack_conv(sd["last_linear.weight"].float().view(512, 1792, 1, 1), s, b - m * s, d)
+        # the tail runs in split precision inside the fused tail kernel (tail.py / csrc/tail_fused.cu)
+        from . import tail
+        self.last = tail.SplitLinear(sd["last_linear.weight"].float().to(d) * s.to(d).view(-1, 1), b - m * s, d)
+        self.logits = None
         if "logits.weight" in sd:
-            P["logits"] = pack_conv(sd["logits.weight"].float()[:, :, None, None], None, sd["logits.bias"].float(), d)
+            self.logits = tail.SplitLinear(sd["logits.weight"].float(), sd["logits.bias"].float(), d)
         self.P = P
 
 
@@ -395,8 +398,8 @@ def _out_hw(h, k, s, p=0):
 
 class EncoderPlan:
     """Op list + activation buffers of one forward for a fixed (batch, H, W).  Input: ``self.x0``, the 16-bit
-    space-to-depth crop tensor (n, ceil(H/2), ceil(W/2), 16) (see pack_stem_s2d); output: ``self.emb_raw`` fp32 (n, 512)
-    = last_bn(last_linear(avgpool)), before L2 normalisation."""
+    space-to-depth crop tensor (n, ceil(H/2), ceil(W/2), 16) (see pack_stem_s2d); output: ``self.x8``, the block8 activations
+    (n, h7, w7, 1792) that the fused tail kernel pools (avgpool_1a -> last_linear -> last_bn -> ..., tail.py)."""
 
     def __init__(self, weights, n, h, w, device):
         P = weights.P
@@ -469,11 +472,10 @@ class EncoderPlan:
             ol.conv(P[p + ".b1a"], View(t8a), View(t8b), pad=(0, 1))
             ol.conv(P[p + ".b1b"], View(t8b), View(cat8, 192, 192), pad=(1, 0))
             ol.conv(P[p + ".out"], View(cat8), View(x8), residual=View(x8), relu=(i is not None))
-        # ---- avgpool -> last_linear + last_bn (fp32 out)
-        pooled = torch.empty(n, 1, 1, 1792, **bf)
-        self.emb_raw = torch.empty(n, 512, dtype=torch.float32, device=device)
-        ol.avgpool(View(x8), pooled)
-        ol.conv(P["last"], View(pooled), None, relu=False, out_f32=self.emb_raw)
+        # ---- avgpool -> last_linear + last_bn -> ...: the fused tail kernel reads x8 (tail.TailPlan, in_mode 0)
+        self.x8 = x8
+        self.weights = weights
+        self.tails = {}
         self.taps = {"conv2d_1a": c1a, "conv2d_2b": c2b, "conv2d_4b_repeat_1": x35, "repeat_2": x17, "block8": x8}
 
     def run(self):

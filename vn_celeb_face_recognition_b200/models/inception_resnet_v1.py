@@ -125,31 +125,85 @@ class InceptionResnetV1(nn.Module):
             self._plans = {}
         return self._packed
 
+    #: cached EncoderPlans (activation buffers + captured graph, ~2.7 MB per crop), least recently used first
+    max_plans = 3
+
     def _plan(self, n, h, w, dev):
         key = (n, h, w)
-        if key not in self._plans:
-            self._plans[key] = encoder_plan.EncoderPlan(self._ensure(dev), n, h, w, dev)
-        return self._plans[key]
+        self._ensure(dev)
+        plan = self._plans.pop(key, None)
+        if plan is None:
+            while len(self._plans) >= self.max_plans:          # evict the least recently used plan (unbounded cache)
+                self._plans.pop(next(iter(self._plans)))
+            plan = encoder_plan.EncoderPlan(self._packed, n, h, w, dev)
+        self._plans[key] = plan                                # most recently used last
+        return plan
 
-    def embed_s2d(self, x_s2d, size):
+    def _bucket(self, m):
+        return min(self.chunk, -(-m // self.plan_bucket) * self.plan_bucket)
+
+    def _tail_plan(self, plan, classifier):
+        """The fused tail of ``plan``: last_linear+last_bn -> L2-normalise [-> classifier's dense_1/ReLU/dense_2/log-softmax]
+        (or -> logits -> log_softmax when ``self.classify``), cached per (plan, classifier weights)."""
+        from .. import tail
+        dev = plan.x8.device
+        if self.classify:
+            key, layers = "logits", [(self._packed.last, "identity"), (self._packed.logits, "logsoftmax")]
+        elif classifier is not None:
+            cl = classifier.split_layers(dev)
+            key, layers = ("mlp", id(cl)), [(self._packed.last, "l2norm")] + cl
+        else:
+            key, layers = "emb", [(self._packed.last, "l2norm")]
+        tp = plan.tails.get(key)
+        if tp is None:
+            if len(plan.tails) > 3:
+                plan.tails.clear()
+            tp = plan.tails[key] = tail.TailPlan(layers, plan.n, dev, in_mode=0)
+            tp.layers_ref = layers
+        return tp
+
+    def embed_s2d(self, x_s2d, size, classifier=None, threshold=0.0, thr_class=None, payload=None, want_half=False, mark=None):
         """Device-resident fast path used by the fused pipeline: x 16-bit space-to-depth crops (n, ceil(S/2), ceil(S/2),
-        16) of S x S faces (vnfr_face_crops half_layout 1) -> (emb fp32 (n,512), emb 16-bit (n,512)), both
-        L2-normalised.  Chunked by ``self.chunk``."""
+        16) of S x S faces (vnfr_face_crops half_layout 1) -> dict(emb fp32 (n,512) L2-normalised[, emb16][, label int64,
+        prob fp32 when ``classifier`` is given]).  One graph replay of the convolutions + ONE fused tail kernel per chunk
+        of ``self.chunk`` crops.  ``payload``: (cap + 1, 514) fp32 all-gather send buffer -- embeddings / labels / probs
+        are then written straight into its rows [0, n) and n into its count cell payload[cap, 0]."""
         n = x_s2d.shape[0]
         h = w = int(size)
         dev = x_s2d.device
-        emb = torch.empty(n, 512, dtype=torch.float32, device=dev)
-        emb16 = torch.empty(n, 512, dtype=x_s2d.dtype, device=dev)
-        for s in range(0, n, self.chunk):
-            m = min(self.chunk, n - s)
-            # plans (activation buffers + captured graph) are cached per batch size: face counts vary from batch to batch,
-            # so round up to a bucket of 64 crops (rows are independent; the padding rows are computed and ignored)
-            plan = self._plan(min(self.chunk, -(-m // self.plan_bucket) * self.plan_bucket), h, w, dev)
-            plan.x0[:m].copy_(x_s2d[s:s + m])
-            plan.run()
-            _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(emb[s:s + m]),
-                      _lib.ptr(emb16[s:s + m]), encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())
-        return emb, emb16
+        out = {}
+        if payload is not None:
+            assert payload.shape[1] == 514 and payload.shape[0] > n
+            emb = payload[:n, :512]
+        else:
+            emb = torch.empty(n, 512, dtype=torch.float32, device=dev)
+        out["emb"] = emb
+        emb16 = torch.empty(n, 512, dtype=x_s2d.dtype, device=dev) if want_half else None
+        out["emb16"] = emb16
+        if classifier is not None:
+            out["label"] = torch.empty(n, dtype=torch.int64, device=dev)
+            out["prob"] = torch.empty(n, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            for s in range(0, n, self.chunk):
+                m = min(self.chunk, n - s)
+                # plans (activation buffers + captured graph) are cached per batch size: face counts vary from batch to batch,
+                # so round up to a bucket of 64 crops (rows are independent; the padding rows are computed and ignored)
+                plan = self._plan(self._bucket(m), h, w, dev)
+                plan.x0[:m].copy_(x_s2d[s:s + m])
+                plan.run()
+                if mark is not None:
+                    mark("encoder")                       # stage marker (bench.py): the convolutions end here
+                tp = self._tail_plan(plan, classifier)
+                last = s + m >= n
+                tp.run(m, x=plan.x8.view(plan.n, -1, plan.x8.shape[-1]),
+                       out_vecs=[emb[s:s + m]] + [None] * (len(tp.layers) - 1),
+                       emb_half=None if emb16 is None else emb16[s:s + m],
+                       label=out["label"][s:s + m] if classifier is not None else None,
+                       prob=out["prob"][s:s + m] if classifier is not None else None,
+                       payload=None if payload is None else payload[s:s + m],
+                       thr=threshold, thr_class=thr_class, n_classes=classifier.num_classes if classifier is not None else 0,
+                       count_cell=payload[-1, :1] if (payload is not None and last) else None, count_value=n)
+        return out
 
     def forward(self, x):
         """inception_resnet_v1.py:272-303 (eval semantics)."""
@@ -162,31 +216,18 @@ class InceptionResnetV1(nn.Module):
         n, c, h, w = x.shape
         assert c == 3, "expected (B,3,H,W)"
         out = torch.empty(n, self.num_classes if self.classify else 512, dtype=torch.float32, device=dev)
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(dev):
             for s in range(0, n, self.chunk):
                 m = min(self.chunk, n - s)
-                plan = self._plan(m, h, w, dev)
+                plan = self._plan(self._bucket(m), h, w, dev)
                 _lib.call("vnfr_nchw3_to_s2d16", _lib.ptr(x[s:s + m]), m, h, w, _lib.ptr(plan.x0),
                           encoder_plan.dtype_code(plan.dtype), _lib.stream_ptr())
                 plan.run()
+                tp = self._tail_plan(plan, None)
+                x8 = plan.x8.view(plan.n, -1, plan.x8.shape[-1])
                 if self.classify:
-                    self._classify(plan, m, out[s:s + m])
+                    # logits + log_softmax (inception_resnet_v1.py:298-300)
+                    tp.run(m, x=x8, out_vecs=[None, out[s:s + m]], n_classes=self.num_classes)
                 else:
-                    _lib.call("vnfr_l2norm_rows", _lib.ptr(plan.emb_raw), m, 512, 512, _lib.ptr(out[s:s + m]), None, 0,
-                              _lib.stream_ptr())
+                    tp.run(m, x=x8, out_vecs=[out[s:s + m]])
         return out
-
-    def _classify(self, plan, m, out):
-        # logits + log_softmax (inception_resnet_v1.py:298-300)
-        pc = self._packed.P["logits"]
-        if not hasattr(plan, "cls"):
-            x16 = torch.empty(m, 1, 1, 512, dtype=plan.dtype, device=out.device)
-            logits = torch.empty(m, pc.cout, dtype=torch.float32, device=out.device)
-            ol = encoder_plan.OpList()
-            ol.conv(pc, encoder_plan.View(x16), None, relu=False, out_f32=logits)
-            plan.cls = (x16, logits, ol)
-        x16, logits, ol = plan.cls
-        x16.view(m, 512).copy_(plan.emb_raw)
-        ol.run()
-        _lib.call("vnfr_logsoftmax_argmax", _lib.ptr(logits), m, self.num_classes, logits.shape[1], _lib.ptr(out), None,
-                  None, _lib.stream_ptr())

@@ -1,17 +1,19 @@
 """Drop-in for the reference's ``models.MLPModel`` (models/mlp_model.py:4-15): Linear(input_dim,2048)+ReLU ->
 (dropout, training only) -> Linear(2048,C) -> log_softmax.  ``state_dict`` keys dense_1.*, dense_2.* as written by the
-reference's trainer checkpoints (trainer/base_trainer.py:83-105; loaded at demo_image.py:16-21).  Forward = two
-tcgen05 GEMMs with fused bias/ReLU epilogues + one log-softmax kernel; no CPU fallback."""
+reference's trainer checkpoints (trainer/base_trainer.py:83-105; loaded at demo_image.py:16-21).  Forward = ONE launch of the
+fused tail kernel (csrc/tail_fused.cu: both contractions on the tensor cores in split precision, bias / ReLU / log-softmax /
+argmax in its row phases); no CPU fallback."""
 import torch
 from torch import nn
 
-from .. import _lib, encoder_plan
+from .. import _lib, tail
 
 
 class MLPModel(nn.Module):
+    #: rows per launch of the fused tail kernel (scratch is allocated per 128-row bucket up to this size)
     chunk = 4096
-    #: 16-bit compute type (torch.float16 default / torch.bfloat16); None = encoder_plan.HALF
-    half_dtype = None
+    #: cached TailPlans (one per row-capacity bucket), least recently used first
+    max_plans = 4
 
     def __init__(self, input_dim, num_classes):
         super().__init__()
@@ -35,31 +37,47 @@ class MLPModel(nn.Module):
         self._invalidate()
         return r
 
-    def _plan(self, n, dev):
-        if self._packed is None:
-            assert self.input_dim % 8 == 0, "input_dim must be a multiple of 8"
-            self._packed = encoder_plan.MlpWeights(self.state_dict(), dev, self.half_dtype)
+    def split_layers(self, dev):
+        """[(SplitLinear dense_1, "relu"), (SplitLinear dense_2, "logsoftmax")] on ``dev`` (packed once per weight set)."""
+        if self._packed is None or self._packed[0] != dev:
+            sd = self.state_dict()
+            self._packed = (dev, [(tail.SplitLinear(sd["dense_1.weight"], sd["dense_1.bias"], dev), "relu"),
+                                  (tail.SplitLinear(sd["dense_2.weight"], sd["dense_2.bias"], dev), "logsoftmax")])
             self._plans = {}
-        if n not in self._plans:
-            self._plans[n] = encoder_plan.MlpPlan(self._packed, n, dev)
-        return self._plans[n]
+        return self._packed[1]
 
-    def classify_half(self, emb16, logp=None):
-        """Device fast path: emb 16-bit (n, input_dim) -> (label int64 (n,), prob fp32 (n,)) [+ log-probs into ``logp``]:
-        argmax / exp(max log-prob) of identify_person (demo_image.py:126-130) fused with the log-softmax."""
-        n = emb16.shape[0]
-        dev = emb16.device
+    def _plan(self, n, dev):
+        layers = self.split_layers(dev)
+        bucket = -(-n // 128) * 128
+        plan = self._plans.pop(bucket, None)
+        if plan is None:
+            plan = tail.TailPlan(layers, bucket, dev, in_mode=1)
+            while len(self._plans) >= self.max_plans:
+                self._plans.pop(next(iter(self._plans)))
+        self._plans[bucket] = plan                      # most recently used last
+        return plan
+
+    def classify(self, emb, logp=None, threshold=0.0, thr_class=None):
+        """Device fast path: emb fp32 (n, input_dim) -> (label int64 (n,), prob fp32 (n,)) [+ log-probs into ``logp``]:
+        argmax / exp(max log-prob) / threshold of identify_person (demo_image.py:113-137) fused with the log-softmax."""
+        n = emb.shape[0]
+        dev = emb.device
+        emb = emb.float()
+        if emb.stride(1) != 1:
+            emb = emb.contiguous()
         label = torch.empty(n, dtype=torch.int64, device=dev)
         prob = torch.empty(n, dtype=torch.float32, device=dev)
-        for s in range(0, n, self.chunk):
-            m = min(self.chunk, n - s)
-            plan = self._plan(m, dev)
-            plan.x.view(m, self.input_dim).copy_(emb16[s:s + m])
-            plan.run()
-            _lib.call("vnfr_logsoftmax_argmax", _lib.ptr(plan.logits), m, self.num_classes, plan.logits.shape[1],
-                      _lib.ptr(None if logp is None else logp[s:s + m]), _lib.ptr(label[s:s + m]), _lib.ptr(prob[s:s + m]),
-                      _lib.stream_ptr())
+        with torch.cuda.device(dev):
+            for s in range(0, n, self.chunk):
+                m = min(self.chunk, n - s)
+                self._plan(m, dev).run(m, x_f32=emb[s:s + m], out_vecs=[None, None if logp is None else logp[s:s + m]],
+                                       label=label[s:s + m], prob=prob[s:s + m], thr=threshold, thr_class=thr_class,
+                                       n_classes=self.num_classes)
         return label, prob
+
+    def classify_half(self, emb16, logp=None):
+        """Kept for callers that hold 16-bit embeddings: same as ``classify`` on their fp32 values."""
+        return self.classify(emb16.float(), logp)
 
     def forward(self, input):
         if not (isinstance(input, torch.Tensor) and input.is_cuda):
@@ -67,7 +85,6 @@ class MLPModel(nn.Module):
         if self.training:
             raise _lib.VnfrError("training-mode forward (dropout p=0.5) is out of scope; call .eval()")
         with torch.no_grad():
-            x16 = input.detach().to(self.half_dtype or encoder_plan.HALF).contiguous()
             logp = torch.empty(input.shape[0], self.num_classes, dtype=torch.float32, device=input.device)
-            self.classify_half(x16, logp)
+            self.classify(input.detach(), logp)
         return logp

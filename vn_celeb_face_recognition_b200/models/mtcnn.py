@@ -285,21 +285,16 @@ class MTCNN(nn.Module):
             w3s = encoder_plan.pack_conv_split2(osd["conv3.weight"], osd["conv3.bias"], dev, 64)
             rsd = self.rnet.state_dict()
             rw2s = encoder_plan.pack_conv_split2(rsd["conv2.weight"], rsd["conv2.bias"], dev, 32)
-            self._packed = {"dev": dev, "pnet_host": pw, "rnet": rw.to(dev), "onet": ow.to(dev), "onet_w2s": w2s.w, "onet_w3s": w3s.w,
-                            "rnet_w2s": rw2s.w}
-            MTCNN._pnet_owner = None
-        if MTCNN._pnet_owner is not self._packed:
-            # P-Net weights live in __constant__ memory (one set per process): re-upload when another instance used it
-            pw = self._packed["pnet_host"]
-            _lib.call("vnfr_pnet_set_weights", C.c_void_p(pw.data_ptr()), pw.numel(), _lib.stream_ptr())
-            torch.cuda.current_stream().synchronize()      # the source is pageable host memory
-            MTCNN._pnet_owner = self._packed
+            self._packed = {"dev": dev, "pnet": _lib.pack_pnet_weights(pw, dev), "rnet": rw.to(dev), "onet": ow.to(dev),
+                            "onet_w2s": w2s.w, "onet_w3s": w3s.w, "rnet_w2s": rw2s.w}
         return self._packed
-
-    _pnet_owner = None
 
     # ---- the device pipeline ------------------------------------------------------------------------------------
     def detect_device(self, frames_u8, select_largest=None, mark=None, slot=0):
+        with torch.cuda.device(frames_u8.device):      # the C library launches on the CURRENT device
+            return self._detect_device(frames_u8, select_largest, mark, slot)
+
+    def _detect_device(self, frames_u8, select_largest=None, mark=None, slot=0):
         """frames_u8: CUDA uint8 (B,H,W,3) RGB.  Runs the whole three-stage cascade on the current stream and returns
         the DetectWorkspace holding out_count (B,), out_box (B,capf,5), out_pts (B,capf,10), status -- all on device,
         nothing synchronised."""
@@ -326,7 +321,7 @@ class MTCNN(nn.Module):
         if ws.L > 0:
             _lib.call("vnfr_pyramid_resize_norm", C.byref(ws.pyr), P(frames_u8), P(ws.levels), st)
             mark("pyramid")
-            _lib.call("vnfr_pnet_sweep_compact", C.byref(ws.pyr), P(ws.levels), t0, cap1, P(ws.cand_count), P(ws.cand_cell),
+            _lib.call("vnfr_pnet_sweep_compact", C.byref(ws.pyr), P(ws.levels), P(wts["pnet"]), t0, cap1, P(ws.cand_count), P(ws.cand_cell),
                       P(ws.cand_score), P(ws.cand_reg), None, None, st)
             mark("pnet")
         _lib.call("vnfr_stage1_boxes", C.byref(ws.pyr), cap1, P(ws.cand_count), P(ws.cand_cell), P(ws.cand_score),
@@ -444,9 +439,10 @@ class MTCNN(nn.Module):
         tmpl = None
         if template is not None:
             tmpl = (C.c_float * 10)(*[float(v) for v in np.asarray(template, dtype=np.float32).reshape(-1)])
-        _lib.call("vnfr_face_crops", _lib.ptr(ws.frames), ws.B, ws.H, ws.W, capf, _lib.ptr(ws.out_count), _lib.ptr(ws.out_box),
-                  _lib.ptr(ws.out_pts), mode, S, margin, tmpl, encoder_plan.dtype_code(dt), max_faces, _lib.ptr(ws.offs),
-                  _lib.ptr(u8 if want_u8 else None), _lib.ptr(half), _lib.ptr(fimg), _lib.ptr(ws.status), 1, _lib.stream_ptr())
+        with torch.cuda.device(dev):
+            _lib.call("vnfr_face_crops", _lib.ptr(ws.frames), ws.B, ws.H, ws.W, capf, _lib.ptr(ws.out_count), _lib.ptr(ws.out_box),
+                      _lib.ptr(ws.out_pts), mode, S, margin, tmpl, encoder_plan.dtype_code(dt), max_faces, _lib.ptr(ws.offs),
+                      _lib.ptr(u8 if want_u8 else None), _lib.ptr(half), _lib.ptr(fimg), _lib.ptr(ws.status), 1, _lib.stream_ptr())
         return (u8 if want_u8 else None), half, fimg, max_faces
 
     # ---- reference API ------------------------------------------------------------------------------------------
@@ -553,10 +549,22 @@ class MTCNN(nn.Module):
             return _np_array(sel_b), _np_array(sel_p), _np_array(sel_pt)
         return sel_b[0], sel_p[0][0], sel_pt[0]
 
+    @staticmethod
+    def _crop_mode(img):
+        """crop_resize (detect_face.py:309-325) picks its resampler by input type: torch.Tensor -> adaptive average +
+        ``.byte()`` (vnfr_face_crops mode 0), numpy.ndarray -> cv2.resize(INTER_AREA) (mode 2), PIL.Image ->
+        Image.resize(BILINEAR) (mode 3)."""
+        items = list(img) if isinstance(img, (list, tuple)) else [img]
+        modes = {0 if isinstance(x, torch.Tensor) else (2 if isinstance(x, np.ndarray) else 3) for x in items}
+        if len(modes) != 1:
+            raise _lib.VnfrError("MTCNN.extract: a batch must hold one image type (Tensor, ndarray or PIL)")
+        return modes.pop()
+
     def extract(self, img, batch_boxes, save_path):
-        """mtcnn.py:458-509.  Crops run on the GPU (vnfr_face_crops mode 0 = the reference's torch.Tensor crop path:
-        area resize + byte truncation) for every input type; faces are returned as float tensors on ``self.device``."""
+        """mtcnn.py:458-509.  Crops run on the GPU with the resampler the reference uses for the input's type (see
+        ``_crop_mode``); like the reference's, the returned faces are float CPU tensors."""
         batch_mode = self._is_batch(img)
+        crop_mode = self._crop_mode(img)
         frames = self._to_frames(img)
         if not batch_mode:
             batch_boxes = [batch_boxes]
@@ -584,9 +592,11 @@ class MTCNN(nn.Module):
             offs = torch.zeros(B + 1, dtype=torch.int32, device=dev)
             status = torch.zeros(1, dtype=torch.int32, device=dev)
             d_cnt, d_box = cnt.to(dev), box.to(dev)        # keep the device copies alive across the launch
-            _lib.call("vnfr_face_crops", _lib.ptr(frames), B, H, W, capf, _lib.ptr(d_cnt), _lib.ptr(d_box), None, 0,
-                      self.image_size, self.margin, None, encoder_plan.dtype_code(encoder_plan.HALF), total, _lib.ptr(offs),
-                      _lib.ptr(u8), _lib.ptr(half), None, _lib.ptr(status), 0, _lib.stream_ptr())
+            with torch.cuda.device(dev):
+                _lib.call("vnfr_face_crops", _lib.ptr(frames), B, H, W, capf, _lib.ptr(d_cnt), _lib.ptr(d_box), None, crop_mode,
+                          self.image_size, self.margin, None, encoder_plan.dtype_code(encoder_plan.HALF), total, _lib.ptr(offs),
+                          _lib.ptr(u8), _lib.ptr(half), None, _lib.ptr(status), 0, _lib.stream_ptr())
+            u8 = u8.cpu()                                                  # the reference crops on the host: CPU tensors out
             faces_f = u8.permute(0, 3, 1, 2).float()                       # F.to_tensor(np.float32(face)), detect_face.py:376
             if self.post_process:
                 faces_f = fixed_image_standardization(faces_f)

@@ -57,9 +57,30 @@ class FacePipeline:
         self.template = center_point if center_point is not None else center_point_dict.get(str(tuple(target_fs)))
         if self.mode == 1 and self.template is None:
             raise ValueError("no landmark template for target size %s" % (target_fs,))
-        self.threshold = threshold
+        self.threshold = threshold          # float, or the reference's per-class dict {str(label): threshold} (demo_image.py:118-124)
         self.max_faces_per_frame = max_faces_per_frame
         self.return_faces_u8 = return_faces_u8
+        self._payloads, self._payload_slot, self._thr_class = {}, 0, None
+
+    def _payload(self, B, dev):
+        """The all-gather send buffer of the next batch: (cap + 1, 514) fp32 -- row f = [embedding (512) | label | prob] of
+        face f, the face count in [cap, 0] (dist.all_gather_payload exchanges it as is).  Two buffers alternate so that the
+        read-back / exchange of batch i can still be in flight while the tail kernel of batch i+1 writes."""
+        cap = max(B * self.max_faces_per_frame, 1)
+        key = (cap, dev)
+        if key not in self._payloads:
+            self._payloads = {key: [torch.zeros(cap + 1, 514, dtype=torch.float32, device=dev) for _ in range(2)]}
+        self._payload_slot = 1 - self._payload_slot
+        return self._payloads[key][self._payload_slot]
+
+    def _thresholds(self, dev):
+        """(scalar threshold, per-class device tensor or None) for the fused tail kernel."""
+        if isinstance(self.threshold, dict):
+            if self._thr_class is None or self._thr_class.device != dev:
+                nc = self.cls.num_classes
+                self._thr_class = torch.tensor([float(self.threshold[str(i)]) for i in range(nc)], dtype=torch.float32, device=dev)
+            return 0.0, self._thr_class
+        return float(self.threshold or 0.0), None
 
     def run_device(self, frames_u8, mark=None, pipelined=False):
         """frames_u8: CUDA uint8 (B,H,W,3).  Returns a dict of DEVICE tensors + the face count (one tiny sync to size
@@ -116,21 +137,25 @@ class FacePipeline:
             F = int(host[:-1].sum())
             out = {"count": ws.out_count, "boxes": ws.out_box, "points": ws.out_pts, "n_faces": F, "faces_u8": None if u8 is None else u8[:F],
                    "face_img": fimg[:F], "count_host": host[:-1].copy(), "ws": ws}
+            dev = ws.out_box.device
+            payload = self._payload(ws.B, dev)
+            out["payload"] = payload
+            if F > payload.shape[0] - 1:
+                raise _lib.VnfrError("more faces than max_faces_per_frame allows")
             if F == 0:
-                dev = ws.out_box.device
-                out.update(emb=torch.zeros(0, 512, device=dev), label=torch.zeros(0, dtype=torch.int64, device=dev),
+                payload[-1, 0] = 0.0
+                out.update(emb=payload[:0, :512], label=torch.zeros(0, dtype=torch.int64, device=dev),
                            prob=torch.zeros(0, device=dev))
                 return out
-            emb, emb16 = self.enc.embed_s2d(half[:F], self.S)
-            mark("encoder")
-            out["emb"] = emb
+            # convolutions (one graph replay) + ONE fused tail kernel: pool -> bottleneck -> L2 norm -> MLP -> log-softmax ->
+            # argmax -> identify_person's threshold (demo_image.py:131-137), rows written straight into the send buffer
+            thr, thr_class = self._thresholds(dev) if self.cls is not None else (0.0, None)
+            res = self.enc.embed_s2d(half[:F], self.S, classifier=self.cls, threshold=thr, thr_class=thr_class, payload=payload,
+                                     mark=mark)
+            mark("tail")
+            out["emb"] = res["emb"]
             if self.cls is not None:
-                label, prob = self.cls.classify_half(emb16)
-                mark("classifier")
-                # identify_person thresholding (demo_image.py:131-137): below threshold -> num_classes ("Unknown")
-                if self.threshold and self.threshold > 0:
-                    label = torch.where(prob >= self.threshold, label, torch.full_like(label, self.cls.num_classes))
-                out["label"], out["prob"] = label, prob
+                out["label"], out["prob"] = res["label"], res["prob"]
         return out
 
     #: device-resident frames: the cascade runs as this many sub-batches alternating between two streams
@@ -236,8 +261,8 @@ class PendingResult:
             fp._stage_owner = [None, None]
             cap = max(B * fp.max_faces_per_frame, 1)
             pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype).pin_memory()
-            fp._stage = [dict(boxes=pin(B, out["boxes"].shape[1], 5, dtype=torch.float32), emb=pin(cap, out["emb"].shape[1], dtype=torch.float32),
-                              label=pin(cap, dtype=torch.int64), prob=pin(cap, dtype=torch.float32)) for _ in range(2)]
+            fp._stage = [dict(boxes=pin(B, out["boxes"].shape[1], 5, dtype=torch.float32),
+                              rows=pin(cap, out["payload"].shape[1], dtype=torch.float32)) for _ in range(2)]
             fp._stage_key, fp._stage_slot = key, 0
         slot = fp._stage_slot
         st = fp._stage[slot]
@@ -253,15 +278,12 @@ class PendingResult:
         # blocks the host until everything enqueued before it (the encoder of this batch) has finished
         st["boxes"].copy_(out["boxes"], non_blocking=True)
         self.boxes = st["boxes"][:, :nmax]
-        if F > st["emb"].shape[0]:
+        if F > st["rows"].shape[0]:
             raise _lib.VnfrError("more faces than max_faces_per_frame allows")
-        self.emb, self.label, self.prob = st["emb"][:F], st["label"][:F], st["prob"][:F]
+        self.rows = st["rows"][:F]
         self.has_cls = "label" in out
         if F:
-            self.emb.copy_(out["emb"], non_blocking=True)
-            if self.has_cls:
-                self.label.copy_(out["label"], non_blocking=True)
-                self.prob.copy_(out["prob"], non_blocking=True)
+            self.rows.copy_(out["payload"][:F], non_blocking=True)        # [embedding | label | prob] rows: one contiguous copy
         self.done = torch.cuda.Event()
         self.done.record(torch.cuda.current_stream(dev))
         self.out = out                                   # keeps the device tensors alive until the copies have run
@@ -272,9 +294,11 @@ class PendingResult:
         self.done.synchronize()
         cnt, F = self.cnt, self.F
         boxes = self.boxes.numpy()
-        lab = self.label.numpy().copy() if self.has_cls else np.zeros(F, np.int64)
-        prob = self.prob.numpy().copy() if self.has_cls else np.zeros(F, np.float32)
-        emb = self.emb.numpy().copy()
+        rows = self.rows.numpy()
+        D = rows.shape[1] - 2
+        lab = rows[:, D].astype(np.int64) if self.has_cls else np.zeros(F, np.int64)
+        prob = rows[:, D + 1].copy() if self.has_cls else np.zeros(F, np.float32)
+        emb = rows[:, :D].copy()
         res, o = [], 0
         for b in range(len(cnt)):
             n = int(cnt[b])
