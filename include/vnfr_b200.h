@@ -199,13 +199,32 @@ typedef struct {
 int vnfr_conv_prepare(VnfrConvOp* op_host);
 int vnfr_conv_run(const VnfrConvOp* op_host, void* stream);
 
+/* ---- encoder: a whole Block17 in one persistent kernel ---------------------------------------------------------------
+ * models/inception_resnet_v1.py:70-95: branch0 / branch1.0 (1x1, one GEMM with N = 256) -> 1x7 -> 7x1 -> 1x1 projection
+ * (+ bias, residual scale folded in) + x -> ReLU, IN PLACE on x: NHWC 16-bit [n_img][8][8][896] (the 8x8 map of a 160x160
+ * crop).  One CTA owns two images from x to the updated x; the branch activations stay in shared memory / TMEM.
+ * Weights in the layout of VnfrConvOp.weights: w1 [256][896] (branch0 rows 0..127, branch1.0 rows 128..255), w2 [128][896]
+ * (k = kx*128 + c), w3 [128][896] (k = ky*128 + c), w4 [896][256]; folded-BN biases b1 [256], b2 [128], b3 [128], b4 [896]. */
+typedef struct {
+  unsigned char tmap[5][128];     /* x (4-D, v-order box), w1, w2, w3, w4: filled by vnfr_block17_prepare              */
+  void* x;
+  const void *w1, *w2, *w3, *w4;
+  const float *b1, *b2, *b3, *b4;
+  int32_t n_img;
+  int32_t dtype;                  /* 0 = bf16, 1 = fp16                                                              */
+} VnfrBlock17Op;
+int vnfr_block17_prepare(VnfrBlock17Op* op_host);
+int vnfr_block17_run(const VnfrBlock17Op* op_host, void* stream);
+
 /* A flat op list = one encoder / classifier forward.  kind 0: convolution (all fields of `conv`); kind 1:
- * MaxPool2d(3,2) and kind 2: AdaptiveAvgPool2d(1) reuse conv.{in, out0, n_img, in_h, in_w, cin, in_pitch, out0_pitch}.
+ * MaxPool2d(3,2) and kind 2: AdaptiveAvgPool2d(1) reuse conv.{in, out0, n_img, in_h, in_w, cin, in_pitch, out0_pitch};
+ * kind 3: fused Block17, `ext` points at a host VnfrBlock17Op (conv is unused).
  * vnfr_run_ops launches them in order on `stream` (one host call per forward instead of one per layer). */
 typedef struct {
   int32_t kind;
   int32_t reserved;
   VnfrConvOp conv;
+  const void* ext;
 } VnfrOp;
 int vnfr_run_ops(const VnfrOp* ops_host, int n_ops, void* stream);
 

@@ -293,3 +293,44 @@ def test_shifted_view_split_precision_conv(dev, mode):
     err32 = (ref32[:4 * 441].double() - ref[:4 * 441]).abs().max().item()
     print("split mode %d: max err %.3e (fp32 conv2d: %.3e)" % (mode, err, err32))
     assert err < 3e-6 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("n", [1, 5, 301])
+def test_fused_block17_matches_unfused_and_torch(dev, n):
+    """csrc/block17_fused.cu (1x1 -> 1x7 -> 7x1 -> projection + residual + ReLU in one persistent kernel, in place) against
+    the four-launch form of the same packed weights and against torch fp32 (inception_resnet_v1.py:70-95).  n = 1 / 5: odd
+    image counts (half-empty last tile); n = 301: 151 tiles on 148 CTAs (persistent loop, barrier phases across tiles)."""
+    from oracle import nets
+    from vn_celeb_face_recognition_b200 import encoder_plan as ep
+    sd = {k: v.to(dev) for k, v in golden_encoder_state_dict().items() if k.startswith("repeat_2.3.")}
+    p = "repeat_2.3"
+    dt = torch.float16
+    P_in = ep.pack_basic(sd, [p + ".branch0", p + ".branch1.0"], dev, block_n=256, dtype=dt)
+    P_a = ep.pack_basic(sd, [p + ".branch1.1"], dev, dtype=dt)
+    P_b = ep.pack_basic(sd, [p + ".branch1.2"], dev, dtype=dt)
+    P_out = ep.pack_projection(sd, p + ".conv2d", 0.10, dev, dtype=dt)
+    g = torch.Generator().manual_seed(n)
+    x0 = torch.relu(torch.randn(n, 8, 8, 896, generator=g)).to(dev).to(dt)
+    # fused, in place
+    xf = x0.clone()
+    ol = ep.OpList()
+    ol.block17(P_in, P_a, P_b, P_out, xf)
+    ol.run()
+    # the four-launch form
+    xu = x0.clone()
+    cat, ta, tb = (torch.empty(n, 8, 8, c, dtype=dt, device=dev) for c in (256, 128, 128))
+    ol2 = ep.OpList()
+    ol2.conv(P_in, ep.View(xu), ep.View(cat, 0, 128), dst1=ep.View(ta), n_split=128)
+    ol2.conv(P_a, ep.View(ta), ep.View(tb), pad=(0, 3))
+    ol2.conv(P_b, ep.View(tb), ep.View(cat, 128, 128), pad=(3, 0))
+    ol2.conv(P_out, ep.View(cat), ep.View(xu), residual=ep.View(xu), relu=True)
+    ol2.run()
+    torch.cuda.synchronize()
+    ref = nets._block17({k: v.float().cpu() for k, v in sd.items()}, p, x0.float().cpu().permute(0, 3, 1, 2), 0.10).permute(0, 2, 3, 1)
+    got, unf = xf.float().cpu(), xu.float().cpu()
+    scale = ref.abs().max().item()
+    e_f, e_u, e_fu = (got - ref).abs().max().item(), (unf - ref).abs().max().item(), (got - unf).abs().max().item()
+    print("n=%d: fused vs torch %.4f, unfused vs torch %.4f, fused vs unfused %.4f (scale %.2f)" % (n, e_f, e_u, e_fu, scale))
+    assert e_f < 0.02 * scale and e_fu < 0.02 * scale
+    rel = (got - ref).norm() / ref.norm()
+    assert rel < 3e-3, rel

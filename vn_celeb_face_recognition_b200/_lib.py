@@ -42,7 +42,16 @@ class ConvOp(C.Structure):
 
 
 class Op(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("conv", ConvOp)]
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("conv", ConvOp), ("ext", C.c_void_p)]
+
+
+class Block17Op(C.Structure):
+    _fields_ = [
+        ("tmap", (C.c_ubyte * 128) * 5), ("x", C.c_void_p),
+        ("w1", C.c_void_p), ("w2", C.c_void_p), ("w3", C.c_void_p), ("w4", C.c_void_p),
+        ("b1", C.c_void_p), ("b2", C.c_void_p), ("b3", C.c_void_p), ("b4", C.c_void_p),
+        ("n_img", C.c_int32), ("dtype", C.c_int32),
+    ]
 
 
 class TailLayer(C.Structure):
@@ -98,6 +107,8 @@ _SIGS = {
     "vnfr_l2norm_rows": [_P, _I, _I, _I, _P, _P, _I, _P],
     "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
     "vnfr_topk_rows": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "vnfr_block17_prepare": [C.POINTER(Block17Op)],
+    "vnfr_block17_run": [C.POINTER(Block17Op), _P],
     "vnfr_tail_prepare": [C.POINTER(TailOp)],
     "vnfr_tail_run": [C.POINTER(TailOp), _I, _P],
 }

@@ -210,6 +210,8 @@ __device__ void pil_bilinear_pixel(const uint8_t* crop, int pitch_px, int cw, in
   for (int c = 0; c < 3; ++c) out[c] = pil_clip8(acc[c]);
 }
 
+// MODE is a template parameter so that the hot modes (0, 1) do not carry the registers of the cv2 / PIL resamplers.
+template <int MODE>
 __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
   const int total_raw = a.offs[a.B];
   if (total_raw > a.max_faces && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.status, 16);
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
   __shared__ int s_box[4];      // integer crop box x1,y1,x2,y2 (exclusive ends)
   __shared__ unsigned short s_tab[32 * 32 * 4];
   __shared__ int s_ad[MAX_S], s_bd[MAX_S], s_x0[MAX_S], s_y0[MAX_S];   // OpenCV's adelta / bdelta / per-row X0, Y0
-  if (a.mode == 1)
+  if (MODE == 1)
     for (int i = threadIdx.x; i < 32 * 32 * 4 / 2; i += blockDim.x)
       reinterpret_cast<uint32_t*>(s_tab)[i] = reinterpret_cast<const uint32_t*>(g_bilin)[i];
   for (int f = blockIdx.x; f < total; f += gridDim.x) {
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
     const float* bx = a.box + ((size_t)b * a.capf + slot) * 5;
     if (threadIdx.x == 0) {
       if (a.face_img != nullptr) a.face_img[f] = b;
-      if (a.mode != 1) {
+      if (MODE != 1) {
         // extract_face: margin in fp32 like numpy float32 scalars (detect_face.py:358-368)
         const float m0 = div_rn(mul_rn((float)a.margin, sub_rn(bx[2], bx[0])), (float)(a.S - a.margin));
         const float m1 = div_rn(mul_rn((float)a.margin, sub_rn(bx[3], bx[1])), (float)(a.S - a.margin));
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
       }
     }
     __syncthreads();
-    if (a.mode == 1) {
+    if (MODE == 1) {
       // per-column / per-row fixed-point terms (AB_BITS = 10), exactly OpenCV's adelta/bdelta and X0/Y0 incl. round_delta
       for (int i = threadIdx.x; i < S; i += blockDim.x) {
         s_ad[i] = (int)llrint(s_m[0] * (double)i * 1024.0);
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
     }
     const int x1 = s_box[0], y1 = s_box[1], cw = s_box[2] - s_box[0], ch = s_box[3] - s_box[1];
     const uint8_t* img = a.frames + (size_t)b * a.H * a.W * 3;
-    if (a.mode == 0) {
+    if (MODE == 0) {
       for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
         const int oy = i / S, ox = i - oy * S;
         unsigned r = 0, g = 0, bl = 0;
@@ -301,13 +303,13 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
         }
         store_px(a, (size_t)f * S * S + i, r, g, bl);
       }
-    } else if (a.mode == 2 || a.mode == 3) {
+    } else if (MODE == 2 || MODE == 3) {
       const uint8_t* crop = img + ((size_t)y1 * a.W + x1) * 3;
       for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
         const int oy = i / S, ox = i - oy * S;
         unsigned c3[3] = {0, 0, 0};
         if (cw > 0 && ch > 0) {
-          if (a.mode == 2) cv_area_pixel(crop, a.W, cw, ch, S, ox, oy, c3);
+          if (MODE == 2) cv_area_pixel(crop, a.W, cw, ch, S, ox, oy, c3);
           else pil_bilinear_pixel(crop, a.W, cw, ch, S, ox, oy, c3);
         }
         store_px(a, (size_t)f * S * S + i, c3[0], c3[1], c3[2]);
@@ -414,7 +416,12 @@ extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int c
   for (int i = 0; i < 10; ++i) a.tmpl[i] = template_host ? template_host[i] : 0.f;
   a.face_u8 = face_u8; a.face_h = (unsigned short*)face_half; a.face_img = face_img; a.status = status;
   int grid = max_faces < 148 * 8 ? max_faces : 148 * 8;
-  face_crop_kernel<<<grid, 256, 0, st>>>(a);
+  switch (mode) {
+    case 0: face_crop_kernel<0><<<grid, 256, 0, st>>>(a); break;
+    case 1: face_crop_kernel<1><<<grid, 256, 0, st>>>(a); break;
+    case 2: face_crop_kernel<2><<<grid, 256, 0, st>>>(a); break;
+    default: face_crop_kernel<3><<<grid, 256, 0, st>>>(a); break;
+  }
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

@@ -560,6 +560,7 @@ extern "C" int vnfr_run_ops(const VnfrOp* ops, int n_ops, void* stream) {
       case 0: rc = vnfr_conv_run(c, stream); break;
       case 1: rc = vnfr_maxpool3s2_nhwc(c->in, c->n_img, c->in_h, c->in_w, c->cin, c->in_pitch, c->out0, c->out0_pitch, c->dtype, stream); break;
       case 2: rc = vnfr_avgpool_nhwc(c->in, c->n_img, c->in_h * c->in_w, c->cin, c->in_pitch, c->out0, c->dtype, stream); break;
+      case 3: rc = vnfr_block17_run(reinterpret_cast<const VnfrBlock17Op*>(ops[i].ext), stream); break;
       default: vnfr_set_error(__FILE__, __LINE__, "unknown op kind"); return VNFR_ERR_ARG;
     }
     if (rc != VNFR_OK) return rc;

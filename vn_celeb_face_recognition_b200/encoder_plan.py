@@ -38,6 +38,9 @@ for _c in os.environ.get("VNFR_SV_OFF_CIN", "").split(","):      # experiments: 
 SV_MIN_USEFUL = float(os.environ.get("VNFR_SV_MIN_USEFUL", "0.7"))
 
 USE_GRAPHS = not os.environ.get("VNFR_NO_GRAPH")
+#: Block17 as one fused kernel per block (csrc/block17_fused.cu) when its map is 8x8 (160x160 crops); VNFR_NO_FUSED_B17=1
+#: keeps the four-launch form (A/B measurements)
+FUSED_B17 = not os.environ.get("VNFR_NO_FUSED_B17")
 
 
 def dtype_code(dt):
@@ -291,6 +294,24 @@ class OpList:
         self.keep += [pc, src, dst0, dst1, residual]
         self._arr = None
 
+    def block17(self, p_in, p_a, p_b, p_out, x):
+        """One fused Block17 (csrc/block17_fused.cu), in place on ``x`` (n, 8, 8, 896): ``p_in`` = branch0 | branch1.0 packed
+        as one N = 256 GEMM, ``p_a`` / ``p_b`` the 1x7 / 7x1 convolutions, ``p_out`` the projection (residual scale folded)."""
+        assert tuple(x.shape[1:]) == (8, 8, 896) and x.is_contiguous()
+        assert tuple(p_in.w.shape) == (256, 896) and tuple(p_a.w.shape) == (128, 896) and tuple(p_b.w.shape) == (128, 896)
+        assert tuple(p_out.w.shape) == (896, 256) and (p_a.kh, p_a.kw, p_b.kh, p_b.kw) == (1, 7, 7, 1)
+        b = _lib.Block17Op()
+        b.x, b.n_img, b.dtype = x.data_ptr(), x.shape[0], dtype_code(x.dtype)
+        b.w1, b.w2, b.w3, b.w4 = p_in.w.data_ptr(), p_a.w.data_ptr(), p_b.w.data_ptr(), p_out.w.data_ptr()
+        b.b1, b.b2, b.b3, b.b4 = p_in.bias.data_ptr(), p_a.bias.data_ptr(), p_b.bias.data_ptr(), p_out.bias.data_ptr()
+        _lib.call("vnfr_block17_prepare", C.byref(b))
+        op = _lib.Op()
+        op.kind = 3
+        op.ext = C.addressof(b)
+        self.ops.append(op)
+        self.keep += [b, p_in, p_a, p_b, p_out, x]
+        self._arr = None
+
     def maxpool(self, src, dst):
         op = _lib.Op()
         op.kind = 1
@@ -448,8 +469,13 @@ class EncoderPlan:
         ol.maxpool(View(x35), View(x17, 640, 256))
         # ---- 10 x Block17 (scale 0.10)
         cat17, t17a, t17b = buf(h6, w6, 256), buf(h6, w6, 128), buf(h6, w6, 128)
+        fused17 = FUSED_B17 and (h6, w6) == (8, 8)
         for i in range(10):
             p = "repeat_2.%d" % i
+            if fused17:
+                # the whole block in one persistent kernel: branch activations never leave shared memory / TMEM
+                ol.block17(P[p + ".in"], P[p + ".b1a"], P[p + ".b1b"], P[p + ".out"], x17)
+                continue
             ol.conv(P[p + ".in"], View(x17), View(cat17, 0, 128), dst1=View(t17a), n_split=128)
             ol.conv(P[p + ".b1a"], View(t17a), View(t17b), pad=(0, 3))
             ol.conv(P[p + ".b1b"], View(t17b), View(cat17, 128, 128), pad=(3, 0))
