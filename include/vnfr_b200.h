@@ -251,6 +251,10 @@ int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* 
 int vnfr_topk_rows(const float* scores, int n, int g, int pitch, int k, int col_offset, int accumulate, float* out_val,
                    int32_t* out_idx, void* stream);
 
+/* cv2.cvtColor(frame, COLOR_BGR2RGB) of demo_video.py:107-110 on the device: swaps bytes 0 and 2 of every packed u8 pixel
+ * (n_pixels a multiple of 4; in == out allowed), so BGR video frames can be uploaded as they are decoded.               */
+int vnfr_swap_rb_u8(const uint8_t* in, uint8_t* out, long long n_pixels, void* stream);
+
 /* ---- fused tail: pool -> bottleneck -> L2-normalise -> MLP -> log-softmax/argmax in ONE cooperative kernel --------------
  * Replaces avgpool_1a + last_linear + last_bn + F.normalize (models/inception_resnet_v1.py:294-302; `logits` +
  * log_softmax :298-300 when classify), MLPModel.forward (models/mlp_model.py:10-15) and the argmax / exp / threshold of

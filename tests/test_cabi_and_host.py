@@ -171,3 +171,49 @@ def test_select_boxes_all_methods_match_reference_golden():
     sb, sp, spt = m.select_boxes(boxes[0], probs[0], points[0], imgs[0], method="probability")
     np.testing.assert_array_equal(np.asarray(sb, np.float32), g["single_box"])
     assert np.float32(sp) == g["single_prob"] and np.asarray(spt).shape == (1, 5, 2)
+
+
+def test_tracker_rows_byte_identical_to_reference_lines():
+    """video.tracker_rows vs the text the reference's own demo_video.py lines 154-181 produce (tests/golden/tracker_rows.npz,
+    oracle/make_golden_tracker.py exec's them): Time, "names", Frame_idx, "boxes / [w,h,w,h]"."""
+    from conftest import load_golden
+    from vn_celeb_face_recognition_b200 import video
+    g = load_golden("tracker_rows")
+    if str(g["numpy_version"]).split(".")[0] != np.__version__.split(".")[0]:
+        pytest.skip("the list repr of numpy scalars differs between numpy major versions")
+    counts, boxes, names = g["counts"].tolist(), g["boxes"], [str(n) for n in g["names"]]
+    per_boxes, per_names, o = [], [], 0
+    for c in counts:
+        per_boxes.append([boxes[o + i] for i in range(c)])
+        per_names.append(names[o:o + c])
+        o += c
+    info = [[float(t), i + 1] for i, t in enumerate(g["times"])]
+    assert video.tracker_rows(info, per_names, per_boxes, tuple(g["frame_shape"].tolist())) == str(g["text"])
+
+
+def test_frame_batcher_follows_demo_video_queue():
+    """demo_video.py:78-101: batches of n_frames, a short last batch at the end of the video, time = count / fps, count
+    from 1; frames land in (pinned when CUDA is present) batch buffers unchanged."""
+    from vn_celeb_face_recognition_b200 import video
+
+    class Cap:
+        def __init__(self, n):
+            self.frames = [np.full((4, 6, 3), i, np.uint8) for i in range(n)]
+            self.i = 0
+
+        def read(self):
+            if self.i >= len(self.frames):
+                return False, None
+            self.i += 1
+            return True, self.frames[self.i - 1]
+
+        def get(self, prop):
+            assert prop == 5
+            return 25.0
+
+    out = [(f.clone(), info) for f, info in video.FrameBatcher(Cap(5), 2)]
+    assert [f.shape[0] for f, _ in out] == [2, 2, 1]
+    assert [i for _, info in out for i in info] == [[(k + 1) / 25.0, k + 1] for k in range(5)]
+    assert [int(f[j, 0, 0, 0]) for f, _ in out for j in range(f.shape[0])] == [0, 1, 2, 3, 4]
+    assert list(video.FrameBatcher(Cap(0), 4)) == []
+    assert [f.shape[0] for f, _ in video.FrameBatcher(Cap(4), 4)] == [4]

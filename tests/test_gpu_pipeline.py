@@ -448,6 +448,13 @@ def test_cal_embedding_matches_reference_golden(dev, models, tmp_path):
     # batch size dividing the file count: the reference crashes on the empty trailing batch, we skip it
     pipeline.cal_embedding(os.path.join(synth.ASSETS, "faces"), 10, models["enc"], tr, str(tmp_path / "b10"), dev)
     assert len(os.listdir(tmp_path / "b10")) == 20
+    # threaded decode / write-behind and 2-way sharding: the same 20 files with the same contents
+    for r in range(2):
+        pipeline.cal_embedding(os.path.join(synth.ASSETS, "faces"), 6, models["enc"], tr, str(tmp_path / "shard"), dev, workers=4,
+                               rank=r, world=2)
+    assert sorted(os.listdir(tmp_path / "shard")) == files
+    e2 = np.stack([np.load(os.path.join(tmp_path / "shard", f))["arr_0"] for f in files])
+    assert (e2 * embs).sum(1).min() > 0.99999            # batch composition differs (6 vs 64): not bit-identical, same vectors
 
 
 def test_host_frame_path_overlapped_copy_equals_device_path(dev, models):
@@ -579,3 +586,45 @@ def test_classify_head_and_per_class_thresholds_match_reference_golden(dev, mode
     exp = np.array([1001 if thr[str(int(l))] > p else int(l) for l, p in zip(labels, probs)])
     np.testing.assert_array_equal(got, exp)
     assert (got == 1001).any() and (got != 1001).any()
+
+
+def test_bgr_frames_and_video_loop(dev, models):
+    """FacePipeline(bgr=True): OpenCV-order frames, channel swap on the device (demo_video.py:107-110) -> exactly the RGB
+    results, for device frames, pinned host batches and pageable arrays; video.run_video reproduces the demo_video loop
+    (batches of n_frames, short last batch, tracker rows) on top of it."""
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import pipeline, video
+    fr = np.concatenate([synth.frames("small", 18, first_seed=0), synth.frames("small", 3, first_seed=40)])      # 21 frames
+    bgr = np.ascontiguousarray(fr[..., ::-1])
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    ref = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity")(fr)
+    fpb = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", bgr=True)
+    d_bgr = torch.from_numpy(bgr).to(dev)
+    keep = d_bgr.clone()
+    for inp in (d_bgr, torch.from_numpy(bgr).pin_memory(), bgr):
+        got = fpb(inp)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a["boxes"], b["boxes"])
+            np.testing.assert_array_equal(a["labels"], b["labels"])
+            np.testing.assert_array_equal(a["emb"], b["emb"])
+    assert torch.equal(d_bgr, keep), "the caller's device frames must not be modified"
+
+    class Cap:
+        def __init__(self, frames):
+            self.frames, self.i = frames, 0
+
+        def read(self):
+            self.i += 1
+            return (True, self.frames[self.i - 1]) if self.i <= len(self.frames) else (False, None)
+
+        def get(self, prop):
+            return 30.0
+
+    names = {i: "id%d" % i for i in range(1001)}
+    text, n_frames, n_faces = video.run_video(Cap(list(bgr)), fpb, names, n_frames=8)
+    lines = text.split("\n")
+    assert lines[0] == "Time,Names,Frame_idx,Bboxes" and n_frames == 21 and n_faces == sum(len(r["labels"]) for r in ref)
+    exp = "".join(video.tracker_rows([[(k + 1) / 30.0, k + 1] for k in range(i, min(i + 8, 21))],
+                                     [[names[int(l)] for l in r["labels"]] for r in ref[i:i + 8]],
+                                     [[b for b in r["boxes"]] for r in ref[i:i + 8]], fr.shape[1:]) for i in range(0, 21, 8))
+    assert "\n".join(lines[1:]) == exp

@@ -249,6 +249,17 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_rows_kernel(const float* __
   }
 }
 
+// BGR <-> RGB on packed u8 pixels (cv2.cvtColor(frame, COLOR_BGR2RGB), demo_video.py:107-110): one thread = 4 pixels = three
+// 32-bit words, bytes shuffled with PRMT; in == out is allowed.
+__global__ void swap_rb_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long n_quads) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_quads; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t w0 = in[3 * i], w1 = in[3 * i + 1], w2 = in[3 * i + 2];
+    out[3 * i] = __byte_perm(w0, w1, 0x5012);
+    out[3 * i + 1] = __byte_perm(__byte_perm(w1, w0, 0x3070), w2, 0x3410);
+    out[3 * i + 2] = __byte_perm(w2, w1, 0x1236);
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -326,6 +337,17 @@ extern "C" int vnfr_topk_rows(const float* scores, int n, int g, int pitch, int 
   VNFR_REQUIRE(k >= 1 && k <= TOPK_MAX && g >= 0 && pitch >= g, "k must be in [1,8] and pitch >= g");
   if (n == 0) return VNFR_OK;
   topk_rows_kernel<<<n, TOPK_THREADS, 0, (cudaStream_t)stream>>>(scores, g, pitch, k, col_offset, accumulate, out_val, out_idx);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_swap_rb_u8(const uint8_t* in, uint8_t* out, long long n_pixels, void* stream) {
+  VNFR_REQUIRE(in != nullptr && out != nullptr, "null pointer");
+  VNFR_REQUIRE(n_pixels % 4 == 0 && ((uintptr_t)in % 4) == 0 && ((uintptr_t)out % 4) == 0, "pixel count must be a multiple of 4 and the buffers 4-byte aligned");
+  if (n_pixels == 0) return VNFR_OK;
+  swap_rb_kernel<<<grid_for(n_pixels / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(in),
+                                                                            reinterpret_cast<uint32_t*>(out), n_pixels / 4);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

@@ -49,7 +49,7 @@ class FacePipeline:
     align="extract":    MTCNN.extract semantics (box crop + area resize + fixed_image_standardization)."""
 
     def __init__(self, detector, encoder, classifier=None, target_fs=(160, 160), align="similarity", center_point=None,
-                 threshold=0.0, max_faces_per_frame=32, return_faces_u8=False):
+                 threshold=0.0, max_faces_per_frame=32, return_faces_u8=False, bgr=False):
         assert target_fs[0] == target_fs[1], "square targets only"
         self.det, self.enc, self.cls = detector, encoder, classifier
         self.S = int(target_fs[0])
@@ -60,7 +60,31 @@ class FacePipeline:
         self.threshold = threshold          # float, or the reference's per-class dict {str(label): threshold} (demo_image.py:118-124)
         self.max_faces_per_frame = max_faces_per_frame
         self.return_faces_u8 = return_faces_u8
+        #: frames arrive in OpenCV's BGR order (cv2.VideoCapture.read): the channel swap of demo_video.py:107-110 runs on the
+        #: device (vnfr_swap_rb_u8) instead of cv2.cvtColor on the host
+        self.bgr = bgr
         self._payloads, self._payload_slot, self._thr_class = {}, 0, None
+        self._rgb_bufs = {}
+
+    def _to_rgb(self, frames_dev, slot_key, in_place):
+        """BGR device frames -> RGB (in place when the buffer is ours, else into a cached buffer per ``slot_key``)."""
+        if not self.bgr:
+            return frames_dev
+        assert frames_dev.is_contiguous()
+        out = frames_dev
+        if not in_place:
+            key = (slot_key, tuple(frames_dev.shape), frames_dev.device)
+            out = self._rgb_bufs.get(key)
+            if out is None:
+                if len(self._rgb_bufs) > 4:
+                    self._rgb_bufs.clear()
+                out = self._rgb_bufs[key] = torch.empty_like(frames_dev)
+        n_px = frames_dev.numel() // 3
+        if n_px % 4:
+            raise _lib.VnfrError("bgr=True needs a pixel count that is a multiple of 4")
+        with torch.cuda.device(frames_dev.device):
+            _lib.call("vnfr_swap_rb_u8", _lib.ptr(frames_dev), _lib.ptr(out), n_px, _lib.stream_ptr())
+        return out
 
     def _payload(self, B, dev):
         """The all-gather send buffer of the next batch: (cap + 1, 514) fp32 -- row f = [embedding (512) | label | prob] of
@@ -97,6 +121,9 @@ class FacePipeline:
         mark = mark or (lambda name: None)
         with torch.no_grad():
             B = frames_u8.shape[0]
+            if self.bgr:
+                self._rgb_slot = 1 - getattr(self, "_rgb_slot", 0)
+                frames_u8 = self._to_rgb(frames_u8.contiguous(), self._rgb_slot, in_place=False)
             for attempt in range(6):
                 if marked or B < 32:
                     ws = self.det.detect_device(frames_u8, mark=mark)
@@ -203,6 +230,8 @@ class FacePipeline:
         with torch.cuda.stream(cs):
             for b0, b1 in bounds:
                 buf[b0:b1].copy_(t[b0:b1], non_blocking=True)
+                if self.bgr:
+                    self._to_rgb(buf[b0:b1], None, in_place=True)      # on the copy stream, right behind the sub-batch's H2D
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 events.append(ev)
@@ -398,30 +427,59 @@ def create_batch_images(list_files, batch_size):
     return batches, n_batchs
 
 
-def create_image_tensors(data_dir_path, list_files, transforms):
-    """find_embedding.py:23-32."""
+def create_image_tensors(data_dir_path, list_files, transforms, pool=None):
+    """find_embedding.py:23-32; ``pool`` (a concurrent.futures executor) decodes + transforms the files in parallel
+    (PIL / zlib release the GIL), results stay in file order."""
     from PIL import Image
-    return torch.stack([transforms(Image.open(str(Path(data_dir_path) / f))) for f in list_files], 0)
+    load = lambda f: transforms(Image.open(str(Path(data_dir_path) / f)))
+    items = list(pool.map(load, list_files)) if pool is not None else [load(f) for f in list_files]
+    return torch.stack(items, 0)
 
 
-def save_embeddings(embeddings, list_files, output_dir):
+def save_embeddings(embeddings, list_files, output_dir, pool=None):
     """find_embedding.py:34-42: one ``<stem>.npz`` per image, key ``arr_0``, (512,) fp32 -- the wire format
-    VNCelebEmbDataset reads (data_loader/vn_celeb_emb_dataset.py:14)."""
-    for i in range(embeddings.shape[0]):
+    VNCelebEmbDataset reads (data_loader/vn_celeb_emb_dataset.py:14).  ``pool``: write the files from worker threads."""
+    def save(i):
         np.savez_compressed(str(Path(output_dir) / "{}.npz".format(list_files[i].split(".")[0])), embeddings[i])
+    if pool is not None:
+        return [pool.submit(save, i) for i in range(embeddings.shape[0])]
+    for i in range(embeddings.shape[0]):
+        save(i)
+    return []
 
 
-def cal_embedding(data_dir, batch_size, model, transforms, output_dir, device):
+def cal_embedding(data_dir, batch_size, model, transforms, output_dir, device, workers=0, rank=0, world=1):
     """find_embedding.py:45-59.  Unlike the reference an EMPTY trailing batch is skipped instead of crashing in
-    torch.stack (the reference raises when len(files) % batch_size == 0)."""
+    torch.stack (the reference raises when len(files) % batch_size == 0).
+
+    Extensions for the offline-embedding configs, same files / same ``.npz`` bytes-on-disk format:
+    ``workers`` > 0 decodes batch i+1 and writes batch i-1 on a thread pool while the GPU embeds batch i; ``rank`` /
+    ``world`` shard the sorted file list into contiguous blocks (dist.shard_range), each rank writing its own files."""
+    from concurrent.futures import ThreadPoolExecutor
+    from . import dist as vdist
     os.makedirs(output_dir, exist_ok=True)
     model.eval()
     list_files = sorted(os.listdir(data_dir))
+    if world > 1:
+        lo, hi = vdist.shard_range(len(list_files), rank, world)
+        list_files = list_files[lo:hi]
     batches, n_batchs = create_batch_images(list_files, batch_size)
-    for batch_file in batches:
-        if not batch_file:
-            continue
-        tensors = create_image_tensors(Path(data_dir), batch_file, transforms).to(device)
-        with torch.no_grad():
-            embeddings = model(tensors).detach().cpu().numpy()
-        save_embeddings(embeddings, batch_file, output_dir)
+    batches = [b for b in batches if b]
+    pool = ThreadPoolExecutor(max_workers=workers) if workers and workers > 0 else None
+    try:
+        nxt = pool.submit(create_image_tensors, Path(data_dir), batches[0], transforms, pool) if (pool and batches) else None
+        writes = []
+        for k, batch_file in enumerate(batches):
+            if pool is not None:
+                tensors = nxt.result()
+                nxt = pool.submit(create_image_tensors, Path(data_dir), batches[k + 1], transforms, None) if k + 1 < len(batches) else None
+            else:
+                tensors = create_image_tensors(Path(data_dir), batch_file, transforms)
+            with torch.no_grad():
+                embeddings = model(tensors.to(device)).detach().cpu().numpy()
+            writes += save_embeddings(embeddings, batch_file, output_dir, pool)
+        for w in writes:
+            w.result()
+    finally:
+        if pool is not None:
+            pool.shutdown(wait=True)
