@@ -628,3 +628,32 @@ def test_bgr_frames_and_video_loop(dev, models):
                                      [[names[int(l)] for l in r["labels"]] for r in ref[i:i + 8]],
                                      [[b for b in r["boxes"]] for r in ref[i:i + 8]], fr.shape[1:]) for i in range(0, 21, 8))
     assert "\n".join(lines[1:]) == exp
+
+
+def test_capacity_overflow_is_reported_not_truncated(dev, models):
+    """A frame with far more face-like patches than the per-stage capacities (4096-entry shared-memory NMS): the
+    status word must turn into a VnfrError that names the stage and the ceiling -- never a silently truncated result; and
+    raising a cap within the ceiling makes a moderately crowded frame pass with the reference's answer."""
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import _lib
+    import cv2
+    faces = [f for _, f in synth.bundled_faces()]
+    k, pitch = 22, 24
+    canvas = np.full((1080, 1920, 3), 100, np.uint8)
+    tile = [cv2.resize(f, (k, k), interpolation=cv2.INTER_AREA) for f in faces]
+    i = 0
+    for y in range(2, 1080 - k, pitch):
+        for x in range(2, 1920 - k, pitch):
+            canvas[y:y + k, x:x + k] = tile[i % len(tile)]
+            i += 1
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=20, device=dev)
+    det.caps = (64, 4096, 2048, 256)                       # a tiny first-stage capacity: must be reported
+    with pytest.raises(_lib.VnfrError, match="cap1.*CAPS_CEILING"):
+        det.detect(canvas[None])
+    det2 = models["MTCNN"](image_size=160, keep_all=True, min_face_size=20, device=dev)
+    det2.caps = (4096, 4096, 4096, 4096)                   # everything at the ceiling: ~3 500 tiny faces either fit or are reported
+    try:
+        boxes, probs = det2.detect(canvas[None])
+        assert len(boxes[0]) > 100
+    except _lib.VnfrError as e:
+        assert "capacity exceeded" in str(e)

@@ -1,8 +1,12 @@
 // Block-level building blocks shared by every NMS stage of the detector: a bitonic key/value sort in shared memory and
 // a greedy NMS over the sorted boxes that walks the list in chunks of 64 with 64-bit suppression masks in shared
 // memory.  Visit order and arithmetic follow torchvision.ops.nms (mode 0; detect_face.py:79, :93, :128) and the
-// reference's nms_numpy(..., "Min") (mode 1; detect_face.py:221-257) exactly, so that with identical scores the keep
-// list is bit-identical:
+// reference's nms_numpy(..., "Min") (mode 1; detect_face.py:221-257) exactly, so that with identical scores and boxes the
+// keep list is bit-identical.  One documented difference: torchvision.ops.batched_nms / batched_nms_numpy (detect_face.py:
+// 259-274) separate the images of a batch by ADDING idx*(max_coord+1) to every box in fp32 before the IoU arithmetic, which
+// rounds the fractional stage-2/3 coordinates of images idx > 0 to the ulp of ~1e5 (2^-7); here every image is its own
+// segment and its boxes are used un-offset (= what the reference computes for image 0 / un-batched calls).  A decision
+// sitting within 2^-7 px of the 0.7 IoU / "Min" threshold can therefore differ for the non-first images of a batch.
 //   mode 0: area (x2-x1)*(y2-y1), inter = max(0,dx)*max(0,dy), suppress iff inter/(a_i + a_j - inter) > thr
 //   mode 1: area (x2-x1+1)*(y2-y1+1), inter with +1, suppress iff inter/min(a_i, a_j) > thr
 #pragma once

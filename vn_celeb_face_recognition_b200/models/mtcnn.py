@@ -211,8 +211,13 @@ class MTCNN(nn.Module):
     """MTCNN face detection module -- see the module docstring; keyword arguments as in mtcnn.py:200-204."""
 
     #: per-stage capacities (candidates per (image, level) / boxes per image into R-Net / into O-Net / faces per image).
-    #: Exceeding one raises (results would otherwise be truncated); raise the cap and call again.
+    #: Exceeding one raises VnfrError (results would otherwise be silently truncated; the reference has no such limit).
+    #: The first three are bounded by CAPS_CEILING: every NMS runs inside ONE CTA with sort keys, boxes and keep list in
+    #: shared memory (36 B per entry: 4 096 entries = 144 KB of the SM's 227 KB).  Measured headroom: the crowded 4K /
+    #: min_face_size 20 config peaks at 979 R-Net boxes per frame and ~1.3 k P-Net candidates per (image, level).  A frame
+    #: beyond the ceiling (tens of thousands of face-like patches) must be tiled by the caller.
     caps = (4096, 4096, 2048, 256)
+    CAPS_CEILING = (4096, 4096, 4096, None)
     #: average R-Net / O-Net candidates per frame the crop workspaces are sized for (6.9 KB / 27.6 KB per crop)
     crop_ws_per_frame = (2048, 256)
     #: minimum size (crops) of the two workspaces whatever the batch
@@ -415,7 +420,9 @@ class MTCNN(nn.Module):
                      "cap3 (boxes per image into O-Net)", "capf (faces per image)", "max_faces",
                      "crop workspace (MTCNN.crop_ws_per_frame)"]
             over = [n for i, n in enumerate(names) if status & (1 << i)]
-            raise _lib.VnfrError("detection capacity exceeded: %s -- raise MTCNN.caps" % ", ".join(over))
+            raise _lib.VnfrError("detection capacity exceeded: %s.  MTCNN.caps = %s can be raised up to MTCNN.CAPS_CEILING = %s (the "
+                                 "per-CTA shared-memory NMS holds 4096 boxes; capf / max_faces_per_frame have no ceiling); a frame "
+                                 "beyond that must be split into tiles by the caller" % (", ".join(over), MTCNN.caps, MTCNN.CAPS_CEILING))
 
     def face_crops_device(self, ws, mode, image_size, margin=0, template=None, half_dtype=None, max_faces=None,
                           want_u8=True):
