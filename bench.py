@@ -23,6 +23,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "faces/sec detect+embed+classify (1080p)"
 UNIT = "faces/s"
+
+#: BASELINE.json configs measured by this file.  Per-frame algorithmic work of the detection kernels: SURVEY.md 8(d) / Appendix C.
+WORKLOADS = {
+    3: dict(workload="pipeline_1080p (BASELINE config 3)", kind="1080p", frames=64, min_face=50, max_faces=32, cpu_frames=8, ref_frames=64,
+            frame="1920x1080x3 u8", pnet_gflop=0.818, pyramid_mb=9.11, metric=METRIC),
+    4: dict(workload="pipeline_4k_crowded (BASELINE config 4)", kind="4k", frames=8, min_face=20, max_faces=96, cpu_frames=1, ref_frames=2,
+            frame="3840x2160x3 u8", pnet_gflop=21.67, pyramid_mb=97.0,
+            metric="faces/sec detect+embed+classify (crowded 3840x2160, min_face_size 20)"),
+}
 ENC_FLOP_PER_FACE = 2.8353e9          # 1 417.66 MMAC per 160x160 crop (conv + last_linear)
 MLP_FLOP_PER_FACE = 6.2e6
 
@@ -265,23 +274,24 @@ def run_reference(args):
     from vn_celeb_face_recognition_b200 import synthetic
     enc_sd = synthetic.encoder_state_dict_seed0()            # the same seeded weights as our arm (build_models)
     mlp_sd = synthetic.mlp_state_dict(1001, seed=0)
-    n = args.ref_frames
-    frames = make_frames(n, 0)
+    wl = WORKLOADS[args.config]
+    n = args.ref_frames or wl["ref_frames"]              # config 4: a bounded sample (a 4K / min_face 20 frame costs seconds on the CPU)
+    frames = make_frames(n, 0, wl["kind"])
     times, faces = [], 0
     for i in range(args.warmup + args.steps):
-        fps, nf, dt, threads, kind = cpu_reference_leg(frames, enc_sd, mlp_sd)
+        fps, nf, dt, threads, kind = cpu_reference_leg(frames, enc_sd, mlp_sd, min_face_size=wl["min_face"])
         if i >= args.warmup:
             times.append(dt)
             faces += nf
     total = sum(times)
     val = faces / total
-    sample = "%d synthetic 1080p frames (seeds 0..%d, 12 faces each) per step, %d timed steps" % (n, n - 1, args.steps)
+    sample = "%d synthetic %s frames (seeds 0..%d) per step (our arm: %d per rank), %d timed steps" % (n, wl["kind"], n - 1, wl["frames"], args.steps)
     eps, edt = cpu_embed_leg(enc_sd, mlp_sd, threads=threads)
-    line = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+    line = {"metric": wl["metric"], "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "pipeline_1080p (BASELINE config 3)", "frames_per_rank": n, "frames_per_step": n,
-                       "faces_per_step": faces // max(1, args.steps), "min_face_size": 50, "align": "similarity 160x160",
+            "config": {"workload": wl["workload"], "frames_per_rank": n, "frames_per_step": n,
+                       "faces_per_step": faces // max(1, args.steps), "min_face_size": wl["min_face"], "align": "similarity 160x160",
                        "num_classes": 1001},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
                              "embeds_per_s": eps, "embeds_sample": "InceptionResnetV1 + MLP on 64 crops, best of 2, %.2f s" % edt},
@@ -305,11 +315,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    B = args.frames
-    det, enc, cls = build_models(dev)
+    wl = WORKLOADS[args.config]
+    B = args.frames or wl["frames"]
+    det, enc, cls = build_models(dev, min_face_size=wl["min_face"])
     enc.chunk = args.chunk
-    fp = pipeline.FacePipeline(det, enc, cls, (160, 160), "similarity")
-    frames_np = make_frames(B, rank * B)
+    fp = pipeline.FacePipeline(det, enc, cls, (160, 160), "similarity", max_faces_per_frame=wl["max_faces"])
+    frames_np = make_frames(B, rank * B, wl["kind"])
     frames_pinned = torch.from_numpy(frames_np).pin_memory()
     frames_dev = frames_pinned.to(dev)
 
@@ -426,7 +437,7 @@ def run_ours(args):
     # ---- second headline figure of BASELINE.json ("embeds/sec"): InceptionResnetV1 + L2-norm + MLP classify on
     # batch-1024 synthetic 160x160 crops (config 2) through the public forward() API, crops resident on the device
     embed = None
-    if not args.skip_e2e:
+    if not args.skip_e2e and args.config == 3:
         torch.manual_seed(1)
         crops = torch.randn(args.embed_batch, 3, 160, 160, device=dev).clamp_(-1, 1)
         for _ in range(3):
@@ -445,7 +456,9 @@ def run_ours(args):
 
     # ---- config 5 figure: cosine top-5 of a batch of embeddings against this rank's gallery shard (+ NCCL merge)
     topk = None
-    if not args.skip_e2e and args.gallery_rows > 0:
+    if args.config == 3 and args.gallery_rows == 0:
+        args.gallery_rows = 131072
+    if not args.skip_e2e and args.gallery_rows > 0 and args.config == 3:
         from vn_celeb_face_recognition_b200 import gallery
         gen = torch.Generator(device=dev).manual_seed(2 + rank)
         gshard = gallery.GalleryShard(torch.nn.functional.normalize(torch.randn(args.gallery_rows, 512, device=dev, generator=gen), dim=1),
@@ -504,19 +517,38 @@ def run_ours(args):
                                                                       tj["dram_bytes_per_launch"] / 1e6,
                                                                       "" if tj["faces"] == faces_step_rank else
                                                                       ", scaled to this step's %d faces" % faces_step_rank, tj["source"]))
-            roof = {"kernel": "tcgen05 convolutions (sv_conv_kernel + igemm_conv_kernel): all 105 conv launches of the "
-                              "InceptionResnetV1 stage of one step", "bound": "tensor",
+            roof = {"kernel": "tcgen05 convolutions (sv_conv_kernel + igemm_conv_kernel + block17_fused_kernel): all conv launches of "
+                              "the InceptionResnetV1 stage of one step", "bound": "tensor",
                     "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                     "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": peaks["source"] + ", sustained (kernel timed inside a long step)",
                     "stage_ms": enc_ms, "share_of_step": enc_ms / sum(stage_ms.values()),
                     "note": "stage times come from instrumented single-stream passes; the timed loop overlaps the two "
                             "detection half-batches on two streams, so ms_per_step < sum(stage_ms)"}
-        line = {"metric": METRIC, "value": faces / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        # the detection kernels against their own roofs (config 4's step is dominated by them)
+        det_roofs = []
+        if stage_ms.get("pnet", 0) > 0:
+            a = B * wl["pnet_gflop"] / stage_ms["pnet"]               # GFLOP / ms = TFLOP/s
+            det_roofs.append({"kernel": "pnet_kernel (fp32 FMA conv1/conv2 + split-precision tcgen05 conv3, all pyramid levels)",
+                              "bound": "tensor", "achieved": a, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                              "frac": a / peaks["bf16_sustained"], "stage_ms": stage_ms["pnet"],
+                              "note": "%.2f GFLOP of fp32-accurate work per frame; conv3 (57 %%) costs 3 fp16 products per fp32 product, "
+                                      "conv1/conv2 run on the FMA pipe" % wl["pnet_gflop"]})
+        if stage_ms.get("pyramid", 0) > 0:
+            a = B * wl["pyramid_mb"] / stage_ms["pyramid"]            # MB / ms = GB/s
+            det_roofs.append({"kernel": "pyramid_strip_kernel (all levels, one read of the frame)", "bound": "hbm", "achieved": a,
+                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": a / peaks["hbm_gbs"], "stage_ms": stage_ms["pyramid"],
+                              "note": "%.2f MB per frame (frame read once + levels written)" % wl["pyramid_mb"]})
+        if roof is not None and det_roofs:
+            dom = max([roof] + det_roofs, key=lambda r: r["stage_ms"])
+            if dom is not roof:                                       # the JSON's `roofline` is the step's dominant kernel
+                det_roofs = [r for r in det_roofs if r is not dom] + [roof]
+                roof = dict(dom, traffic=None, peak_source=peaks["source"], share_of_step=dom["stage_ms"] / sum(stage_ms.values()))
+        line = {"metric": wl["metric"], "value": faces / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": _half_name(enc.half_dtype), "data": "synthetic",
-                "config": {"workload": "pipeline_1080p (BASELINE config 3)", "frames_per_rank": B, "frame": "1920x1080x3 u8",
-                           "faces_per_step": faces // max(1, args.steps), "min_face_size": 50, "align": "similarity 160x160",
+                "config": {"workload": wl["workload"], "frames_per_rank": B, "frame": wl["frame"],
+                           "faces_per_step": faces // max(1, args.steps), "min_face_size": wl["min_face"], "align": "similarity 160x160",
                            "encoder": "InceptionResnetV1 random-init", "classifier": "MLPModel(512,1001) random-init",
                            "detector_weights": "bundled MTCNN", "detector_dtype": "f32", "encoder_chunk": enc.chunk,
                            "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (frames_np.nbytes / 1e6),
@@ -526,15 +558,16 @@ def run_ours(args):
                         "api": "FacePipeline.__call__ (one batch at a time)" if args.no_pipeline else
                                "FacePipeline.submit / PendingResult.result, two batches in flight"},
                 "gpu_launches": int(launches), "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-                "roofline": roof, "clocks": clocks, "embed": embed, "gallery_topk": topk}
+                "roofline": roof, "roofline_other": det_roofs, "clocks": clocks, "embed": embed, "gallery_topk": topk}
         if world == 1 and not args.no_cpu_baseline:
             enc_sd = {k: v.detach().float().cpu() for k, v in enc.state_dict().items()}
             mlp_sd = {k: v.detach().float().cpu() for k, v in cls.state_dict().items()}
-            n = args.cpu_frames
-            fps, nf, dt, threads, kind, outputs = cpu_reference_leg(frames_np[:n], enc_sd, mlp_sd, repeats=2, want_outputs=True)
+            n = args.cpu_frames or wl["cpu_frames"]
+            fps, nf, dt, threads, kind, outputs = cpu_reference_leg(frames_np[:n], enc_sd, mlp_sd, repeats=2 if args.config == 3 else 1,
+                                                                    min_face_size=wl["min_face"], want_outputs=True)
             eps, edt = cpu_embed_leg(enc_sd, mlp_sd, threads=threads)
             line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": kind,
-                                    "sample": "first %d of the step's 1080p frames (%d faces), best of 2, %.2f s" % (n, nf, dt),
+                                    "sample": "first %d of the step's frames (%d faces), %.2f s" % (n, nf, dt),
                                     "embeds_per_s": eps, "embeds_sample": "InceptionResnetV1 + MLP on 64 crops, best of 2, %.2f s" % edt}
             # parity of the measured step itself: the e2e results of the same frames against the CPU reference path
             line["parity"] = label_parity(res, outputs)
@@ -556,19 +589,28 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="1080p frames per rank per step (BASELINE config 3: 64)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 3 = 1080p pipeline (default, the headline), 4 = crowded 4K / min_face_size 20, "
+                         "2 = embed + classify on 160x160 crops (embeds/s), 5 = offline embedding + sharded cosine top-5")
+    ap.add_argument("--frames", type=int, default=0, help="frames per rank per step (default: the config's: 64 x 1080p / 8 x 4K)")
     ap.add_argument("--chunk", type=int, default=1024, help="encoder crops per internal chunk")
-    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded CPU sample of our arm's cpu_baseline / parity block")
-    ap.add_argument("--ref-frames", type=int, default=64, help="--impl reference: frames per step (default: our arm's 64 per rank)")
-    ap.add_argument("--gallery-rows", type=int, default=131072, help="gallery rows per rank of the cosine top-5 figure (config 5); 0 = skip")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the bounded CPU sample of our arm's cpu_baseline / parity block (default 8 / 1)")
+    ap.add_argument("--ref-frames", type=int, default=0, help="--impl reference: frames per step (default: our arm's frames per rank)")
+    ap.add_argument("--gallery-rows", type=int, default=0, help="gallery rows per rank (config 5: default 125 000; config 3's extra "
+                    "gallery_topk figure: default 131 072, -1 = skip)")
     ap.add_argument("--gallery-queries", type=int, default=8192)
+    ap.add_argument("--crops-per-rank", type=int, default=122880, help="config 5: crops embedded per rank per step (1 M / 8 GPUs = 125 000; "
+                    "rounded down to whole chunks of 4096)")
     ap.add_argument("--embed-batch", type=int, default=1024, help="crops per rank of the embeds/s measurement (config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time: no overlap between consecutive steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.config in (2, 5):
+        import bench_embed
+        (bench_embed.run_reference if args.impl == "reference" else bench_embed.run_ours)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -237,6 +237,9 @@ int vnfr_avgpool_nhwc(const void* in, int n_img, int hw, int c, int in_pitch, vo
 int vnfr_nchw3_to_nhwc8(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream);
 /* Same input -> the space-to-depth layout [n][ceil(h/2)][ceil(w/2)][16] (see vnfr_face_crops half_layout 1). */
 int vnfr_nchw3_to_s2d16(const float* in, int n_img, int h, int w, void* out, int dtype, void* stream);
+/* transforms_default on the device (data_loader/__init__.py:27-34, 52-56: np.float32 -> (x-127.5)/128 -> CHW) fused with the
+ * layout change: u8 HWC faces [n][h][w][3] -> the space-to-depth encoder input (see vnfr_face_crops half_layout 1).        */
+int vnfr_u8hwc_to_s2d16(const uint8_t* in, int n_img, int h, int w, void* out, int dtype, void* stream);
 /* F.normalize(p=2, dim=1) (inception_resnet_v1.py:302): x fp32 [n][d] -> emb fp32 [n][d] and bf16 copy (nullable). */
 int vnfr_l2norm_rows(const float* x, int n, int d, int x_pitch, float* emb, void* emb_half, int dtype, void* stream);
 /* F.log_softmax(dim=1) + argmax + exp(max log-prob) (mlp_model.py:14; demo_image.py:126-130).
@@ -250,6 +253,14 @@ int vnfr_logsoftmax_argmax(const float* logits, int n, int c, int pitch, float* 
  * cosine top-k against a gallery shard (BASELINE.json config 5; the reference itself has no gallery search). */
 int vnfr_topk_rows(const float* scores, int n, int g, int pitch, int k, int col_offset, int accumulate, float* out_val,
                    int32_t* out_idx, void* stream);
+
+/* Cosine top-8 against a gallery shard with the top-k fused into the score GEMM: q 16-bit [m][512], gallery 16-bit
+ * [g_pad][512] (g_pad a multiple of 256, rows >= g_valid ignored) -> out_val / out_idx [splits][m][8], best first, ties
+ * towards the lower row, idx = index_offset + gallery row (-1 = no entry).  The m x g score matrix is never written: scores
+ * go from TMEM straight into per-row running top-8 lists.  `splits` (1..g_pad/256) divides the gallery among CTAs when there
+ * are fewer than ~148 query tiles; the caller merges the `splits` lists per query.                                       */
+int vnfr_gallery_topk(const void* q, int m, const void* gallery, int g_valid, int g_pad, int dtype, int splits, int index_offset,
+                      float* out_val, int32_t* out_idx, void* stream);
 
 /* cv2.cvtColor(frame, COLOR_BGR2RGB) of demo_video.py:107-110 on the device: swaps bytes 0 and 2 of every packed u8 pixel
  * (n_pixels a multiple of 4; in == out allowed), so BGR video frames can be uploaded as they are decoded.               */

@@ -225,7 +225,8 @@ def test_encoder_and_mlp_match_oracle_and_golden(dev, dt, min_cos, margin_thr):
 
 
 def test_gallery_topk_matches_torch(dev):
-    """Cosine top-5 against a gallery shard (config 5): tcgen05 score GEMM + running row-wise top-k over gallery tiles vs
+    """Cosine top-5 against a gallery shard (config 5): the fused score-GEMM + top-k kernel (scores never leave TMEM; 12 gallery
+    tiles split over CTAs and merged, then a single-split run over 40 query tiles... see the loop below) vs
     torch.topk(E @ G^T) in fp32.  Operands are 16-bit, so near-ties may swap: every returned row must be (re-scored in
     fp32) within 2e-3 of the true k-th best, values must match the fp32 scores of the returned rows, and well-separated
     matches (planted duplicates) must be found exactly with global indices."""
@@ -235,8 +236,9 @@ def test_gallery_topk_matches_torch(dev):
     Q = torch.nn.functional.normalize(torch.randn(70, 512, generator=g), dim=1)
     Q[:10] = torch.nn.functional.normalize(G[100:110] + 0.05 * torch.randn(10, 512, generator=g), dim=1)   # planted matches
     shard = gallery.GalleryShard(G.to(dev), index_offset=5000)
-    shard.tile = 1024                                              # 3 gallery tiles -> exercises the accumulate path
-    vals, idx = shard.topk(Q.to(dev), k=5)
+    vals, idx = shard.topk(Q.to(dev), k=5)                         # 1 query tile -> 12 gallery splits, merged
+    v1, i1 = shard.topk(Q.to(dev), k=5, sms=1)                     # the same without splitting: one CTA walks all 12 tiles
+    assert torch.equal(idx, i1) and torch.equal(vals, v1)
     torch.cuda.synchronize()
     ref = Q @ G.t()
     rv, ri = torch.topk(ref, 5, dim=1)
@@ -253,6 +255,21 @@ def test_gallery_topk_matches_torch(dev):
     small = gallery.GalleryShard(G[:3].to(dev))
     v2, i2 = small.topk(Q[:4].to(dev), k=5)
     assert (i2[:, 3:] == -1).all() and torch.isinf(v2[:, 3:]).all() and (i2[:, :3] >= 0).all()
+    # many query tiles (persistent CTAs walk several items), ragged last tile, exact ties -> lower index
+    g2 = torch.Generator(device="cpu").manual_seed(1)
+    Gb = torch.nn.functional.normalize(torch.randn(700, 512, generator=g2), dim=1)
+    Gb[650] = Gb[13]                                               # duplicate rows: identical scores
+    Qb = torch.nn.functional.normalize(torch.randn(20000, 512, generator=g2), dim=1)
+    Qb[5] = Gb[13]
+    big = gallery.GalleryShard(Gb.to(dev))
+    vb, ib = big.topk(Qb.to(dev), k=5)
+    torch.cuda.synchronize()
+    refb = Qb.half().float() @ Gb.half().float().t()
+    rvb, rib = torch.topk(refb, 5, dim=1)
+    assert ib[5, 0].item() == 13 and ib[5, 1].item() == 650
+    resc = torch.gather(refb, 1, ib.cpu())
+    assert (vb.cpu() - resc).abs().max() < 1e-3 and (resc >= rvb[:, 4:5] - 1e-3).all()
+    assert (ib.cpu() == rib).float().mean() > 0.995
 
 
 @pytest.mark.parametrize("mode", [1, 2])

@@ -104,10 +104,12 @@ _SIGS = {
     "vnfr_avgpool_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "vnfr_nchw3_to_nhwc8": [_P, _I, _I, _I, _P, _I, _P],
     "vnfr_nchw3_to_s2d16": [_P, _I, _I, _I, _P, _I, _P],
+    "vnfr_u8hwc_to_s2d16": [_P, _I, _I, _I, _P, _I, _P],
     "vnfr_l2norm_rows": [_P, _I, _I, _I, _P, _P, _I, _P],
     "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
     "vnfr_topk_rows": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "vnfr_swap_rb_u8": [_P, _P, _LL, _P],
+    "vnfr_gallery_topk": [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "vnfr_block17_prepare": [C.POINTER(Block17Op)],
     "vnfr_block17_run": [C.POINTER(Block17Op), _P],
     "vnfr_tail_prepare": [C.POINTER(TailOp)],

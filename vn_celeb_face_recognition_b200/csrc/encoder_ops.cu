@@ -127,6 +127,34 @@ __global__ void nchw3_to_s2d16_kernel(const float* __restrict__ in, int n_img, i
   }
 }
 
+// u8 HWC faces (what the reference's glue hands to transforms_default, data_loader/__init__.py:27-34, 52-56) -> the
+// standardised 16-bit space-to-depth encoder input [n][ceil(h/2)][ceil(w/2)][16]: (x - 127.5) / 128, one thread per 2x2 cell.
+template <bool F16>
+__global__ void u8hwc_to_s2d16_kernel(const uint8_t* __restrict__ in, int n_img, int h, int w, __nv_bfloat16* __restrict__ out) {
+  const int h2 = (h + 1) >> 1, w2 = (w + 1) >> 1;
+  const long long total = (long long)n_img * h2 * w2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / (h2 * w2);
+    const int rem = (int)(i - img * (h2 * w2));
+    const int cy = rem / w2, cx = rem - cy * w2;
+    uint32_t wds[8];
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      const int y = 2 * cy + (sub >> 1), x = 2 * cx + (sub & 1);
+      float r = 0.f, g = 0.f, bl = 0.f;
+      if (y < h && x < w) {
+        const uint8_t* b = in + ((img * h + y) * (long long)w + x) * 3;
+        r = ((float)__ldg(b) - 127.5f) * 0.0078125f; g = ((float)__ldg(b + 1) - 127.5f) * 0.0078125f; bl = ((float)__ldg(b + 2) - 127.5f) * 0.0078125f;
+      }
+      wds[2 * sub] = pack_h2<F16>(r, g);
+      wds[2 * sub + 1] = pack_h2<F16>(bl, 0.f);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    o[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -348,6 +376,16 @@ extern "C" int vnfr_swap_rb_u8(const uint8_t* in, uint8_t* out, long long n_pixe
   if (n_pixels == 0) return VNFR_OK;
   swap_rb_kernel<<<grid_for(n_pixels / 4, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(in),
                                                                             reinterpret_cast<uint32_t*>(out), n_pixels / 4);
+  ++g_vnfr_launches;
+  VNFR_CHECK_LAUNCH();
+  return VNFR_OK;
+}
+
+extern "C" int vnfr_u8hwc_to_s2d16(const uint8_t* in, int n_img, int h, int w, void* out, int dtype, void* stream) {
+  VNFR_REQUIRE(in != nullptr && out != nullptr, "null pointer");
+  if (n_img == 0) return VNFR_OK;
+  auto kern = dtype == 1 ? u8hwc_to_s2d16_kernel<true> : u8hwc_to_s2d16_kernel<false>;
+  kern<<<grid_for((long long)n_img * ((h + 1) / 2) * ((w + 1) / 2), 256), 256, 0, (cudaStream_t)stream>>>(in, n_img, h, w, (__nv_bfloat16*)out);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();
   return VNFR_OK;

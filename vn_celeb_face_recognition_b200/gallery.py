@@ -1,9 +1,9 @@
 """Cosine top-k of L2-normalised embeddings against a gallery shard (BASELINE.json config 5 / north star: "optional cosine
 top-k against a sharded gallery"; the reference itself has no gallery search -- SURVEY.md section 8d).
 
-Each rank holds a contiguous block of gallery rows as 16-bit [rows][512] "weights" of the tcgen05 GEMM kernel
-(csrc/igemm_conv.cu): scores = Q . G^T come out tile by tile in fp32, ``vnfr_topk_rows`` keeps a running top-k per query,
-and ``merge_topk`` combines the per-rank lists (one all_gather of k values + k global indices per query).
+Each rank holds a contiguous block of gallery rows as 16-bit [rows][512]; ``GalleryShard.topk`` is one launch of the fused
+score-GEMM + top-k kernel (csrc/gallery_topk.cu: the score matrix never leaves TMEM), and ``merge_topk`` combines the
+per-rank lists (one all_gather of k values + k global indices per query).
 """
 import torch
 import torch.distributed as dist
@@ -12,67 +12,46 @@ from . import _lib, encoder_plan
 
 
 class GalleryShard:
-    """``emb``: (g, d) float tensor of unit vectors on a CUDA device; ``index_offset``: global row index of row 0."""
-
-    #: gallery rows scored per GEMM launch (score buffer = queries x tile fp32)
-    tile = 32768
-    #: queries per pass
-    q_chunk = 1024
+    """``emb``: (g, 512) float tensor of unit vectors on a CUDA device; ``index_offset``: global row index of row 0."""
 
     def __init__(self, emb, index_offset=0, dtype=None):
         if not emb.is_cuda:
             raise _lib.VnfrError("GalleryShard needs CUDA tensors: this package has no CPU path")
         self.dtype = dtype or encoder_plan.HALF
         self.g, self.d = emb.shape
-        assert self.d % 64 == 0, "embedding size must be a multiple of 64"
+        assert self.d == 512, "embedding size must be 512 (InceptionResnetV1)"
         self.index_offset = int(index_offset)
         dev = emb.device
         g_pad = -(-max(self.g, 1) // 256) * 256
         self.w = torch.zeros(g_pad, self.d, dtype=self.dtype, device=dev)
         self.w[:self.g] = emb.to(self.dtype)
-        self.bias = torch.zeros(g_pad, dtype=torch.float32, device=dev)
-        self._plans = {}
 
-    def _plan(self, n, t0, t1):
-        key = (n, t0, t1)
-        if key not in self._plans:
-            dev = self.w.device
-            rows = t1 - t0                                          # multiple of 256 (padded rows score 0 and are masked)
-            pc = encoder_plan.PackedConv(self.w[t0:t1], self.bias[t0:t1], 1, 1, self.d, rows, 256)
-            x = torch.zeros(n, 1, 1, self.d, dtype=self.dtype, device=dev)
-            scores = torch.empty(n, rows, dtype=torch.float32, device=dev)
-            ol = encoder_plan.OpList()
-            ol.conv(pc, encoder_plan.View(x), None, relu=False, out_f32=scores)
-            self._plans[key] = (x, scores, ol)
-        return self._plans[key]
-
-    def topk(self, q, k=5):
-        """q: (n, d) unit vectors (any float dtype, CUDA).  Returns (values fp32 (n,k), global indices int64 (n,k)) of the
-        k most similar rows of THIS shard, best first; indices of missing entries (g < k) are -1."""
+    def topk(self, q, k=5, sms=148):
+        """q: (n, 512) unit vectors (any float dtype, CUDA).  Returns (values fp32 (n,k), global indices int64 (n,k)) of the
+        k most similar rows of THIS shard, best first; indices of missing entries (g < k) are -1.  ONE launch of the fused
+        score-GEMM + top-k kernel (csrc/gallery_topk.cu); with few queries the gallery is split across CTAs and the per-split
+        lists are merged here."""
         assert 1 <= k <= 8
         n = q.shape[0]
         dev = q.device
-        vals = torch.full((n, k), float("-inf"), dtype=torch.float32, device=dev)
-        idx = torch.full((n, k), 0x7fffffff, dtype=torch.int32, device=dev)
         q16 = q.to(self.dtype).contiguous()
-        for s in range(0, n, self.q_chunk):
-            m = min(self.q_chunk, n - s)
-            v_s, i_s = vals[s:s + m], idx[s:s + m]
-            first = True
-            for t0 in range(0, self.w.shape[0], self.tile):
-                t1 = min(self.w.shape[0], t0 + self.tile)
-                valid = min(self.g, t1) - t0
-                if valid <= 0:
-                    break
-                x, scores, ol = self._plan(m, t0, t1)
-                x.view(m, self.d).copy_(q16[s:s + m])
-                ol.run()
-                _lib.call("vnfr_topk_rows", _lib.ptr(scores), m, valid, scores.shape[1], k, self.index_offset + t0,
-                          0 if first else 1, _lib.ptr(v_s), _lib.ptr(i_s), _lib.stream_ptr())
-                first = False
-        idx64 = idx.to(torch.int64)
-        idx64[idx == 0x7fffffff] = -1
-        return vals, idx64
+        g_tiles = self.w.shape[0] // 256
+        m_tiles = -(-max(n, 1) // 128)
+        splits = max(1, min(g_tiles, -(-sms // m_tiles))) if m_tiles < sms else 1
+        vals = torch.empty(splits, n, 8, dtype=torch.float32, device=dev)
+        idx = torch.empty(splits, n, 8, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("vnfr_gallery_topk", _lib.ptr(q16), n, _lib.ptr(self.w), self.g, self.w.shape[0],
+                      encoder_plan.dtype_code(self.dtype), splits, self.index_offset, _lib.ptr(vals), _lib.ptr(idx), _lib.stream_ptr())
+        v = vals.permute(1, 0, 2).reshape(n, splits * 8)
+        i = idx.permute(1, 0, 2).reshape(n, splits * 8).to(torch.int64)
+        if splits > 1:
+            key = torch.where(i < 0, torch.full_like(i, 1 << 62), i)
+            order = torch.argsort(key, dim=1, stable=True)                # (value desc, index asc): index first, then value
+            v, i = torch.gather(v, 1, order), torch.gather(i, 1, order)
+            order = torch.argsort(v, dim=1, descending=True, stable=True)
+            v, i = torch.gather(v, 1, order), torch.gather(i, 1, order)
+        return v[:, :k].contiguous(), i[:, :k].contiguous()
 
 
 def merge_topk(vals, idx, k=None, group=None):

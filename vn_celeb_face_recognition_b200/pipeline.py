@@ -185,6 +185,26 @@ class FacePipeline:
                 out["label"], out["prob"] = res["label"], res["prob"]
         return out
 
+    def embed_faces(self, faces_u8, payload=None, mark=None):
+        """Aligned faces (n, S, S, 3) uint8 -- what parallel_detect_and_align returns, on the host (pinned for an asynchronous
+        copy) or on the device -- -> transforms_default + InceptionResnetV1 + MLP + identify_person's threshold on the device
+        (recognize_celeb, demo_image.py:50-76, without its host transforms).  Returns the embed_s2d dict (emb, label, prob)
+        of device tensors; with ``payload`` the rows go straight into that send buffer."""
+        t = torch.as_tensor(faces_u8)
+        dev = t.device if t.is_cuda else (self.det._cuda_device() if self.det is not None else torch.device(self.enc.device))
+        if not t.is_cuda:
+            t = t.to(dev, non_blocking=True)
+        n, S = t.shape[0], t.shape[1]
+        dt = self.enc.half_dtype or encoder_plan.HALF
+        key = (n, S, dt, t.device)
+        if getattr(self, "_s2d_key", None) != key:
+            self._s2d = torch.zeros(n, (S + 1) // 2, (S + 1) // 2, 16, dtype=dt, device=t.device)
+            self._s2d_key = key
+        with torch.no_grad(), torch.cuda.device(t.device):
+            _lib.call("vnfr_u8hwc_to_s2d16", _lib.ptr(t.contiguous()), n, S, S, _lib.ptr(self._s2d), encoder_plan.dtype_code(dt), _lib.stream_ptr())
+            thr, thr_class = self._thresholds(t.device) if self.cls is not None else (0.0, None)
+            return self.enc.embed_s2d(self._s2d, S, classifier=self.cls, threshold=thr, thr_class=thr_class, payload=payload, mark=mark)
+
     #: device-resident frames: the cascade runs as this many sub-batches alternating between two streams
     device_chunks = int(os.environ.get("VNFR_DEVICE_CHUNKS", "2"))
     #: frames per sub-batch of the host-frame path (H2D of sub-batch i+1 overlaps the cascade of sub-batch i).  Measured for
