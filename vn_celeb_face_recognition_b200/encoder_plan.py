@@ -41,6 +41,8 @@ USE_GRAPHS = not os.environ.get("VNFR_NO_GRAPH")
 #: Block17 as one fused kernel per block (csrc/block17_fused.cu) when its map is 8x8 (160x160 crops); VNFR_NO_FUSED_B17=1
 #: keeps the four-launch form (A/B measurements)
 FUSED_B17 = not os.environ.get("VNFR_NO_FUSED_B17")
+#: Block35's two parallel 3x3 convolutions as one block-diagonal launch (VNFR_NO_GROUPED_B35=1: two launches)
+GROUPED_B35 = not os.environ.get("VNFR_NO_GROUPED_B35")
 
 
 def dtype_code(dt):
@@ -187,6 +189,27 @@ def pack_stem_s2d(sd, prefix, device, dtype=None):
                     if ky < 3 and kx < 3:
                         w2[:, (sy * 2 + sx) * 4:(sy * 2 + sx) * 4 + 3, ty, tx] = w[:, :, ky, kx]
     return pack_conv(w2, None, b, device, cin_pad=16, dtype=dtype)
+
+
+def pack_basic_grouped(sd, prefixes, device, dtype=None):
+    """Sibling BasicConv2d with the SAME kernel size but DIFFERENT inputs (each reads its own channel slice of one tensor, in
+    order) as ONE block-diagonal convolution: cout = sum of couts, cin = sum of cins, zero weights off the diagonal.  Block35's
+    branch1.1 and branch2.1 (3x3, 32 -> 32 each, inception_resnet_v1.py:44-51) become one 64 -> 64 launch: the tensor pipe
+    does twice the (tiny) work, but a launch of this size is latency-bound, so one launch costs about what each of the two did."""
+    ws, bs = [], []
+    for p in prefixes:
+        w, s, b = fold_bn(sd, p)
+        ws.append(w * s.view(-1, 1, 1, 1))
+        bs.append(b)
+    cout, cin = sum(w.shape[0] for w in ws), sum(w.shape[1] for w in ws)
+    kh, kw = ws[0].shape[2:]
+    big = torch.zeros(cout, cin, kh, kw, dtype=torch.float32, device=ws[0].device)
+    o = i = 0
+    for w in ws:
+        big[o:o + w.shape[0], i:i + w.shape[1]] = w
+        o += w.shape[0]
+        i += w.shape[1]
+    return pack_conv(big, None, torch.cat(bs, 0), device, None, None, dtype)
 
 
 def pack_projection(sd, p, scale, device, block_n=None, dtype=None):
@@ -377,6 +400,7 @@ class EncoderWeights:
             P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0", p + ".branch2.0"], d)      # N = 96
             P[p + ".b1"] = pack_basic(sd, [p + ".branch1.1"], d)
             P[p + ".b2a"] = pack_basic(sd, [p + ".branch2.1"], d)
+            P[p + ".b12"] = pack_basic_grouped(sd, [p + ".branch1.1", p + ".branch2.1"], d, dtype=self.dtype)
             P[p + ".b2b"] = pack_basic(sd, [p + ".branch2.2"], d)
             P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.17, d)
         P["m6a.b0"] = pack_basic(sd, ["mixed_6a.branch0"], d)
@@ -454,8 +478,12 @@ class EncoderPlan:
         for i in range(5):
             p = "repeat_1.%d" % i
             ol.conv(P[p + ".in"], View(x35), View(cat, 0, 32), dst1=View(t1), n_split=32)
-            ol.conv(P[p + ".b1"], View(t1, 0, 32), View(cat, 32, 32), pad=(1, 1))
-            ol.conv(P[p + ".b2a"], View(t1, 32, 32), View(t2), pad=(1, 1))
+            if GROUPED_B35:
+                # branch1.1 and branch2.1 as one block-diagonal 64 -> 64 convolution writing both destinations
+                ol.conv(P[p + ".b12"], View(t1), View(cat, 32, 32), dst1=View(t2), n_split=32, pad=(1, 1))
+            else:
+                ol.conv(P[p + ".b1"], View(t1, 0, 32), View(cat, 32, 32), pad=(1, 1))
+                ol.conv(P[p + ".b2a"], View(t1, 32, 32), View(t2), pad=(1, 1))
             ol.conv(P[p + ".b2b"], View(t2), View(cat, 64, 32), pad=(1, 1))
             ol.conv(P[p + ".out"], View(cat), View(x35), residual=View(x35), relu=True)
         # ---- Mixed_6a
