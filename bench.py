@@ -321,8 +321,25 @@ def run_ours(args):
     enc.chunk = args.chunk
     fp = pipeline.FacePipeline(det, enc, cls, (160, 160), "similarity", max_faces_per_frame=wl["max_faces"])
     frames_np = make_frames(B, rank * B, wl["kind"])
-    frames_pinned = torch.from_numpy(frames_np).pin_memory()
-    frames_dev = frames_pinned.to(dev)
+    fp_host = fp
+    if args.ingest == "nv12":
+        # host frames as a video decoder delivers them (NV12, 1.5 B/px): every leg -- device-resident, e2e, CPU baseline -- sees the
+        # SAME pixels, cv2's decode of those NV12 frames; only the e2e path uploads NV12 and converts on the device
+        import cv2
+        Hh, Ww = frames_np.shape[1:3]
+        nv12 = np.empty((B, Hh * 3 // 2, Ww), np.uint8)
+        for i in range(B):
+            i420 = cv2.cvtColor(frames_np[i], cv2.COLOR_RGB2YUV_I420)
+            nv12[i, :Hh] = i420[:Hh]
+            nv12[i, Hh:] = np.stack([i420[Hh:Hh + Hh // 4].reshape(Hh // 2, Ww // 2), i420[Hh + Hh // 4:].reshape(Hh // 2, Ww // 2)],
+                                    axis=-1).reshape(Hh // 2, Ww)
+            frames_np[i] = cv2.cvtColor(nv12[i], cv2.COLOR_YUV2RGB_NV12)
+        fp_host = pipeline.FacePipeline(det, enc, cls, (160, 160), "similarity", max_faces_per_frame=wl["max_faces"], input_format="nv12")
+        frames_pinned = torch.from_numpy(nv12).pin_memory()
+        frames_dev = torch.from_numpy(frames_np).to(dev)
+    else:
+        frames_pinned = torch.from_numpy(frames_np).pin_memory()
+        frames_dev = frames_pinned.to(dev)
 
     stage_ms = {}
     ev_log = []
@@ -405,14 +422,14 @@ def run_ours(args):
     # ---- end to end through the public API: pinned host frames in, host results out (`e2e`)
     e2e_steps = 1 if args.skip_e2e else args.steps
     for _ in range(0 if args.skip_e2e else 3):
-        fp(frames_pinned)
+        fp_host(frames_pinned)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     faces_e2e, d2h = 0, 0
     e0.record()
     if args.no_pipeline:
         for _ in range(e2e_steps):
-            res = fp(frames_pinned)
+            res = fp_host(frames_pinned)
             faces_e2e += sum(len(r["labels"]) for r in res)
     else:
         # the streaming form of the public call: two batches in flight -- batch i+1 is submitted (its H2D copy and cascade
@@ -420,7 +437,7 @@ def run_ours(args):
         # frames are copied from pinned host memory and every step's results are read back inside the timed region.
         pending = None
         for _ in range(e2e_steps):
-            nxt = fp.submit(frames_pinned)
+            nxt = fp_host.submit(frames_pinned)
             if pending is not None:
                 res = pending.result()
                 faces_e2e += sum(len(r["labels"]) for r in res)
@@ -553,7 +570,7 @@ def run_ours(args):
                            "detector_weights": "bundled MTCNN", "detector_dtype": "f32", "encoder_chunk": enc.chunk,
                            "l2_policy": "inputs larger than L2 (%.0f MB of frames per step)" % (frames_np.nbytes / 1e6),
                            "batches_in_flight": 1 if args.no_pipeline else 2, "work_per_frame": work, "collective": "all_gather(emb,label,prob)" if world > 1 else "none"},
-                "e2e": {"value": faces_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_np.nbytes),
+                "e2e": {"value": faces_e2e / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_pinned.numel()), "ingest": args.ingest,
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps,
                         "api": "FacePipeline.__call__ (one batch at a time)" if args.no_pipeline else
                                "FacePipeline.submit / PendingResult.result, two batches in flight"},
@@ -602,6 +619,8 @@ def main():
     ap.add_argument("--crops-per-rank", type=int, default=122880, help="config 5: crops embedded per rank per step (1 M / 8 GPUs = 125 000; "
                     "rounded down to whole chunks of 4096)")
     ap.add_argument("--embed-batch", type=int, default=1024, help="crops per rank of the embeds/s measurement (config 2)")
+    ap.add_argument("--ingest", default="rgb", choices=["rgb", "nv12"], help="host frame format of the e2e leg: packed RGB (what the "
+                    "reference's cap.read + cvtColor hands over) or NV12 as a video decoder delivers it (half the H2D bytes, converted on the device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time: no overlap between consecutive steps")

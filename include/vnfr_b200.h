@@ -266,6 +266,11 @@ int vnfr_gallery_topk(const void* q, int m, const void* gallery, int g_valid, in
  * (n_pixels a multiple of 4; in == out allowed), so BGR video frames can be uploaded as they are decoded.               */
 int vnfr_swap_rb_u8(const uint8_t* in, uint8_t* out, long long n_pixels, void* stream);
 
+/* NV12 video frames [n][h*3/2][w] u8 (luma plane, then interleaved U,V at half resolution) -> packed RGB [n][h][w][3], BT.601
+ * limited range, bit-identical to cv2.cvtColor(COLOR_YUV2RGB_NV12): the decode-side colour conversion of the ingest path
+ * (demo_video.py:78-110) on the device, at half the host -> device bytes of RGB frames.                                     */
+int vnfr_nv12_to_rgb_u8(const uint8_t* in, uint8_t* out, int n_img, int h, int w, void* stream);
+
 /* ---- fused tail: pool -> bottleneck -> L2-normalise -> MLP -> log-softmax/argmax in ONE cooperative kernel --------------
  * Replaces avgpool_1a + last_linear + last_bn + F.normalize (models/inception_resnet_v1.py:294-302; `logits` +
  * log_softmax :298-300 when classify), MLPModel.forward (models/mlp_model.py:10-15) and the argmax / exp / threshold of

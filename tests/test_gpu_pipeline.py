@@ -657,3 +657,35 @@ def test_capacity_overflow_is_reported_not_truncated(dev, models):
         assert len(boxes[0]) > 100
     except _lib.VnfrError as e:
         assert "capacity exceeded" in str(e)
+
+
+def test_nv12_ingest_bit_identical_to_cv2(dev, models):
+    """FacePipeline(input_format="nv12"): NV12 frames (what a video decoder delivers, 1.5 bytes per pixel) are converted on the
+    device exactly as cv2.cvtColor(COLOR_YUV2RGB_NV12) does; results equal the RGB pipeline fed with cv2's conversion, for
+    device frames and for pinned host batches (sub-batched copy + conversion on the copy stream)."""
+    import cv2
+    from oracle import synth
+    from vn_celeb_face_recognition_b200 import _lib, pipeline
+    fr = synth.frames("small", 20, first_seed=0)
+    B, H, W, _ = fr.shape
+    assert H % 2 == 0 and W % 2 == 0
+    nv12 = np.empty((B, H * 3 // 2, W), np.uint8)
+    for i in range(B):
+        i420 = cv2.cvtColor(fr[i], cv2.COLOR_RGB2YUV_I420)                       # planar Y | U | V
+        nv12[i, :H] = i420[:H]
+        u, v = i420[H:H + H // 4].reshape(H // 2, W // 2), i420[H + H // 4:].reshape(H // 2, W // 2)
+        nv12[i, H:] = np.stack([u, v], axis=-1).reshape(H // 2, W)
+    rgb_cv = np.stack([cv2.cvtColor(nv12[i], cv2.COLOR_YUV2RGB_NV12) for i in range(B)])
+    d_in, d_out = torch.from_numpy(nv12).to(dev), torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev)
+    _lib.call("vnfr_nv12_to_rgb_u8", _lib.ptr(d_in), _lib.ptr(d_out), B, H, W, _lib.stream_ptr())
+    np.testing.assert_array_equal(d_out.cpu().numpy(), rgb_cv)
+    det = models["MTCNN"](image_size=160, keep_all=True, min_face_size=50, device=dev)
+    ref = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity")(rgb_cv)
+    fpn = pipeline.FacePipeline(det, models["enc"], models["mlp"], (160, 160), "similarity", input_format="nv12")
+    assert sum(len(r["labels"]) for r in ref) > 20
+    for inp in (d_in, torch.from_numpy(nv12).pin_memory()):
+        got = fpn(inp)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a["boxes"], b["boxes"])
+            np.testing.assert_array_equal(a["labels"], b["labels"])
+            np.testing.assert_array_equal(a["emb"], b["emb"])

@@ -109,6 +109,7 @@ _SIGS = {
     "vnfr_logsoftmax_argmax": [_P, _I, _I, _I, _P, _P, _P, _P],
     "vnfr_topk_rows": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "vnfr_swap_rb_u8": [_P, _P, _LL, _P],
+    "vnfr_nv12_to_rgb_u8": [_P, _P, _I, _I, _I, _P],
     "vnfr_gallery_topk": [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "vnfr_block17_prepare": [C.POINTER(Block17Op)],
     "vnfr_block17_run": [C.POINTER(Block17Op), _P],

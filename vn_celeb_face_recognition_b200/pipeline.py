@@ -49,7 +49,7 @@ class FacePipeline:
     align="extract":    MTCNN.extract semantics (box crop + area resize + fixed_image_standardization)."""
 
     def __init__(self, detector, encoder, classifier=None, target_fs=(160, 160), align="similarity", center_point=None,
-                 threshold=0.0, max_faces_per_frame=32, return_faces_u8=False, bgr=False):
+                 threshold=0.0, max_faces_per_frame=32, return_faces_u8=False, bgr=False, input_format="rgb"):
         assert target_fs[0] == target_fs[1], "square targets only"
         self.det, self.enc, self.cls = detector, encoder, classifier
         self.S = int(target_fs[0])
@@ -63,8 +63,21 @@ class FacePipeline:
         #: frames arrive in OpenCV's BGR order (cv2.VideoCapture.read): the channel swap of demo_video.py:107-110 runs on the
         #: device (vnfr_swap_rb_u8) instead of cv2.cvtColor on the host
         self.bgr = bgr
+        #: "rgb": frames (B,H,W,3) u8;  "nv12": frames (B, H*3/2, W) u8 as a video decoder delivers them (luma plane + interleaved
+        #: half-resolution U,V) -- converted on the device with cv2's BT.601 fixed point (vnfr_nv12_to_rgb_u8): half the
+        #: host -> device bytes of RGB frames
+        assert input_format in ("rgb", "nv12") and not (bgr and input_format == "nv12")
+        self.input_format = input_format
         self._payloads, self._payload_slot, self._thr_class = {}, 0, None
         self._rgb_bufs = {}
+
+    def _nv12_to_rgb(self, raw, out):
+        """raw (n, H*3/2, W) u8 device NV12 -> out (n, H, W, 3) u8 RGB on the current stream."""
+        n, h32, W = raw.shape
+        H = h32 * 2 // 3
+        with torch.cuda.device(raw.device):
+            _lib.call("vnfr_nv12_to_rgb_u8", _lib.ptr(raw), _lib.ptr(out), n, H, W, _lib.stream_ptr())
+        return out
 
     def _to_rgb(self, frames_dev, slot_key, in_place):
         """BGR device frames -> RGB (in place when the buffer is ours, else into a cached buffer per ``slot_key``)."""
@@ -121,6 +134,15 @@ class FacePipeline:
         mark = mark or (lambda name: None)
         with torch.no_grad():
             B = frames_u8.shape[0]
+            if self.input_format == "nv12":
+                self._rgb_slot = 1 - getattr(self, "_rgb_slot", 0)
+                H, W = frames_u8.shape[1] * 2 // 3, frames_u8.shape[2]
+                key = ("nv12", self._rgb_slot, B, H, W, frames_u8.device)
+                if key not in self._rgb_bufs:
+                    if len(self._rgb_bufs) > 4:
+                        self._rgb_bufs.clear()
+                    self._rgb_bufs[key] = torch.empty(B, H, W, 3, dtype=torch.uint8, device=frames_u8.device)
+                frames_u8 = self._nv12_to_rgb(frames_u8.contiguous(), self._rgb_bufs[key])
             if self.bgr:
                 self._rgb_slot = 1 - getattr(self, "_rgb_slot", 0)
                 frames_u8 = self._to_rgb(frames_u8.contiguous(), self._rgb_slot, in_place=False)
@@ -229,10 +251,15 @@ class FacePipeline:
         Two frame buffers / workspace slots alternate between calls and nothing here waits for the work an earlier call
         left on the current stream: the H2D copy and the cascade of batch i+1 overlap the encoder of batch i when the
         caller keeps two batches in flight (``submit``)."""
-        B, H, W, _ = t.shape
-        key = (B, H, W, dev)
+        nv12 = self.input_format == "nv12"
+        if nv12:
+            B, H, W = t.shape[0], t.shape[1] * 2 // 3, t.shape[2]
+        else:
+            B, H, W, _ = t.shape
+        key = (B, H, W, dev, nv12)
         if getattr(self, "_fbuf_key", None) != key:
             self._fbufs = [torch.empty(B, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self._rawbufs = [torch.empty_like(t, device=dev) for _ in range(2)] if nv12 else None
             self._fbuf_key = key
             self._copy_stream = torch.cuda.Stream(dev)
             self._host_crops_done = [None, None]
@@ -249,7 +276,12 @@ class FacePipeline:
         bounds = self._sub_batches(B)
         with torch.cuda.stream(cs):
             for b0, b1 in bounds:
-                buf[b0:b1].copy_(t[b0:b1], non_blocking=True)
+                if nv12:                                               # half the bytes over PCIe, colour conversion behind the copy
+                    raw = self._rawbufs[slot]
+                    raw[b0:b1].copy_(t[b0:b1], non_blocking=True)
+                    self._nv12_to_rgb(raw[b0:b1], buf[b0:b1])
+                else:
+                    buf[b0:b1].copy_(t[b0:b1], non_blocking=True)
                 if self.bgr:
                     self._to_rgb(buf[b0:b1], None, in_place=True)      # on the copy stream, right behind the sub-batch's H2D
                 ev = torch.cuda.Event()
@@ -279,7 +311,7 @@ class FacePipeline:
         t = torch.as_tensor(frames)
         if t.is_cuda:
             out = self.run_device(t)
-        elif t.is_pinned() and t.dim() == 4 and t.shape[0] > self.sub_batch and t.dtype == torch.uint8:
+        elif t.is_pinned() and t.dim() == (3 if self.input_format == "nv12" else 4) and t.shape[0] > self.sub_batch and t.dtype == torch.uint8:
             out = self._run_host_frames(t, dev)
         else:
             out = self.run_device(t.to(dev, non_blocking=True))
