@@ -421,35 +421,54 @@ def run_ours(args):
 
     # ---- end to end through the public API: pinned host frames in, host results out (`e2e`)
     e2e_steps = 1 if args.skip_e2e else args.steps
-    for _ in range(0 if args.skip_e2e else 3):
-        fp_host(frames_pinned)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    faces_e2e, d2h = 0, 0
-    e0.record()
-    if args.no_pipeline:
-        for _ in range(e2e_steps):
-            res = fp_host(frames_pinned)
-            faces_e2e += sum(len(r["labels"]) for r in res)
-    else:
-        # the streaming form of the public call: two batches in flight -- batch i+1 is submitted (its H2D copy and cascade
-        # start under the encoder of batch i), then the results of batch i are collected on the host.  Every step's
-        # frames are copied from pinned host memory and every step's results are read back inside the timed region.
-        pending = None
-        for _ in range(e2e_steps):
-            nxt = fp_host.submit(frames_pinned)
-            if pending is not None:
-                res = pending.result()
-                faces_e2e += sum(len(r["labels"]) for r in res)
-            pending = nxt
-        res = pending.result()
-        faces_e2e += sum(len(r["labels"]) for r in res)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+
+    def measure_e2e(fph, pinned):
+        for _ in range(0 if args.skip_e2e else 3):
+            fph(pinned)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nf, res = 0, None
+        e0.record()
+        if args.no_pipeline:
+            for _ in range(e2e_steps):
+                res = fph(pinned)
+                nf += sum(len(r["labels"]) for r in res)
+        else:
+            # the streaming form of the public call: two batches in flight -- batch i+1 is submitted (its H2D copy and cascade
+            # start under the encoder of batch i), then the results of batch i are collected on the host.  Every step's
+            # frames are copied from pinned host memory and every step's results are read back inside the timed region.
+            pending = None
+            for _ in range(e2e_steps):
+                nxt = fph.submit(pinned)
+                if pending is not None:
+                    res = pending.result()
+                    nf += sum(len(r["labels"]) for r in res)
+                pending = nxt
+            res = pending.result()
+            nf += sum(len(r["labels"]) for r in res)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), nf, res
+
+    ms_e2e, faces_e2e, res = measure_e2e(fp_host, frames_pinned)
     nf_step = faces_e2e // max(1, e2e_steps)
     # face counts + status, the (B, capf, 5) box tensor (copied whole: contiguous async copy), label / prob / embedding per face
     d2h = (B + 1) * 4 + B * det.caps[3] * 5 * 4 + nf_step * (8 + 4 + 512 * 4)
+    # the same measurement with the host frames in the decoder's native NV12 (half the bytes over PCIe; extra key `e2e_nv12`):
+    # at 8 GPUs the RGB frames of all ranks (8 x 398 MB per 10 ms step) exceed what one host can push (~170 GB/s measured)
+    ms_nv12 = faces_nv12 = None
+    if args.ingest == "rgb" and not args.skip_e2e and not args.no_nv12:
+        import cv2
+        Hh, Ww = frames_np.shape[1:3]
+        nv12 = np.empty((B, Hh * 3 // 2, Ww), np.uint8)
+        for i in range(B):
+            i420 = cv2.cvtColor(frames_np[i], cv2.COLOR_RGB2YUV_I420)
+            nv12[i, :Hh] = i420[:Hh]
+            nv12[i, Hh:] = np.stack([i420[Hh:Hh + Hh // 4].reshape(Hh // 2, Ww // 2), i420[Hh + Hh // 4:].reshape(Hh // 2, Ww // 2)],
+                                    axis=-1).reshape(Hh // 2, Ww)
+        fp_nv = pipeline.FacePipeline(det, enc, cls, (160, 160), "similarity", max_faces_per_frame=wl["max_faces"], input_format="nv12")
+        nv_pinned = torch.from_numpy(nv12).pin_memory()
+        ms_nv12, faces_nv12, _ = measure_e2e(fp_nv, nv_pinned)
 
     # ---- second headline figure of BASELINE.json ("embeds/sec"): InceptionResnetV1 + L2-norm + MLP classify on
     # batch-1024 synthetic 160x160 crops (config 2) through the public forward() API, crops resident on the device
@@ -499,12 +518,14 @@ def run_ours(args):
 
     # ---- reductions over ranks
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_nv12 or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
-        c = torch.tensor([faces, faces_e2e, launches], device=dev, dtype=torch.float64)
+        ms, ms_e2e, ms_nv12_max = t.tolist()
+        c = torch.tensor([faces, faces_e2e, launches, faces_nv12 or 0], device=dev, dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        faces, faces_e2e, launches = [int(v) for v in c.tolist()]
+        faces, faces_e2e, launches, faces_nv12_sum = [int(v) for v in c.tolist()]
+        if ms_nv12 is not None:
+            ms_nv12, faces_nv12 = ms_nv12_max, faces_nv12_sum
 
     if rank == 0:
         ws = out["ws"]
@@ -574,6 +595,11 @@ def run_ours(args):
                         "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / e2e_steps,
                         "api": "FacePipeline.__call__ (one batch at a time)" if args.no_pipeline else
                                "FacePipeline.submit / PendingResult.result, two batches in flight"},
+                "e2e_nv12": None if ms_nv12 is None else {
+                    "value": faces_nv12 / (ms_nv12 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(frames_np.nbytes // 2),
+                    "ms_per_step": ms_nv12 / e2e_steps,
+                    "note": "the same e2e measurement with NV12 host frames (a video decoder's native output, 1.5 B/px) converted on the "
+                            "device bit-identically to cv2.cvtColor(COLOR_YUV2RGB_NV12): FacePipeline(input_format='nv12')"},
                 "gpu_launches": int(launches), "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
                 "roofline": roof, "roofline_other": det_roofs, "clocks": clocks, "embed": embed, "gallery_topk": topk}
         if world == 1 and not args.no_cpu_baseline:
@@ -621,6 +647,7 @@ def main():
     ap.add_argument("--embed-batch", type=int, default=1024, help="crops per rank of the embeds/s measurement (config 2)")
     ap.add_argument("--ingest", default="rgb", choices=["rgb", "nv12"], help="host frame format of the e2e leg: packed RGB (what the "
                     "reference's cap.read + cvtColor hands over) or NV12 as a video decoder delivers it (half the H2D bytes, converted on the device)")
+    ap.add_argument("--no-nv12", action="store_true", help="skip the extra e2e_nv12 measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: one un-warmed e2e step")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time: no overlap between consecutive steps")
