@@ -4,7 +4,7 @@ Weight packing (done once per ``load_state_dict`` / first forward, on the GPU wi
   * BatchNorm (eval, eps 1e-3) is folded into the conv: W' = W * gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps)
     (inception_resnet_v1.py:12-33); the residual scale of Block35/17/8 is folded into the projection conv
     (``out*scale + x``, :64-66, :92-94, :121-125).
-  * weights go to bf16 [cout_pad][k_pad] with k = (ky*KW + kx)*cin + c (NHWC implicit-GEMM order), zero padded.
+  * weights go to 16-bit [cout_pad][k_pad] with k = (ky*KW + kx)*cin + c (NHWC implicit-GEMM order), zero padded.
   * sibling 1x1 branch convs that read the same input are concatenated along cout and run as ONE GEMM whose epilogue
     scatters column ranges to different destinations (the concat buffer / the branch scratch).
 Activations are NHWC 16-bit (fp16 / bf16); ``torch.cat`` never runs: every conv writes straight into its channel slice.
@@ -41,6 +41,10 @@ USE_GRAPHS = not os.environ.get("VNFR_NO_GRAPH")
 #: Block17 as one fused kernel per block (csrc/block17_fused.cu) when its map is 8x8 (160x160 crops); VNFR_NO_FUSED_B17=1
 #: keeps the four-launch form (A/B measurements)
 FUSED_B17 = not os.environ.get("VNFR_NO_FUSED_B17")
+#: crops per pass of the Block35 section (VNFR_B35_CHUNK).  Default: one pass over the whole batch -- measured for 768 crops
+#: (encoder stage): one pass 4.16 ms, chunks of 384 / 256 / 192 / 128 crops 4.22 / 4.32 / 4.48 / 4.67 ms: keeping a chunk's trunk
+#: L2-resident across the five blocks does not pay for the extra launches (the section is launch- / latency-bound, not DRAM-bound)
+B35_CHUNK = int(os.environ.get("VNFR_B35_CHUNK", str(1 << 30)))
 #: Block35's two parallel 3x3 convolutions as one block-diagonal launch (VNFR_NO_GROUPED_B35=1: two launches)
 GROUPED_B35 = not os.environ.get("VNFR_NO_GROUPED_B35")
 
@@ -474,18 +478,26 @@ class EncoderPlan:
         ol.conv(P["conv2d_4a"], View(c3b), View(c4a))
         ol.conv(P["conv2d_4b"], View(c4a), View(x35), stride=2)
         # ---- 5 x Block35 (scale 0.17)
-        cat, t1, t2 = buf(h5, w5, 96), buf(h5, w5, 64), buf(h5, w5, 32)
-        for i in range(5):
-            p = "repeat_1.%d" % i
-            ol.conv(P[p + ".in"], View(x35), View(cat, 0, 32), dst1=View(t1), n_split=32)
-            if GROUPED_B35:
-                # branch1.1 and branch2.1 as one block-diagonal 64 -> 64 convolution writing both destinations
-                ol.conv(P[p + ".b12"], View(t1), View(cat, 32, 32), dst1=View(t2), n_split=32, pad=(1, 1))
-            else:
-                ol.conv(P[p + ".b1"], View(t1, 0, 32), View(cat, 32, 32), pad=(1, 1))
-                ol.conv(P[p + ".b2a"], View(t1, 32, 32), View(t2), pad=(1, 1))
-            ol.conv(P[p + ".b2b"], View(t2), View(cat, 64, 32), pad=(1, 1))
-            ol.conv(P[p + ".out"], View(cat), View(x35), residual=View(x35), relu=True)
+        cat_f, t1_f, t2_f = buf(h5, w5, 96), buf(h5, w5, 64), buf(h5, w5, 32)
+        # Optionally (VNFR_B35_CHUNK) the five blocks run chunk by chunk over the batch so that a chunk's trunk + branch buffers
+        # (0.26 MB per crop) stay in L2 across its 20 launches; measured slower than one pass (see B35_CHUNK), so off by default.
+        n_b35 = max(1, min(n, -(-n // B35_CHUNK)))
+        bounds35 = [(k * n // n_b35, (k + 1) * n // n_b35) for k in range(n_b35)]
+        for a0, a1 in bounds35:
+            if a1 <= a0:
+                continue
+            xs, cat, t1, t2 = x35[a0:a1], cat_f[a0:a1], t1_f[a0:a1], t2_f[a0:a1]
+            for i in range(5):
+                p = "repeat_1.%d" % i
+                ol.conv(P[p + ".in"], View(xs), View(cat, 0, 32), dst1=View(t1), n_split=32)
+                if GROUPED_B35:
+                    # branch1.1 and branch2.1 as one block-diagonal 64 -> 64 convolution writing both destinations
+                    ol.conv(P[p + ".b12"], View(t1), View(cat, 32, 32), dst1=View(t2), n_split=32, pad=(1, 1))
+                else:
+                    ol.conv(P[p + ".b1"], View(t1, 0, 32), View(cat, 32, 32), pad=(1, 1))
+                    ol.conv(P[p + ".b2a"], View(t1, 32, 32), View(t2), pad=(1, 1))
+                ol.conv(P[p + ".b2b"], View(t2), View(cat, 64, 32), pad=(1, 1))
+                ol.conv(P[p + ".out"], View(cat), View(xs), residual=View(xs), relu=True)
         # ---- Mixed_6a
         h6, w6 = _out_hw(h5, 3, 2), _out_hw(w5, 3, 2)
         x17 = buf(h6, w6, 896)
@@ -531,35 +543,6 @@ class EncoderPlan:
         self.weights = weights
         self.tails = {}
         self.taps = {"conv2d_1a": c1a, "conv2d_2b": c2b, "conv2d_4b_repeat_1": x35, "repeat_2": x17, "block8": x8}
-
-    def run(self):
-        self.ol.run()
-
-
-class MlpWeights:
-    """MLPModel (mlp_model.py:6-8): dense_1 512->2048 (+ReLU), dense_2 2048->C."""
-
-    def __init__(self, sd, device, dtype=None):
-        self.dtype = dtype or HALF
-        self.num_classes = sd["dense_2.weight"].shape[0]
-        self.input_dim = sd["dense_1.weight"].shape[1]
-        self.d1 = pack_conv(sd["dense_1.weight"].float()[:, :, None, None], None, sd["dense_1.bias"].float(), device,
-                            dtype=self.dtype)
-        self.d2 = pack_conv(sd["dense_2.weight"].float()[:, :, None, None], None, sd["dense_2.bias"].float(), device,
-                            dtype=self.dtype)
-
-
-class MlpPlan:
-    """x bf16 (n, input_dim) -> logits fp32 (n, cout16) (first num_classes columns valid)."""
-
-    def __init__(self, weights, n, device):
-        self.w = weights
-        self.x = torch.zeros(n, 1, 1, weights.input_dim, dtype=weights.dtype, device=device)
-        self.hid = torch.empty(n, 1, 1, 2048, dtype=weights.dtype, device=device)
-        self.logits = torch.empty(n, weights.d2.cout, dtype=torch.float32, device=device)
-        self.ol = OpList()
-        self.ol.conv(weights.d1, View(self.x), View(self.hid), relu=True)
-        self.ol.conv(weights.d2, View(self.hid), None, relu=False, out_f32=self.logits)
 
     def run(self):
         self.ol.run()
