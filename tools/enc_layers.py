@@ -29,7 +29,10 @@ for i, op in enumerate(plan.ol.ops):
     torch.cuda.synchronize()
     us = t0.elapsed_time(t1) / reps * 1e3
     c = op.conv
-    if op.kind == 0:
+    if op.kind == 3:
+        fl = 2.0 * n * 64 * (896 * 256 + 2 * 896 * 128 + 256 * 896)
+        rows.append((i, "block17", n * 64, 896, 896, 0, 9, us, fl / us / 1e6, 2.0 * 2 * n * 64 * 896 / us / 1e3))
+    elif op.kind == 0:
         M = c.n_img * c.out_h * c.out_w
         K = c.kh * c.kw * c.cin
         fl = 2.0 * M * K * c.cout

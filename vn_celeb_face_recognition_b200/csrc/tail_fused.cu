@@ -87,11 +87,9 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-__device__ __forceinline__ void split_store(__half* hi_row, __half* lo_row, int i, float v) {
-  const __half h = __float2half_rn(v);
-  hi_row[i] = h;
-  lo_row[i] = __float2half_rn(v - __half2float(h));
-}
+// Optional phase timestamps of CTA 0 (tools/tail_probe.py): globaltimer ns at kernel start and after every grid barrier.
+__device__ unsigned long long* g_tail_dbg = nullptr;
+#define TL_STAMP(i) do { if (g_tail_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) g_tail_dbg[i] = globaltimer_ns(); } while (0)
 
 __global__ void __launch_bounds__(TL_THREADS, 1)
 tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_w0,
@@ -125,6 +123,8 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   unsigned int epoch = 0;
+  int stamp = 0;
+  TL_STAMP(stamp++);
   const int gthreads = gridDim.x * TL_THREADS, gtid = blockIdx.x * TL_THREADS + tid;
 
   // ================================================================== INPUT phase: rows -> split planes of layer 0
@@ -137,14 +137,21 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (p.in_mode == 0) {
         const uint16_t* xr = reinterpret_cast<const uint16_t*>(p.x) + (size_t)row * p.hw * p.x_pitch + cg * 8;
-        for (int px = 0; px < p.hw; ++px) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(xr + (size_t)px * p.x_pitch));
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int px0 = 0; px0 < p.hw; px0 += 9) {            // nine independent 16-byte loads in flight (hw = 9 for 160 px crops), summed in pixel order
+          uint4 v3[9];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float lo, hi;
-            if (p.x_f16) unpack2<true>(w[e], lo, hi); else unpack2<false>(w[e], lo, hi);
-            s[2 * e] += lo; s[2 * e + 1] += hi;
+          for (int u = 0; u < 9; ++u)
+            v3[u] = px0 + u < p.hw ? __ldg(reinterpret_cast<const uint4*>(xr + (size_t)(px0 + u) * p.x_pitch)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int u = 0; u < 9; ++u) {
+            if (px0 + u >= p.hw) break;
+            const uint32_t w[4] = {v3[u].x, v3[u].y, v3[u].z, v3[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float lo, hi;
+              if (p.x_f16) unpack2<true>(w[e], lo, hi); else unpack2<false>(w[e], lo, hi);
+              s[2 * e] += lo; s[2 * e + 1] += hi;
+            }
           }
         }
         const float d = (float)p.hw;
@@ -170,6 +177,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
     fence_proxy_async_global();
   }
   grid_sync(p.bar, epoch);
+  TL_STAMP(stamp++);
 
   // pipeline state of the three GEMM roles persists across layers (barrier phases keep running)
   int ps = 0; uint32_t pph = 1;            // producer: stage, "slot free" parity
@@ -258,41 +266,66 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
       }
     }
     grid_sync(p.bar, epoch);
+    TL_STAMP(stamp++);
 
-    // ================================================================ ROW phase: one warp per row
+    // ================================================================ ROW phase: one warp per row.  A lane owns the column quads
+    // q = lane + 32 j (columns 4q..4q+3); quads are processed in batches of 4 per lane (512 columns per warp) with the loads of
+    // ALL K splits of a batch in flight at once (the first version's one-load-at-a-time loop was pure L2 latency: 26-68 us per
+    // phase), partial sums are added in split order (deterministic).
     {
       float* rowbuf = reinterpret_cast<float*>(smem_al) + warp * TL_ROWBUF_FLOATS;
       const int gwarps = gridDim.x * (TL_THREADS / 32), gwarp = blockIdx.x * (TL_THREADS / 32) + warp;
       const size_t plane = (size_t)p.n_pad * L.N_pad;
+      const int n_batches = L.N_pad >> 9, tail_quads = (L.N_pad & 511) >> 7;     // batches of 4 quads per lane + 0..3 single quads
       for (int row = gwarp; row < p.n; row += gwarps) {
         const float* pr = L.partial + (size_t)row * L.N_pad;
         float ss = 0.f, mx = -CUDART_INF_F;
         int arg = 0x7fffffff;
-        for (int i = lane; i < L.N; i += 32) {
-          float v = __ldcg(pr + i);
-          for (int sp = 1; sp < L.split_k; ++sp) v += __ldcg(pr + sp * plane + i);
-          v += __ldg(L.bias + i);
-          if (L.rowop == 1) v = fmaxf(v, 0.f);
-          rowbuf[i] = v;
-          ss += v * v;
-          if (v > mx) { mx = v; arg = i; }
+        auto consume = [&](float4 v, int col) {            // bias, activation, row statistics, stash in the row buffer
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(L.bias + col));
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (L.rowop == 1) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          *reinterpret_cast<float4*>(rowbuf + col) = v;
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          if (col < L.N && v.x > mx) { mx = v.x; arg = col; }
+          if (col + 1 < L.N && v.y > mx) { mx = v.y; arg = col + 1; }
+          if (col + 2 < L.N && v.z > mx) { mx = v.z; arg = col + 2; }
+          if (col + 3 < L.N && v.w > mx) { mx = v.w; arg = col + 3; }
+        };
+        for (int bt = 0; bt < n_batches; ++bt) {
+          const int col0 = bt * 512 + lane * 4;
+          float4 acc[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = __ldcg(reinterpret_cast<const float4*>(pr + col0 + 128 * j));
+          for (int sp = 1; sp < L.split_k; ++sp) {
+            float4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = __ldcg(reinterpret_cast<const float4*>(pr + sp * plane + col0 + 128 * j));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[j].x += t[j].x; acc[j].y += t[j].y; acc[j].z += t[j].z; acc[j].w += t[j].w; }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) consume(acc[j], col0 + 128 * j);
         }
+        for (int j = 0; j < tail_quads; ++j) {
+          const int col = n_batches * 512 + 128 * j + lane * 4;
+          float4 acc = __ldcg(reinterpret_cast<const float4*>(pr + col));
+          for (int sp = 1; sp < L.split_k; ++sp) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(pr + sp * plane + col));
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          consume(acc, col);
+        }
+        __syncwarp();
+        const int n_quads = L.N_pad >> 7;                   // quads per lane
         __half* hi_row = L.a_next != nullptr ? L.a_next + (size_t)row * L.N : nullptr;
         __half* lo_row = L.a_next != nullptr ? L.a_next + ((size_t)p.n_pad + row) * L.N : nullptr;
         float* ov = L.out_vec != nullptr ? L.out_vec + (size_t)row * L.out_vec_pitch : nullptr;
+        float scale = 1.f, shift = 0.f;                     // output = v / scale - shift
         if (L.rowop == 2) {
           // F.normalize(p=2, dim=1, eps=1e-12): x / max(||x||, eps)
           ss = warp_sum_f(ss);
-          const float denom = fmaxf(sqrtf(ss), 1e-12f);
-          for (int i = lane; i < L.N; i += 32) {
-            const float v = rowbuf[i] / denom;
-            if (ov != nullptr) ov[i] = v;
-            if (p.emb_half != nullptr) {
-              if (p.emb_half_f16) reinterpret_cast<__half*>(p.emb_half)[(size_t)row * L.N + i] = __float2half_rn(v);
-              else reinterpret_cast<__nv_bfloat16*>(p.emb_half)[(size_t)row * L.N + i] = __float2bfloat16_rn(v);
-            }
-            if (hi_row != nullptr) split_store(hi_row, lo_row, i, v);
-          }
+          scale = fmaxf(sqrtf(ss), 1e-12f);
         } else if (L.rowop == 3) {
           // log_softmax + argmax (first maximal index) + exp(max log-prob) + identify_person's threshold
 #pragma unroll
@@ -302,11 +335,17 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
             if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
           }
           float se = 0.f;
-          for (int i = lane; i < L.N; i += 32) se += expf(rowbuf[i] - mx);
+          for (int j = 0; j < n_quads; ++j) {
+            const int col = 128 * j + lane * 4;
+            const float4 v = *reinterpret_cast<const float4*>(rowbuf + col);
+            if (col < L.N) se += expf(v.x - mx);
+            if (col + 1 < L.N) se += expf(v.y - mx);
+            if (col + 2 < L.N) se += expf(v.z - mx);
+            if (col + 3 < L.N) se += expf(v.w - mx);
+          }
           se = warp_sum_f(se);
           const float lse = logf(se);
-          if (ov != nullptr)
-            for (int i = lane; i < L.N; i += 32) ov[i] = rowbuf[i] - mx - lse;
+          shift = mx + lse;
           if (lane == 0) {
             const float pb = expf(-lse);
             const float th = p.thr_class != nullptr ? __ldg(p.thr_class + arg) : p.thr;
@@ -316,11 +355,33 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
             if (p.label_f != nullptr) p.label_f[(size_t)row * p.lp_pitch] = (float)lab;
             if (p.prob_f != nullptr) p.prob_f[(size_t)row * p.lp_pitch] = pb;
           }
-        } else {
-          for (int i = lane; i < L.N; i += 32) {
-            const float v = rowbuf[i];
-            if (ov != nullptr) ov[i] = v;
-            if (hi_row != nullptr) split_store(hi_row, lo_row, i, v);
+        }
+        if (ov != nullptr || hi_row != nullptr || (L.rowop == 2 && p.emb_half != nullptr)) {
+          for (int j = 0; j < n_quads; ++j) {
+            const int col = 128 * j + lane * 4;
+            if (col >= L.N) break;
+            float4 v = *reinterpret_cast<const float4*>(rowbuf + col);
+            if (L.rowop == 2) { v.x = v.x / scale; v.y = v.y / scale; v.z = v.z / scale; v.w = v.w / scale; }
+            else if (L.rowop == 3) { v.x -= shift; v.y -= shift; v.z -= shift; v.w -= shift; }
+            if (ov != nullptr) {                            // rows of `ov` need not be 16-byte aligned (pitch = n_classes)
+              ov[col] = v.x;
+              if (col + 1 < L.N) ov[col + 1] = v.y;
+              if (col + 2 < L.N) ov[col + 2] = v.z;
+              if (col + 3 < L.N) ov[col + 3] = v.w;
+            }
+            if (L.rowop == 2 && p.emb_half != nullptr) {    // N is a multiple of 4 here (embedding width)
+              uint2 pk;
+              if (p.emb_half_f16) { pk.x = pack2<true>(v.x, v.y); pk.y = pack2<true>(v.z, v.w); }
+              else { pk.x = pack2<false>(v.x, v.y); pk.y = pack2<false>(v.z, v.w); }
+              *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p.emb_half) + (size_t)row * L.N + col) = pk;
+            }
+            if (hi_row != nullptr) {                        // the next layer's K = N is a multiple of 64: whole quads
+              const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+              const __half2 l0 = __floats2half2_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+              const __half2 l1 = __floats2half2_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+              *reinterpret_cast<uint2*>(hi_row + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+              *reinterpret_cast<uint2*>(lo_row + col) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            }
           }
         }
         __syncwarp();
@@ -329,6 +390,7 @@ tail_fused_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_consta
       fence_proxy_async_smem();              // and its TMA writes reuse the shared memory of the row buffers
     }
     if (l + 1 < p.n_layers) grid_sync(p.bar, epoch);
+    TL_STAMP(stamp++);
   }
 
   __syncthreads();
@@ -352,6 +414,12 @@ size_t tail_smem_bytes() { return 1024 + (size_t)TL_STAGES * TL_STAGE_BYTES + 16
 }  // namespace
 
 extern long long g_vnfr_launches;
+
+// debug hook (not part of include/vnfr_b200.h): device buffer of 16 uint64 timestamps, or null to switch off
+extern "C" int vnfr_tail_debug(unsigned long long* dev_buf) {
+  VNFR_CUDA(cudaMemcpyToSymbol(g_tail_dbg, &dev_buf, sizeof(dev_buf)));
+  return VNFR_OK;
+}
 
 extern "C" int vnfr_tail_prepare(VnfrTailOp* op) {
   VNFR_REQUIRE(op != nullptr, "op is null");
