@@ -111,13 +111,32 @@ int vnfr_onet_forward(const uint8_t* frames, int B, int H, int W, int cap, const
                       const float* weights, float* prob, float* reg, float* lmk, int32_t* offs, float* crops, int crop_cap,
                       int32_t* status, void* stream);
 
+/* The layers after the last tensor-core convolution of R-Net (maxpool 3/2 -> conv3 2x2 + PReLU -> dense4 + PReLU -> heads,
+ * mtcnn.py:84-99) and O-Net (maxpool 2/2 -> conv4 2x2 + PReLU -> dense5 + PReLU -> heads, mtcnn.py:138-157) as three
+ * split-precision tensor-core GEMMs over all crops of the batch (heads_chain.cu) instead of the per-crop FMA kernels.
+ * Every fp32 weight matrix is passed as two fp16 planes: rows [0, N_pad) = fp16(w), rows [N_pad, 2 N_pad) = fp16(w - hi),
+ * N_pad = N rounded up to 128, row length K:
+ *   w[0]: the 2x2 convolution, K = 256: column (ky*2 + kx)*64 + c = weight[n][c][ky][kx], channels c >= C_in zero;
+ *   w[1]: the dense layer exactly as torch stores it (K = 576 / 1152, the reference's (W,H,C) flatten order);
+ *   w[2]: the heads stacked: R-Net [dense5_1 (2); dense5_2 (4)], O-Net [dense6_1 (2); dense6_2 (4); dense6_3 (10)].
+ * bias[l]: fp32 [N_pad]; alpha[0..1]: PReLU slopes fp32 [N_pad] of the convolution and the dense layer.
+ * planes: workspace of vnfr_heads_back_workspace_bytes(onet, crop_cap) bytes, 1024-byte aligned.                        */
+typedef struct VnfrHeadsBack {
+  const void* w[3];
+  const float* bias[3];
+  const float* alpha[2];
+  void* planes;
+} VnfrHeadsBack;
+long long vnfr_heads_back_workspace_bytes(int onet, int crop_cap);
+
 /* R-Net with conv2 (28 -> 48, 3x3; 64 % of its FLOPs) on the tensor cores in split precision (two fp16 parts per fp32 operand,
  * three products, fp32 accumulation; vnfr_conv_run with VnfrConvOp.split3 = 2) over all crops in one launch; the other layers
  * stay on the fp32 FMA path.  w2_split: fp16 [48][896] (split2 layout, sv_ck 32); p1: fp16 [crop_cap][11][11][64] and
- * c2: fp32 [crop_cap][81][48] workspaces.  Same outputs and semantics as vnfr_rnet_forward.                           */
+ * c2: fp32 [crop_cap][81][48] workspaces.  back (nullable): run the layers after conv2 on the tensor cores as well
+ * (VnfrHeadsBack above).  Same outputs and semantics as vnfr_rnet_forward.                                              */
 int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
                          const float* weights, const void* w2_split, float* prob, float* reg, int32_t* offs, float* crops,
-                         void* p1, float* c2, int crop_cap, int32_t* status, void* stream);
+                         void* p1, float* c2, int crop_cap, int32_t* status, const VnfrHeadsBack* back, void* stream);
 
 /* O-Net with conv2 (63 % of its FLOPs) on the tensor cores in split precision, fp32 accumulation (vnfr_conv_run with
  * VnfrConvOp.split3 = split_mode) over all crops in one launch; the other layers stay on the fp32 FMA path.
@@ -126,11 +145,12 @@ int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, co
  * c2: fp32 [crop_cap][441][64] workspace.
  * w3_split (nullable): conv3 (64 -> 64, 3x3; 18 % of the FLOPs) on the tensor cores as well, always as two fp16 parts:
  * fp16 [64][1728] (pack_conv_split2, sv_ck 64) with workspaces p3: fp16 [crop_cap][10][10][128] and c3: fp32 [crop_cap][64][64];
- * NULL keeps conv3 on the FMA path (p3 / c3 are then ignored).  Same outputs and semantics as vnfr_onet_forward.     */
+ * NULL keeps conv3 on the FMA path (p3 / c3 are then ignored).  back (nullable, needs w3_split): the layers after conv3 on
+ * the tensor cores as well (VnfrHeadsBack above).  Same outputs and semantics as vnfr_onet_forward.                     */
 int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
                          const float* weights, const void* w2_split, int split_mode, float* prob, float* reg, float* lmk,
                          int32_t* offs, float* crops, void* p1, float* c2, const void* w3_split, void* p3, float* c3,
-                         int crop_cap, int32_t* status, void* stream);
+                         int crop_cap, int32_t* status, const VnfrHeadsBack* back, void* stream);
 
 /* Stage-2 tail (detect_face.py:119-136): score > threshold, NMS(0.7), bbreg, rerec, pad. */
 int vnfr_stage2_boxes(int B, int H, int W, int cap2, const int32_t* s2_count, const float* s2_box, const float* s2_prob,

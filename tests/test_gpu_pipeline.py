@@ -123,20 +123,27 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
             crops_t = torch.empty_like(crops)
             p1 = torch.empty(len(y) * 121 * 64, dtype=torch.float16, device=dev)
             c2 = torch.empty(len(y) * 81 * 48, device=dev)
-            _lib.call("vnfr_rnet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), P(prob_t), P(reg_t),
-                      P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), _lib.stream_ptr())
-            torch.cuda.synchronize()
-            assert torch.equal(crops_t, crops)
-            errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item())
-            print("rnet tensor-core conv2: max |d prob| %.2e  |d reg| %.2e" % errs)
-            assert errs[0] < 5e-6 and errs[1] < 2e-5, errs
+            import ctypes
+            back_w = M.HeadsBackWeights(sds[net], False, dev)
+            for back in (None, back_w.struct(M.heads_back_planes(False, len(y), dev))):
+                prob_t.zero_(); reg_t.zero_()
+                _lib.call("vnfr_rnet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), P(prob_t), P(reg_t),
+                          P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), ctypes.byref(back) if back is not None else None,
+                          _lib.stream_ptr())
+                torch.cuda.synchronize()
+                assert torch.equal(crops_t, crops)
+                errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item())
+                print("rnet tensor-core conv2%s: max |d prob| %.2e  |d reg| %.2e" % ((" + back half" if back is not None else "",) + errs))
+                assert errs[0] < 5e-6 and errs[1] < 2e-5, errs
         else:
             _lib.call("vnfr_onet_forward", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(prob), P(reg), P(lmk),
                       P(offs), P(crops), len(y), P(status), _lib.stream_ptr())
             # the same through the tensor-core conv2 path (split precision: 3 x bf16 / 2 x fp16 parts): must agree with the
             # FMA path to fp32 noise
             from vn_celeb_face_recognition_b200 import encoder_plan as ep
-            for mode, tc3 in ((1, False), (2, False), (2, True)):
+            import ctypes
+            back_w = M.HeadsBackWeights(sds[net], True, dev)
+            for mode, tc3, tcb in ((1, False, False), (2, False, False), (2, True, False), (2, True, True)):
                 pack = ep.pack_conv_split2 if mode == 2 else ep.pack_conv_split3
                 w2s = pack(sds[net]["conv2.weight"], sds[net]["conv2.bias"], dev, 32).w
                 prob_t = torch.zeros_like(prob); reg_t = torch.zeros_like(reg); lmk_t = torch.zeros_like(lmk)
@@ -153,13 +160,13 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
                     c3 = torch.empty(len(y) * 64 * 64, device=dev)
                 _lib.call("vnfr_onet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), mode, P(prob_t),
                           P(reg_t), P(lmk_t), P(offs), P(crops_t), P(p1), P(c2), P(w3s), P(p3), P(c3), len(y), P(status),
-                          _lib.stream_ptr())
+                          ctypes.byref(back_w.struct(M.heads_back_planes(True, len(y), dev))) if tcb else None, _lib.stream_ptr())
                 torch.cuda.synchronize()
                 assert torch.equal(crops_t, crops)
                 errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item(), (lmk_t - lmk).abs().max().item())
-                print("onet tensor-core conv2 (split mode %d)%s: max |d prob| %.2e  |d reg| %.2e  |d lmk| %.2e" % (
-                    (mode, " + conv3" if tc3 else "") + errs))
-                assert errs[0] < 5e-6 and errs[1] < 2e-5 and errs[2] < 2e-5, (mode, tc3, errs)
+                print("onet tensor-core conv2 (split mode %d)%s%s: max |d prob| %.2e  |d reg| %.2e  |d lmk| %.2e" % (
+                    (mode, " + conv3" if tc3 else "", " + back half" if tcb else "") + errs))
+                assert errs[0] < 5e-6 and errs[1] < 2e-5 and errs[2] < 2e-5, (mode, tc3, tcb, errs)
         torch.cuda.synchronize()
         assert status.item() == 0
         ref_in = taps[key_in][order]

@@ -54,6 +54,11 @@ class Block17Op(C.Structure):
     ]
 
 
+class HeadsBack(C.Structure):
+    """VnfrHeadsBack (include/vnfr_b200.h): split-precision weights + workspace of the R-/O-Net layers after the last conv."""
+    _fields_ = [("w", C.c_void_p * 3), ("bias", C.c_void_p * 3), ("alpha", C.c_void_p * 2), ("planes", C.c_void_p)]
+
+
 class TailLayer(C.Structure):
     _fields_ = [
         ("K", C.c_int32), ("N", C.c_int32), ("N_pad", C.c_int32), ("split_k", C.c_int32), ("rowop", C.c_int32),
@@ -90,9 +95,10 @@ _SIGS = {
     "vnfr_nms_segments": [_I, _I, _P, _P, _P, _F, _I, _P, _P, _P],
     "vnfr_stage1_boxes": [C.POINTER(Pyramid), _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
     "vnfr_rnet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
-    "vnfr_rnet_forward_tc": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
+    "vnfr_rnet_forward_tc": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, C.POINTER(HeadsBack), _P],
     "vnfr_onet_forward": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
-    "vnfr_onet_forward_tc": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
+    "vnfr_onet_forward_tc": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P,
+                             C.POINTER(HeadsBack), _P],
     "vnfr_stage2_boxes": [_I, _I, _I, _I, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P],
     "vnfr_stage3_faces": [_I, _I, _P, _P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P],
     "vnfr_face_crops": [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _I, _P],
@@ -131,6 +137,8 @@ def lib():
         l.vnfr_rnet_weight_floats.restype = C.c_int
         l.vnfr_onet_weight_floats.restype = C.c_int
         l.vnfr_pnet_packed_bytes.restype = C.c_int
+        l.vnfr_heads_back_workspace_bytes.restype = C.c_longlong
+        l.vnfr_heads_back_workspace_bytes.argtypes = [C.c_int, C.c_int]
         for name, args in _SIGS.items():
             fn = getattr(l, name)      # AttributeError if the symbol is missing: fail loudly
             fn.argtypes = args
@@ -141,7 +149,7 @@ def lib():
 
 def exported_symbols():
     return ["vnfr_last_error", "vnfr_version", "vnfr_launch_count", "vnfr_rnet_weight_floats",
-            "vnfr_onet_weight_floats", "vnfr_pnet_packed_bytes"] + sorted(_SIGS)
+            "vnfr_onet_weight_floats", "vnfr_pnet_packed_bytes", "vnfr_heads_back_workspace_bytes"] + sorted(_SIGS)
 
 
 def check(rc):

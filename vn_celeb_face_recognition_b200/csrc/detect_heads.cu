@@ -1178,6 +1178,10 @@ __global__ void scan_counts_kernel(const int* __restrict__ count, int B, int cap
 
 }  // namespace
 
+// heads_chain.cu
+int vnfr_heads_back_run(int onet, const VnfrHeadsBack* hb, const float* conv_map, int B, int cap, const int32_t* offs,
+                        const int32_t* pad, float* prob, float* reg, float* lmk, int crop_cap, void* stream);
+
 extern "C" int vnfr_heads_debug(long long* dev_buf) {      // debug hook (not part of include/vnfr_b200.h)
   VNFR_CUDA(cudaMemcpyToSymbol(g_heads_dbg, &dev_buf, sizeof(dev_buf)));
   return VNFR_OK;
@@ -1223,8 +1227,9 @@ static int run_head(bool onet, const uint8_t* frames, int B, int H, int W, int c
 extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
                                     const float* weights, const void* w2_split, int split_mode, float* prob, float* reg, float* lmk,
                                     int32_t* offs, float* crops, void* p1, float* c2, const void* w3_split, void* p3, float* c3,
-                                    int crop_cap, int32_t* status, void* stream) {
+                                    int crop_cap, int32_t* status, const VnfrHeadsBack* back, void* stream) {
   VNFR_REQUIRE(frames && count && pad && weights && w2_split && prob && reg && lmk && offs && crops && p1 && c2 && status, "null pointer");
+  VNFR_REQUIRE(back == nullptr || w3_split != nullptr, "the tensor-core back half of O-Net needs conv3 on the tensor cores (w3_split)");
   VNFR_REQUIRE(split_mode == 1 || split_mode == 2, "split_mode must be 1 (3 x bf16) or 2 (2 x fp16)");
   const bool tc3 = w3_split != nullptr;
   VNFR_REQUIRE(!tc3 || (p3 != nullptr && c3 != nullptr && ((uintptr_t)p3 % 16) == 0 && ((uintptr_t)c3 % 16) == 0),
@@ -1305,6 +1310,7 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
     op3.n_img_dev = offs + B;
     const int rc = vnfr_conv_run(&op3, stream);
     if (rc != VNFR_OK) return rc;
+    if (back != nullptr) return vnfr_heads_back_run(1, back, c3, B, cap, offs, pad, prob, reg, lmk, crop_cap, stream);
     onet_back_kernel<true><<<148, NT, OB_SMEM, st>>>(a);
   } else {
     onet_back_kernel<false><<<148, NT, OB_SMEM, st>>>(a);
@@ -1318,7 +1324,8 @@ extern "C" int vnfr_onet_forward_tc(const uint8_t* frames, int B, int H, int W, 
 // 32); p1: fp16 [crop_cap][11][11][64], c2: fp32 [crop_cap][81][48] workspaces (15 488 B and 15 552 B per crop).
 extern "C" int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, int cap, const int32_t* count, const int32_t* pad,
                                     const float* weights, const void* w2_split, float* prob, float* reg, int32_t* offs,
-                                    float* crops, void* p1, float* c2, int crop_cap, int32_t* status, void* stream) {
+                                    float* crops, void* p1, float* c2, int crop_cap, int32_t* status, const VnfrHeadsBack* back,
+                                    void* stream) {
   VNFR_REQUIRE(frames && count && pad && weights && w2_split && prob && reg && offs && crops && p1 && c2 && status, "null pointer");
   VNFR_REQUIRE(crop_cap > 0 && ((uintptr_t)crops % 16) == 0 && ((uintptr_t)p1 % 16) == 0 && ((uintptr_t)c2 % 16) == 0,
                "workspaces must hold at least one crop and be 16-byte aligned");
@@ -1366,6 +1373,7 @@ extern "C" int vnfr_rnet_forward_tc(const uint8_t* frames, int B, int H, int W, 
     const int rc = vnfr_conv_run(&op, stream);
     if (rc != VNFR_OK) return rc;
   }
+  if (back != nullptr) return vnfr_heads_back_run(0, back, c2, B, cap, offs, pad, prob, reg, nullptr, crop_cap, stream);
   rnet_back_kernel<<<148 * 2, NT, RB_SMEM, st>>>(a);
   ++g_vnfr_launches;
   VNFR_CHECK_LAUNCH();

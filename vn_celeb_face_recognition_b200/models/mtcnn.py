@@ -122,6 +122,49 @@ def _pack_onet(sd):
     return torch.cat(parts).contiguous()
 
 
+class HeadsBackWeights:
+    """Split-precision weights (VnfrHeadsBack, include/vnfr_b200.h) of the layers after the last tensor-core convolution:
+    R-Net conv3 / dense4 / dense5_* (mtcnn.py:84-99), O-Net conv4 / dense5 / dense6_* (mtcnn.py:138-157)."""
+
+    def __init__(self, sd, onet, dev):
+        from ..tail import SplitLinear
+        f = lambda k: sd[k].detach().float().cpu()
+        conv, fc = ("conv4", "dense5") if onet else ("conv3", "dense4")
+        heads = ["dense6_1", "dense6_2", "dense6_3"] if onet else ["dense5_1", "dense5_2"]
+        cw = f(conv + ".weight")                                   # (co, ci, 2, 2)
+        co, ci = cw.shape[:2]
+        w1 = torch.zeros(co, 4, 64)
+        w1[:, :, :ci] = cw.permute(0, 2, 3, 1).reshape(co, 4, ci)   # column (ky*2 + kx)*64 + c
+        self.layers = [SplitLinear(w1.reshape(co, 256), f(conv + ".bias"), dev),
+                       SplitLinear(f(fc + ".weight"), f(fc + ".bias"), dev),
+                       SplitLinear(torch.cat([f(h + ".weight") for h in heads]), torch.cat([f(h + ".bias") for h in heads]), dev)]
+        self.alpha = []
+        for name, lin in (("prelu" + conv[-1], self.layers[0]), ("prelu" + fc[-1], self.layers[1])):
+            a = torch.zeros(lin.N_pad, dtype=torch.float32, device=dev)
+            a[:lin.N] = f(name + ".weight").to(dev)
+            self.alpha.append(a)
+        self.onet = bool(onet)
+
+    def struct(self, planes):
+        hb = _lib.HeadsBack()
+        for l in range(3):
+            hb.w[l] = self.layers[l].w.data_ptr()
+            hb.bias[l] = self.layers[l].bias.data_ptr()
+        for l in range(2):
+            hb.alpha[l] = self.alpha[l].data_ptr()
+        hb.planes = planes.data_ptr()
+        return hb
+
+
+def heads_back_planes(onet, crop_cap, dev):
+    """Workspace of the tensor-core back half for ``crop_cap`` crops (1024-byte aligned: torch allocations are 512-byte
+    aligned, so over-allocate and slice)."""
+    n = int(_lib.lib().vnfr_heads_back_workspace_bytes(1 if onet else 0, int(crop_cap)))
+    buf = torch.empty(n + 1024, dtype=torch.uint8, device=dev)
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + n]
+
+
 class DetectWorkspace:
     """Device buffers of one detection pass for a fixed (B, H, W, min_face_size, factor, caps)."""
 
@@ -166,11 +209,12 @@ class DetectWorkspace:
         self.ocrop_cap = max(1, min(B * cap3, max(crop_floor[1], B * crop_ws[1])))
         self.rcrops = torch.empty(self.rcrop_cap * 3 * 24 * 24, **f32)
         self.ocrops = torch.empty(self.ocrop_cap * 3 * 48 * 48, **f32)
-        self.rp1 = self.rc2 = None
+        self.rp1 = self.rc2 = self.rback = None
         if MTCNN.rnet_tensor_cores:
             # R-Net conv2 on the tensor cores: pooled conv1 map as 2 fp16 parts, conv2 output in fp32 (vnfr_rnet_forward_tc)
             self.rp1 = torch.empty(self.rcrop_cap * 11 * 11 * 64, dtype=torch.float16, device=dev)
             self.rc2 = torch.empty(self.rcrop_cap * 9 * 9 * 48, **f32)
+            self.rback = heads_back_planes(False, self.rcrop_cap, dev) if MTCNN.heads_back_tensor_cores else None
         if MTCNN.onet_tensor_cores:
             # O-Net conv2 on the tensor cores: pooled conv1 map as 2 fp16 / 3 bf16 parts, conv2 output in fp32 (vnfr_onet_forward_tc)
             if MTCNN.onet_split_mode == 2:
@@ -178,11 +222,12 @@ class DetectWorkspace:
             else:
                 self.op1 = torch.empty(self.ocrop_cap * 23 * 23 * 96, dtype=torch.bfloat16, device=dev)
             self.oc2 = torch.empty(self.ocrop_cap * 21 * 21 * 64, **f32)
-            self.op3 = self.oc3 = None
+            self.op3 = self.oc3 = self.oback = None
             if MTCNN.onet_split_mode == 2 and MTCNN.onet_conv3_tensor_cores:
                 # conv3 on the tensor cores too: pooled conv2 map as 2 fp16 parts, conv3 output in fp32
                 self.op3 = torch.empty(self.ocrop_cap * 10 * 10 * 128, dtype=torch.float16, device=dev)
                 self.oc3 = torch.empty(self.ocrop_cap * 8 * 8 * 64, **f32)
+                self.oback = heads_back_planes(True, self.ocrop_cap, dev) if MTCNN.heads_back_tensor_cores else None
         self.out_box = torch.zeros(B, capf, 5, **f32)
         self.out_pts = torch.zeros(B, capf, 10, **f32)
 
@@ -231,6 +276,9 @@ class MTCNN(nn.Module):
     onet_split_mode = int(os.environ.get("VNFR_ONET_SPLIT", "2"))
     #: O-Net conv3 on the tensor cores as well (needs onet_split_mode 2); VNFR_ONET_CONV3_FMA=1 keeps it on the FMA pipe
     onet_conv3_tensor_cores = not os.environ.get("VNFR_ONET_CONV3_FMA")
+    #: the layers after the last tensor-core convolution (2x2 conv, dense layer, heads) as split-precision GEMMs over all crops
+    #: (csrc/heads_chain.cu); VNFR_HEADS_BACK_FMA=1 keeps the per-crop FMA kernels
+    heads_back_tensor_cores = not os.environ.get("VNFR_HEADS_BACK_FMA")
 
     def __init__(self, image_size=160, margin=0, min_face_size=20, thresholds=[0.6, 0.7, 0.7], factor=0.709,
                  post_process=True, select_largest=True, selection_method=None, keep_all=False, device=None):
@@ -291,7 +339,8 @@ class MTCNN(nn.Module):
             rsd = self.rnet.state_dict()
             rw2s = encoder_plan.pack_conv_split2(rsd["conv2.weight"], rsd["conv2.bias"], dev, 32)
             self._packed = {"dev": dev, "pnet": _lib.pack_pnet_weights(pw, dev), "rnet": rw.to(dev), "onet": ow.to(dev),
-                            "onet_w2s": w2s.w, "onet_w3s": w3s.w, "rnet_w2s": rw2s.w}
+                            "onet_w2s": w2s.w, "onet_w3s": w3s.w, "rnet_w2s": rw2s.w,
+                            "rnet_back": HeadsBackWeights(rsd, False, dev), "onet_back": HeadsBackWeights(osd, True, dev)}
         return self._packed
 
     # ---- the device pipeline ------------------------------------------------------------------------------------
@@ -336,7 +385,7 @@ class MTCNN(nn.Module):
         if ws.rp1 is not None:
             _lib.call("vnfr_rnet_forward_tc", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
                       P(wts["rnet_w2s"]), P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), P(ws.rcrops), P(ws.rp1), P(ws.rc2),
-                      ws.rcrop_cap, P(ws.status), st)
+                      ws.rcrop_cap, P(ws.status), C.byref(wts["rnet_back"].struct(ws.rback)) if ws.rback is not None else None, st)
         else:
             _lib.call("vnfr_rnet_forward", P(frames_u8), B, H, W, cap2, P(ws.s2_count), P(ws.s2_pad), P(wts["rnet"]),
                       P(ws.s2_prob), P(ws.s2_reg), P(ws.offs), P(ws.rcrops), ws.rcrop_cap, P(ws.status), st)
@@ -348,7 +397,7 @@ class MTCNN(nn.Module):
             _lib.call("vnfr_onet_forward_tc", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
                       P(wts["onet_w2s"]), MTCNN.onet_split_mode, P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), P(ws.op1),
                       P(ws.oc2), P(wts["onet_w3s"] if ws.op3 is not None else None), P(ws.op3), P(ws.oc3), ws.ocrop_cap,
-                      P(ws.status), st)
+                      P(ws.status), C.byref(wts["onet_back"].struct(ws.oback)) if ws.oback is not None else None, st)
         else:
             _lib.call("vnfr_onet_forward", P(frames_u8), B, H, W, cap3, P(ws.s3_count), P(ws.s3_pad), P(wts["onet"]),
                       P(ws.s3_prob), P(ws.s3_reg), P(ws.s3_lmk), P(ws.offs), P(ws.ocrops), ws.ocrop_cap, P(ws.status), st)
