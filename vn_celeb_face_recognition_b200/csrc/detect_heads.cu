@@ -685,6 +685,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) head_front_tc_kernel(const Head
   extern __shared__ __align__(16) uint8_t rt_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
+  __shared__ float4 s_ba[16];                                    // conv1 bias (8 quads) and PReLU slopes (8 quads)
   uint8_t* base = rt_raw + ((1024u - (smem_u32(rt_raw) & 1023u)) & 1023u);
   uint8_t* s_b = base;                                           // B operand
   uint8_t* s_reg = base + F::B_BYTES;                            // A parts, later the conv1 map [rows][OH][32] fp32
@@ -703,6 +704,10 @@ __global__ void __launch_bounds__(RT_THREADS, 2) head_front_tc_kernel(const Head
     const int off = n * 32 + (((k >> 3) ^ ((n >> 2) & 1)) << 4) + 2 * (k & 7);
     *reinterpret_cast<unsigned short*>(s_b + (ky * 2 + 0) * 1024 + off) = __half_as_ushort(hi);
     *reinterpret_cast<unsigned short*>(s_b + (ky * 2 + 1) * 1024 + off) = __half_as_ushort(lo);
+  }
+  if (tid < 64) {
+    const int ch = tid & 31;
+    reinterpret_cast<float*>(s_ba)[tid] = ch < COUT ? __ldg(w + (tid < 32 ? B1 : A1) + ch) : 0.f;
   }
   if (tid == 0) { tc::mbar_init(bar, 1); tc::fence_barrier_init(); }
   if (warp == 0) {
@@ -794,13 +799,15 @@ __global__ void __launch_bounds__(RT_THREADS, 2) head_front_tc_kernel(const Head
           const int r = 128 * mt + (warp & 3) * 32 + lane;
           const int yy = r / S, x = r - S * yy;
           if (yy < ncr && x < OH) {
-            float4* dst = reinterpret_cast<float4*>(s_map + (yy * OH + x) * 32);
+            // map row = pixel, 8 float4 slots XOR-swizzled by the pixel index: lanes (= consecutive pixels) are 128 B apart,
+            // unswizzled their 128-bit stores all hit the same four banks (ncu: 72 % of the kernel's shared wavefronts)
+            const int mrow = yy * OH + x;
+            float4* dst = reinterpret_cast<float4*>(s_map + mrow * 32);
 #pragma unroll
             for (int q = 0; q < COUT / 4; ++q) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = prelu(acc[4 * q + e] + __ldg(w + B1 + 4 * q + e), __ldg(w + A1 + 4 * q + e));
-              dst[q] = make_float4(o[0], o[1], o[2], o[3]);
+              const float4 bb = s_ba[q], aa = s_ba[8 + q];
+              dst[q ^ (mrow & 7)] = make_float4(prelu(acc[4 * q] + bb.x, aa.x), prelu(acc[4 * q + 1] + bb.y, aa.y),
+                                                prelu(acc[4 * q + 2] + bb.z, aa.z), prelu(acc[4 * q + 3] + bb.w, aa.w));
             }
           }
         }
@@ -809,25 +816,32 @@ __global__ void __launch_bounds__(RT_THREADS, 2) head_front_tc_kernel(const Head
       __syncthreads();
       // ---- maxpool 3/2 (ceil: windows clipped at OH) of pooled rows [P0, P1) + two-part fp16 split
       //      -> p1 [crop][PH*PH][hi 32 | lo 32] (COUT real channels)
-      for (int i = tid; i < (P1 - P0) * PH * 32; i += RT_THREADS) {
-        const int c = i & 31, pp = i >> 5;
+      //      (a thread takes four channels: 9 x LDS.128 per 4 outputs)
+      for (int i = tid; i < (P1 - P0) * PH * 8; i += RT_THREADS) {
+        const int q = i & 7, pp = i >> 3;
         const int oyl = pp / PH, ox = pp - PH * oyl;
         const int oy = P0 + oyl;
-        float m = 0.f;
-        if (c < COUT) {
-          m = -CUDART_INF_F;
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * q < COUT) {
+          m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
               const int y = 2 * oy + ky, x = 2 * ox + kx;
-              if (y < OH && x < OH) m = fmaxf(m, s_map[((y - y0) * OH + x) * 32 + c]);
+              if (y < OH && x < OH) {
+                const int mrow = (y - y0) * OH + x;
+                const float4 v = *reinterpret_cast<const float4*>(s_map + mrow * 32 + 4 * (q ^ (mrow & 7)));
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+              }
             }
         }
-        const __half hi = __float2half_rn(m);
-        const __half lo = __float2half_rn(m - __half2float(hi));
-        unsigned short* q = p1 + ((size_t)flat * (PH * PH) + oy * PH + ox) * 64 + c;
-        q[0] = __half_as_ushort(hi); q[32] = __half_as_ushort(lo);
+        const __half2 h0 = __floats2half2_rn(m.x, m.y), h1 = __floats2half2_rn(m.z, m.w);
+        const __half2 l0 = __floats2half2_rn(m.x - __low2float(h0), m.y - __high2float(h0));
+        const __half2 l1 = __floats2half2_rn(m.z - __low2float(h1), m.w - __high2float(h1));
+        unsigned short* d = p1 + ((size_t)flat * (PH * PH) + oy * PH + ox) * 64 + 4 * q;
+        *reinterpret_cast<uint2*>(d) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(d + 32) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
       }
       __syncthreads();               // the map region is rebuilt as the A operand of the next band / crop
     }
