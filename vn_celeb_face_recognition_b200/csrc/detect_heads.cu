@@ -661,7 +661,7 @@ __global__ void __launch_bounds__(NT, 1) rnet_front_kernel(const HeadArgs a) {
 // shared-memory map (aliasing the A buffers), max-pool 3/2 and write the two-part fp16 split that conv2's shifted-view
 // convolution reads.  R-Net: the whole 22x22 map is one band (5 tiles); O-Net: bands of 4 pooled rows = 9 conv rows (4
 // tiles, one conv row recomputed per band).  Two CTAs per SM.
-constexpr int RT_THREADS = 256;
+constexpr int RT_THREADS = 512;         // 2 CTAs x 16 warps per SM: every phase between the barriers is latency-bound
 
 template <int S, int COUT, int PB, int W1, int B1, int A1>
 struct FrontTc {
@@ -786,10 +786,10 @@ __global__ void __launch_bounds__(RT_THREADS, 2) head_front_tc_kernel(const Head
       phase ^= 1u;
       tc::tc_fence_after();
       __syncthreads();               // every thread has seen the MMAs complete: the A buffers may be overwritten by the map
-      // ---- TMEM -> + bias, PReLU -> conv1 map [ncr][OH][32] fp32 (warp group g = warp >> 2 takes row tiles g, g + 2, ...)
+      // ---- TMEM -> + bias, PReLU -> conv1 map [ncr][OH][32] fp32 (warp group g = warp >> 2 takes row tiles g, g + 4, ...)
       {
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int mt = warp >> 2; mt < MT; mt += 2) {
+        for (int mt = warp >> 2; mt < MT; mt += RT_THREADS / 128) {
           float acc[32];
           __syncwarp();
           tc::tmem_ld16_issue(t_lane + 32u * mt, acc);
