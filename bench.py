@@ -359,7 +359,7 @@ def run_ours(args):
         if len(gather_events) >= 2 and gather_events[-2] is not None:
             torch.cuda.current_stream().wait_event(gather_events[-2])
         out = fp.run_device(frames_dev, mark=mark if timed else None, pipelined=not timed and not args.no_pipeline)
-        if world > 1:
+        if world > 1 and not os.environ.get("VNFR_BENCH_NO_EXCHANGE"):      # (diagnostic switch: what the exchange costs)
             if os.environ.get("VNFR_RAGGED_GATHER"):
                 vdist.all_gather_faces(out["emb"], out["label"], out["prob"])
             else:
