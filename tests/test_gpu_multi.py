@@ -61,6 +61,15 @@ def _worker(rank, world, port, q):
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
         emb, label, prob, counts = vdist.compact_faces(gathered, D)
+    # the same exchange without a collective kernel: symmetric send buffer, copy-engine pull from the peers (dist.PeerGather)
+    pg = vdist.PeerGather()
+    sym = pg.alloc((cap + 1, payload.shape[1]), dev)
+    for rep in range(3):                                   # repeated: the barriers' channels / the buffer are reused
+        sym.copy_(payload)
+        g2, D2, ev2 = pg.gather(sym, stream=side if rep & 1 else None)
+        torch.cuda.current_stream().wait_event(ev2)
+        assert D2 == D and torch.equal(g2, gathered), "PeerGather differs from the NCCL all_gather"
+        sym.zero_()                                        # safe: ev2 = every peer has read the buffer
     if rank == 0:
         ref = fp(torch.from_numpy(frames).to(dev))         # single-GPU result on ALL frames
         q.put((emb.cpu().numpy(), label.cpu().numpy(), prob.cpu().numpy(), counts.cpu().numpy(),

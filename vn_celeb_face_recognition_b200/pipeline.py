@@ -106,7 +106,10 @@ class FacePipeline:
         cap = max(B * self.max_faces_per_frame, 1)
         key = (cap, dev)
         if key not in self._payloads:
-            self._payloads = {key: [torch.zeros(cap + 1, 514, dtype=torch.float32, device=dev) for _ in range(2)]}
+            # ``payload_alloc`` (optional attribute, set by dist.PeerGather.attach): allocate the send buffers in memory that
+            # peer GPUs can read (the copy-engine exchange); default: ordinary device memory
+            alloc = getattr(self, "payload_alloc", None) or (lambda shape, d: torch.zeros(*shape, dtype=torch.float32, device=d))
+            self._payloads = {key: [alloc((cap + 1, 514), dev) for _ in range(2)]}
         self._payload_slot = 1 - self._payload_slot
         return self._payloads[key][self._payload_slot]
 
