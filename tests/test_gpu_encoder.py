@@ -272,6 +272,36 @@ def test_gallery_topk_matches_torch(dev):
     assert (ib.cpu() == rib).float().mean() > 0.995
 
 
+def test_gallery_topk_two_cta_kernel_matches(dev):
+    """The tcgen05.mma.cta_group::2 variant of the gallery search (VNFR_GALLERY_2CTA=1: CTA pairs, 256 queries per item, each CTA
+    loads half of every gallery tile) returns exactly what the one-CTA kernel returns (same products, same accumulation order)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, torch
+        sys.path.insert(0, ".")
+        from vn_celeb_face_recognition_b200 import gallery
+        g = torch.Generator().manual_seed(4)
+        G = torch.nn.functional.normalize(torch.randn(5000, 512, generator=g), dim=1).cuda()
+        Q = torch.nn.functional.normalize(torch.randn(1000, 512, generator=g), dim=1).cuda()
+        v, i = gallery.GalleryShard(G).topk(Q, k=5)
+        v2, i2 = gallery.GalleryShard(G).topk(Q[:300], k=5, sms=1000)       # several splits x two query pairs (ragged)
+        torch.save((v.cpu(), i.cpu(), v2.cpu(), i2.cpu()), sys.argv[1])
+    """)
+    import os, tempfile
+    outs = []
+    for two in (False, True):
+        env = dict(os.environ)
+        env.pop("VNFR_GALLERY_2CTA", None)
+        if two:
+            env["VNFR_GALLERY_2CTA"] = "1"
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            outs.append(torch.load(f.name))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_shifted_view_split_precision_conv(dev, mode):
     """Split-precision modes of the shifted-view kernel: fp32 activations and weights as 3 bf16 parts each (6 tensor-core
