@@ -48,6 +48,8 @@ struct SvParams {
   int tmem_cols;           // columns per buffer
   int use_base_offset;     // descriptor base-offset field = (addr >> 7) & 7
   int epi_split;           // 1: the two epilogue warp groups take alternate tiles (narrow tiles)
+  int epi_stage_bytes;     // > 0: per-epilogue-warp shared-memory slot (32 rows) through which narrow rows reach global memory
+                           // as contiguous 16-byte chunks (see epilogue_row_narrow_staged)
   int a_bufs;              // band buffers: 2 (next band loads under this band's MMAs) or 1 (large bands)
   int order;               // MMA issue order inside a K step: 0 = accumulator-major, 1 = rotate over accumulators per K slice
   const int* n_img_dev;    // nullable: device-side count of valid images (bands beyond it are skipped)
@@ -60,6 +62,51 @@ struct SvParams {
 __device__ long long* g_sv_dbg = nullptr;
 #define SV_T0() (dbg ? clock64() : 0ll)
 #define SV_ACC(i, t0) do { if (dbg) dbg[i] += clock64() - (t0); } while (0)
+
+// Narrow tiles (cout = 32 / 64 = the whole NHWC pixel, 64 / 128 bytes): with one accumulator row per thread, a warp-level 16-byte
+// store of epilogue_row_narrow touches 32 different 128-byte lines (ncu on conv2d_2b: LSU wavefronts at 70 % of peak, the top
+// pipe of the kernel).  The valid rows of a warp are CONSECUTIVE output pixels (the raster only skips padding), so the warp
+// parks its rows densely in a shared-memory slot (XOR-swizzled chunks) and streams the slot out with consecutive lanes on
+// consecutive 16-byte chunks: 4 full lines per store instruction.
+template <bool F16, int NC>
+__device__ __forceinline__ void epilogue_row_narrow_staged(const ConvParams& p, const float* sb, uint32_t t_row, int m, bool row_ok,
+                                                           uint32_t slot_smem, int lane) {
+  constexpr int CH = NC / 8;                 // 16-byte chunks per row
+  float v[NC];
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC / 16; ++c) tmem_ld16_issue(t_row + (uint32_t)(16 * c), v + 16 * c);
+#pragma unroll
+  for (int c = 0; c < NC / 16; ++c) tmem_ld_wait(v + 16 * c);
+  const unsigned mask = __ballot_sync(0xffffffffu, row_ok);
+  if (mask == 0u) return;
+  const int slot = __popc(mask & ((1u << lane) - 1u)), nvalid = __popc(mask);
+  const int m_first = __shfl_sync(0xffffffffu, m, __ffs(mask) - 1);
+  if (row_ok) {
+#pragma unroll
+    for (int i = 0; i < NC / 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * i);
+      v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    const uint32_t row = slot_smem + (uint32_t)slot * (uint32_t)(NC * 2);
+#pragma unroll
+    for (int qq = 0; qq < CH; ++qq)
+      sts128(row + (uint32_t)((qq ^ (slot & (CH - 1))) << 4),
+             make_uint4(pack2<F16>(v[8 * qq], v[8 * qq + 1]), pack2<F16>(v[8 * qq + 2], v[8 * qq + 3]),
+                        pack2<F16>(v[8 * qq + 4], v[8 * qq + 5]), pack2<F16>(v[8 * qq + 6], v[8 * qq + 7])));
+  }
+  __syncwarp();
+  uint4* g = reinterpret_cast<uint4*>(p.out0 + (size_t)m_first * NC);
+  for (int i = lane; i < nvalid * CH; i += 32) {
+    const int r = i / CH, ch = i - r * CH;
+    g[i] = lds128(slot_smem + (uint32_t)r * (uint32_t)(NC * 2) + (uint32_t)((ch ^ (r & (CH - 1))) << 4));
+  }
+  __syncwarp();                              // the slot is rewritten by this warp's next tile
+}
 
 template <bool F16, int MPS>   // MPS = tcgen05.mma instructions per K step = channels per plane / 16
 __global__ void __launch_bounds__(SV_THREADS, 1)
@@ -77,6 +124,7 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   const uint32_t bar_afull = bars, bar_aempty = bars + 16u, bar_bres = bars + 32u, bar_full = bars + 40u,
                  bar_empty = bar_full + 8u * q.stages, bar_tfull = bar_empty + 8u * q.stages,
                  bar_tempty = bar_tfull + 8u * q.nbuf, tmem_slot = bar_tempty + 8u * q.nbuf;
+  const uint32_t smem_stage = (tmem_slot + 16u + 127u) & ~127u;                 // 8 epilogue-warp slots of q.epi_stage_bytes
   float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
   uint32_t* s_koff = reinterpret_cast<uint32_t*>(smem_raw + (smem_koff - smem_u32(smem_raw)));
 
@@ -146,7 +194,11 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           const long long e1 = (dbg && warp == 0) ? clock64() : 0ll;
           tc_fence_after();
           const uint32_t t_row = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ab * q.tmem_cols);
-          if (q.epi_split) {
+          if (q.epi_split && q.epi_stage_bytes > 0) {
+            const uint32_t slot = smem_stage + (uint32_t)warp * (uint32_t)q.epi_stage_bytes;
+            if (p.cout == 32) epilogue_row_narrow_staged<F16, 32>(p, s_bias, t_row, m, row_ok, slot, lane);
+            else epilogue_row_narrow_staged<F16, 64>(p, s_bias, t_row, m, row_ok, slot, lane);
+          } else if (q.epi_split) {
             if (p.cout == 32) epilogue_row_narrow<F16, 32>(p, s_bias, t_row, m, row_ok);
             else epilogue_row_narrow<F16, 64>(p, s_bias, t_row, m, row_ok);
           } else {
@@ -362,7 +414,14 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   if (ksteps > 128) return false;
   int tmem_cols = 32;
   while (tmem_cols < op->block_n) tmem_cols <<= 1;
-  const int budget = 212 * 1024;
+  // narrow tiles whose destination rows are exactly the pixel (no channel slice of a wider buffer): staged stores
+  const bool narrow = (op->cout == 32 || op->cout == 64) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
+                      getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr;
+  // (64-wide rows only: for the 32-wide stem layers the slots cost band-buffer space -- conv2d_1a 141 -> 167 us -- and gain
+  // little, conv2d_2a 179 -> 173 us; conv2d_2b, 64 wide: 245 -> 217 us)
+  const int stage_bytes = (narrow && op->cout == 64 && op->out_f32 == nullptr && op->out0 != nullptr && op->out0_pitch == op->cout && op->prelu_alpha == nullptr &&
+                           ((uintptr_t)op->out0 % 16) == 0 && getenv("VNFR_SV_NO_STAGE") == nullptr) ? 32 * op->cout * 2 : 0;
+  const int budget = 212 * 1024 - 8 * stage_bytes;
   const bool b_res = (long long)ksteps * b_tile <= 80 * 1024;
   // accumulator tiles in flight per group: as many independent accumulators as TMEM holds twice over (max 4)
   int mt = 512 / (2 * tmem_cols);
@@ -441,8 +500,8 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   }
   q->a_bufs = bbufs;
   // narrow single-destination tiles without residual: alternate tiles between the two epilogue warp groups
-  q->epi_split = ((op->cout == 32 || op->cout == 64) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
-                  getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr) ? 1 : 0;
+  q->epi_split = narrow ? 1 : 0;
+  q->epi_stage_bytes = stage_bytes;
   q->n_img_dev = op->n_img_dev;
   q->order = 0;      // accumulator-major measured at least as fast as rotating per K slice in every layer (profiles/)
   if (getenv("VNFR_SV_ORDER") != nullptr) q->order = atoi(getenv("VNFR_SV_ORDER"));
@@ -451,7 +510,7 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
 
 size_t sv_smem_bytes(const SvParams& q) {
   const size_t b_bytes = (size_t)(q.b_resident ? q.ksteps : q.stages) * q.b_tile_bytes;
-  return 1024 + (size_t)q.a_bufs * q.a_buf_bytes + b_bytes + 1024 + 512 + 40 + 16 * q.stages + 16 * q.nbuf + 16;
+  return 1024 + (size_t)q.a_bufs * q.a_buf_bytes + b_bytes + 1024 + 512 + 40 + 16 * q.stages + 16 * q.nbuf + 16 + 128 + 8 * (size_t)q.epi_stage_bytes;
 }
 
 }  // namespace
