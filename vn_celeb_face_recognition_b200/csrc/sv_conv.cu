@@ -108,6 +108,50 @@ __device__ __forceinline__ void epilogue_row_narrow_staged(const ConvParams& p, 
   __syncwarp();                              // the slot is rewritten by this warp's next tile
 }
 
+// The same for fp32 destinations (the split-precision convolutions of R-Net / O-Net: 48 / 64 floats per row, + bias + PReLU):
+// slot rows are padded by one chunk (13 / 17), which keeps both the row-per-thread writes and the chunk-per-lane reads
+// conflict-free.
+template <int NC>
+__device__ __forceinline__ void epilogue_row_narrow_staged_f32(const ConvParams& p, const float* sb, uint32_t t_row, int m, bool row_ok,
+                                                               uint32_t slot_smem, int lane) {
+  constexpr int CH = NC / 4, RS = (CH + 1) * 16;      // chunks per row, padded row stride in bytes
+  float v[NC];
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < NC / 16; ++c) tmem_ld16_issue(t_row + (uint32_t)(16 * c), v + 16 * c);
+#pragma unroll
+  for (int c = 0; c < NC / 16; ++c) tmem_ld_wait(v + 16 * c);
+  const unsigned mask = __ballot_sync(0xffffffffu, row_ok);
+  if (mask == 0u) return;
+  const int slot = __popc(mask & ((1u << lane) - 1u)), nvalid = __popc(mask);
+  const int m_first = __shfl_sync(0xffffffffu, m, __ffs(mask) - 1);
+  if (row_ok) {
+    const uint32_t row = slot_smem + (uint32_t)slot * (uint32_t)RS;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sb + 4 * i);
+      float o[4] = {v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w};
+      if (p.relu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.0f);
+      }
+      if (p.alpha != nullptr) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.alpha + 4 * i));
+        o[0] = o[0] > 0.f ? o[0] : o[0] * a4.x; o[1] = o[1] > 0.f ? o[1] : o[1] * a4.y;
+        o[2] = o[2] > 0.f ? o[2] : o[2] * a4.z; o[3] = o[3] > 0.f ? o[3] : o[3] * a4.w;
+      }
+      sts128(row + (uint32_t)(i * 16), make_uint4(__float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3])));
+    }
+  }
+  __syncwarp();
+  uint4* g = reinterpret_cast<uint4*>(p.out_f32 + (size_t)m_first * NC);
+  for (int i = lane; i < nvalid * CH; i += 32) {
+    const int r = i / CH, ch = i - r * CH;
+    g[i] = lds128(slot_smem + (uint32_t)r * (uint32_t)RS + (uint32_t)(ch * 16));
+  }
+  __syncwarp();
+}
+
 template <bool F16, int MPS>   // MPS = tcgen05.mma instructions per K step = channels per plane / 16
 __global__ void __launch_bounds__(SV_THREADS, 1)
 sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a, const SvParams q) {
@@ -196,10 +240,15 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           const uint32_t t_row = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ab * q.tmem_cols);
           if (q.epi_split && q.epi_stage_bytes > 0) {
             const uint32_t slot = smem_stage + (uint32_t)warp * (uint32_t)q.epi_stage_bytes;
-            if (p.cout == 32) epilogue_row_narrow_staged<F16, 32>(p, s_bias, t_row, m, row_ok, slot, lane);
+            if (p.out_f32 != nullptr) {
+              if (p.cout == 48) epilogue_row_narrow_staged_f32<48>(p, s_bias, t_row, m, row_ok, slot, lane);
+              else epilogue_row_narrow_staged_f32<64>(p, s_bias, t_row, m, row_ok, slot, lane);
+            }
+            else if (p.cout == 32) epilogue_row_narrow_staged<F16, 32>(p, s_bias, t_row, m, row_ok, slot, lane);
             else epilogue_row_narrow_staged<F16, 64>(p, s_bias, t_row, m, row_ok, slot, lane);
           } else if (q.epi_split) {
             if (p.cout == 32) epilogue_row_narrow<F16, 32>(p, s_bias, t_row, m, row_ok);
+            else if (p.cout == 48) epilogue_row_narrow<F16, 48>(p, s_bias, t_row, m, row_ok);
             else epilogue_row_narrow<F16, 64>(p, s_bias, t_row, m, row_ok);
           } else {
             epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, chalf);
@@ -415,12 +464,16 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   int tmem_cols = 32;
   while (tmem_cols < op->block_n) tmem_cols <<= 1;
   // narrow tiles whose destination rows are exactly the pixel (no channel slice of a wider buffer): staged stores
-  const bool narrow = (op->cout == 32 || op->cout == 64) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
+  const bool narrow = (op->cout == 32 || op->cout == 64 || (op->cout == 48 && op->out_f32 != nullptr)) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
                       getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr;
   // (64-wide rows only: for the 32-wide stem layers the slots cost band-buffer space -- conv2d_1a 141 -> 167 us -- and gain
   // little, conv2d_2a 179 -> 173 us; conv2d_2b, 64 wide: 245 -> 217 us)
-  const int stage_bytes = (narrow && op->cout == 64 && op->out_f32 == nullptr && op->out0 != nullptr && op->out0_pitch == op->cout && op->prelu_alpha == nullptr &&
-                           ((uintptr_t)op->out0 % 16) == 0 && getenv("VNFR_SV_NO_STAGE") == nullptr) ? 32 * op->cout * 2 : 0;
+  int stage_bytes = (narrow && op->cout == 64 && op->out_f32 == nullptr && op->out0 != nullptr && op->out0_pitch == op->cout && op->prelu_alpha == nullptr &&
+                     ((uintptr_t)op->out0 % 16) == 0 && getenv("VNFR_SV_NO_STAGE") == nullptr) ? 32 * op->cout * 2 : 0;
+  // fp32 destinations (R-Net conv2: 48 floats per row, O-Net conv2 / conv3: 64): measured O-Net stage 1.390 -> 1.333 ms
+  if (narrow && (op->cout == 64 || op->cout == 48) && op->out_f32 != nullptr && op->out_f32_pitch == op->cout && ((uintptr_t)op->out_f32 % 16) == 0 &&
+      (op->prelu_alpha == nullptr || ((uintptr_t)op->prelu_alpha % 16) == 0) && getenv("VNFR_SV_NO_STAGE") == nullptr)
+    stage_bytes = 32 * (op->cout / 4 + 1) * 16;      // fp32 rows, padded by one 16-byte chunk
   const int budget = 212 * 1024 - 8 * stage_bytes;
   const bool b_res = (long long)ksteps * b_tile <= 80 * 1024;
   // accumulator tiles in flight per group: as many independent accumulators as TMEM holds twice over (max 4)
