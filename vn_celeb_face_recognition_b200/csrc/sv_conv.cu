@@ -108,9 +108,8 @@ __device__ __forceinline__ void epilogue_row_narrow_staged(const ConvParams& p, 
   __syncwarp();                              // the slot is rewritten by this warp's next tile
 }
 
-// The same for fp32 destinations (the split-precision convolutions of R-Net / O-Net: 48 / 64 floats per row, + bias + PReLU):
-// slot rows are padded by one chunk (13 / 17), which keeps both the row-per-thread writes and the chunk-per-lane reads
-// conflict-free.
+// The same for fp32 destinations (O-Net's split-precision conv2: 64 floats per row, + bias + PReLU): slot rows are padded by
+// one chunk (17), which keeps both the row-per-thread writes and the chunk-per-lane reads conflict-free.
 template <int NC>
 __device__ __forceinline__ void epilogue_row_narrow_staged_f32(const ConvParams& p, const float* sb, uint32_t t_row, int m, bool row_ok,
                                                                uint32_t slot_smem, int lane) {
@@ -240,15 +239,11 @@ sv_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           const uint32_t t_row = tmem_base + ((uint32_t)(qq * 32) << 16) + (uint32_t)(ab * q.tmem_cols);
           if (q.epi_split && q.epi_stage_bytes > 0) {
             const uint32_t slot = smem_stage + (uint32_t)warp * (uint32_t)q.epi_stage_bytes;
-            if (p.out_f32 != nullptr) {
-              if (p.cout == 48) epilogue_row_narrow_staged_f32<48>(p, s_bias, t_row, m, row_ok, slot, lane);
-              else epilogue_row_narrow_staged_f32<64>(p, s_bias, t_row, m, row_ok, slot, lane);
-            }
+            if (p.out_f32 != nullptr) epilogue_row_narrow_staged_f32<64>(p, s_bias, t_row, m, row_ok, slot, lane);
             else if (p.cout == 32) epilogue_row_narrow_staged<F16, 32>(p, s_bias, t_row, m, row_ok, slot, lane);
             else epilogue_row_narrow_staged<F16, 64>(p, s_bias, t_row, m, row_ok, slot, lane);
           } else if (q.epi_split) {
             if (p.cout == 32) epilogue_row_narrow<F16, 32>(p, s_bias, t_row, m, row_ok);
-            else if (p.cout == 48) epilogue_row_narrow<F16, 48>(p, s_bias, t_row, m, row_ok);
             else epilogue_row_narrow<F16, 64>(p, s_bias, t_row, m, row_ok);
           } else {
             epilogue_row<F16>(p, s_bias, t_row, m, row_ok, 0, p.cout, chalf);
@@ -464,14 +459,16 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   int tmem_cols = 32;
   while (tmem_cols < op->block_n) tmem_cols <<= 1;
   // narrow tiles whose destination rows are exactly the pixel (no channel slice of a wider buffer): staged stores
-  const bool narrow = (op->cout == 32 || op->cout == 64 || (op->cout == 48 && op->out_f32 != nullptr)) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
+  const bool narrow = (op->cout == 32 || op->cout == 64) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
                       getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr;
   // (64-wide rows only: for the 32-wide stem layers the slots cost band-buffer space -- conv2d_1a 141 -> 167 us -- and gain
   // little, conv2d_2a 179 -> 173 us; conv2d_2b, 64 wide: 245 -> 217 us)
   int stage_bytes = (narrow && op->cout == 64 && op->out_f32 == nullptr && op->out0 != nullptr && op->out0_pitch == op->cout && op->prelu_alpha == nullptr &&
                      ((uintptr_t)op->out0 % 16) == 0 && getenv("VNFR_SV_NO_STAGE") == nullptr) ? 32 * op->cout * 2 : 0;
-  // fp32 destinations (R-Net conv2: 48 floats per row, O-Net conv2 / conv3: 64): measured O-Net stage 1.390 -> 1.333 ms
-  if (narrow && (op->cout == 64 || op->cout == 48) && op->out_f32 != nullptr && op->out_f32_pitch == op->cout && ((uintptr_t)op->out_f32 % 16) == 0 &&
+  // fp32 destinations: O-Net conv2 only (64 floats per row, 32-channel planes).  Measured per half batch (ncu): O-Net conv2
+  // 246 -> 208 us; O-Net conv3 (64-channel planes: the slots cost it band space) 83 -> 101 us and R-Net conv2 (48 floats per
+  // row, which would also have to leave its two-warps-per-row epilogue) 158 -> 169 us, so those two keep the direct stores
+  if (narrow && op->cout == 64 && ck == 32 && op->out_f32 != nullptr && op->out_f32_pitch == op->cout && ((uintptr_t)op->out_f32 % 16) == 0 &&
       (op->prelu_alpha == nullptr || ((uintptr_t)op->prelu_alpha % 16) == 0) && getenv("VNFR_SV_NO_STAGE") == nullptr)
     stage_bytes = 32 * (op->cout / 4 + 1) * 16;      // fp32 rows, padded by one 16-byte chunk
   const int budget = 212 * 1024 - 8 * stage_bytes;
