@@ -696,3 +696,54 @@ def test_nv12_ingest_bit_identical_to_cv2(dev, models):
             np.testing.assert_array_equal(a["boxes"], b["boxes"])
             np.testing.assert_array_equal(a["labels"], b["labels"])
             np.testing.assert_array_equal(a["emb"], b["emb"])
+
+
+def test_face_crop_word_loads_equal_byte_loads(dev):
+    """vnfr_face_crops mode 1 (similarity warp): the aligned 32-bit loads of interior pixels (rows of W*3 bytes that are a
+    multiple of 4: 1080p) give bit-identical crops to the byte loads (VNFR_FACE_CROP_BYTES=1), incl. faces cut by the frame
+    border."""
+    import os, subprocess, sys, tempfile, textwrap
+    code = textwrap.dedent("""
+        import ctypes as C, sys, torch
+        sys.path.insert(0, ".")
+        from vn_celeb_face_recognition_b200 import _lib, pipeline
+        dev = torch.device("cuda:0")
+        g = torch.Generator().manual_seed(7)
+        B, H, W, capf, S = 2, 1080, 1920, 8, 160
+        fr = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8).to(dev)
+        cnt = torch.tensor([6, 5], dtype=torch.int32, device=dev)
+        box = torch.zeros(B, capf, 5); pts = torch.zeros(B, capf, 10)
+        for b in range(B):
+            for k in range(6):
+                x0 = [-20.3, 100.7, 700.2, 1800.9, 3.1, 950.5][k]; y0 = [-15.2, 400.4, 1000.6, 5.5, 980.8, 500.0][k]
+                w = [150.0, 81.3, 199.9, 160.2, 120.7, 60.1][k]
+                box[b, k] = torch.tensor([x0, y0, x0 + w, y0 + 1.1 * w, 0.99])
+                lm = torch.tensor([[0.3, 0.35], [0.7, 0.37], [0.5, 0.55], [0.35, 0.75], [0.68, 0.77]]) * torch.tensor([w, 1.1 * w]) + torch.tensor([x0, y0])
+                pts[b, k] = (lm + 0.7 * torch.randn(5, 2, generator=g)).reshape(-1)
+        F = 11
+        u8 = torch.zeros(F, S, S, 3, dtype=torch.uint8, device=dev)
+        half = torch.zeros(F, S // 2, S // 2, 16, dtype=torch.float16, device=dev)
+        offs = torch.zeros(B + 1, dtype=torch.int32, device=dev); status = torch.zeros(1, dtype=torch.int32, device=dev)
+        fimg = torch.zeros(F, dtype=torch.int32, device=dev)
+        tmpl = pipeline.center_point_dict["(160, 160)"]
+        t = (C.c_float * 10)(*tmpl.reshape(-1).tolist())
+        P = _lib.ptr
+        d_box, d_pts = box.to(dev), pts.to(dev)
+        _lib.call("vnfr_face_crops", P(fr), B, H, W, capf, P(cnt), P(d_box), P(d_pts), 1, S, 0, t, 1, F, P(offs), P(u8), P(half),
+                  P(fimg), P(status), 1, _lib.stream_ptr())
+        torch.cuda.synchronize()
+        torch.save((u8.cpu(), half.cpu()), sys.argv[1])
+    """)
+    outs = []
+    for byte_loads in (False, True):
+        env = dict(os.environ)
+        env.pop("VNFR_FACE_CROP_BYTES", None)
+        if byte_loads:
+            env["VNFR_FACE_CROP_BYTES"] = "1"
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=env, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+            outs.append(torch.load(f.name))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    filled = (outs[0][0].reshape(11, -1) > 0).float().mean(dim=1)
+    assert (filled > 0.2).all(), filled                        # every crop has real content (also those cut by the border)

@@ -33,6 +33,7 @@ constexpr int MAX_S = 256;                 // largest supported output edge
 struct FaceArgs {
   const uint8_t* frames;
   int B, H, W, capf, S, mode, margin, max_faces, f16, s2d;
+  int word_loads;          // mode 1: interior pixels read their taps with aligned 32-bit loads (host: geometry allows it)
   const int* count;        // [B]
   const float* box;        // [B][capf][5]
   const float* pts;        // [B][capf][10]  (x0,y0,...,x4,y4)
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(256) face_crop_kernel(const FaceArgs a) {
       }
     } else {
       // cv2.warpAffine, INTER_LINEAR fixed point: AB_BITS = 10, INTER_BITS = 5, weights 2^15
-      const bool words_ok = ((size_t)a.W * 3) % 4 == 0 && (reinterpret_cast<uintptr_t>(a.frames) & 3) == 0 && ((size_t)a.H * a.W * 3) % 4 == 0;
+      const bool words_ok = a.word_loads != 0;
       for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
         const int oy = i / S, ox = i - oy * S;
         const int X = (s_x0[oy] + s_ad[ox]) >> 5, Y = (s_y0[oy] + s_bd[ox]) >> 5;
@@ -432,6 +433,8 @@ extern "C" int vnfr_face_crops(const uint8_t* frames, int B, int H, int W, int c
   FaceArgs a;
   a.frames = frames; a.B = B; a.H = H; a.W = W; a.capf = capf; a.S = image_size; a.mode = mode; a.margin = margin;
   a.max_faces = max_faces; a.f16 = dtype == 1; a.s2d = half_layout == 1;
+  // VNFR_FACE_CROP_BYTES=1 keeps the byte loads everywhere (A/B switch; tests compare the two paths bit for bit)
+  a.word_loads = (((size_t)W * 3) % 4 == 0 && ((uintptr_t)frames & 3) == 0 && getenv("VNFR_FACE_CROP_BYTES") == nullptr) ? 1 : 0;
   a.count = count; a.box = box; a.pts = pts; a.offs = offs;
   for (int i = 0; i < 10; ++i) a.tmpl[i] = template_host ? template_host[i] : 0.f;
   a.face_u8 = face_u8; a.face_h = (unsigned short*)face_half; a.face_img = face_img; a.status = status;
