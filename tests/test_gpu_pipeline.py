@@ -125,7 +125,8 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
             c2 = torch.empty(len(y) * 81 * 48, device=dev)
             import ctypes
             back_w = M.HeadsBackWeights(sds[net], False, dev)
-            for back in (None, back_w.struct(M.heads_back_planes(False, len(y), dev))):
+            back_planes = M.heads_back_planes(False, len(y), dev)          # (kept alive: the struct only holds its address)
+            for back in (None, back_w.struct(back_planes)):
                 prob_t.zero_(); reg_t.zero_()
                 _lib.call("vnfr_rnet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), P(prob_t), P(reg_t),
                           P(offs), P(crops_t), P(p1), P(c2), len(y), P(status), ctypes.byref(back) if back is not None else None,
@@ -143,6 +144,7 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
             from vn_celeb_face_recognition_b200 import encoder_plan as ep
             import ctypes
             back_w = M.HeadsBackWeights(sds[net], True, dev)
+            back_planes = M.heads_back_planes(True, len(y), dev)
             for mode, tc3, tcb in ((1, False, False), (2, False, False), (2, True, False), (2, True, True)):
                 pack = ep.pack_conv_split2 if mode == 2 else ep.pack_conv_split3
                 w2s = pack(sds[net]["conv2.weight"], sds[net]["conv2.bias"], dev, 32).w
@@ -160,7 +162,7 @@ def test_rnet_onet_kernels_match_oracle(dev, models):
                     c3 = torch.empty(len(y) * 64 * 64, device=dev)
                 _lib.call("vnfr_onet_forward_tc", P(d_fr), B, H, W, cap, P(d_cnt), P(d_pad), P(w), P(w2s), mode, P(prob_t),
                           P(reg_t), P(lmk_t), P(offs), P(crops_t), P(p1), P(c2), P(w3s), P(p3), P(c3), len(y), P(status),
-                          ctypes.byref(back_w.struct(M.heads_back_planes(True, len(y), dev))) if tcb else None, _lib.stream_ptr())
+                          ctypes.byref(back_w.struct(back_planes)) if tcb else None, _lib.stream_ptr())
                 torch.cuda.synchronize()
                 assert torch.equal(crops_t, crops)
                 errs = ((prob_t - prob).abs().max().item(), (reg_t - reg).abs().max().item(), (lmk_t - lmk).abs().max().item())
