@@ -38,6 +38,8 @@ for _c in os.environ.get("VNFR_SV_OFF_CIN", "").split(","):      # experiments: 
 SV_MIN_USEFUL = float(os.environ.get("VNFR_SV_MIN_USEFUL", "0.7"))
 
 USE_GRAPHS = not os.environ.get("VNFR_NO_GRAPH")
+#: N tile of Block8's 1x3 / 3x1 convolutions (192 channels on 54 row tiles: one N tile leaves 94 SMs idle)
+B8_BLOCK_N = int(os.environ.get("VNFR_B8_BLOCK_N", "96")) or None      # measured: 192 -> 126 us, 96 -> 116 us, 64 -> 152 us (12 launches)
 #: Block17 as one fused kernel per block (csrc/block17_fused.cu) when its map is 8x8 (160x160 crops); VNFR_NO_FUSED_B17=1
 #: keeps the four-launch form (A/B measurements)
 FUSED_B17 = not os.environ.get("VNFR_NO_FUSED_B17")
@@ -425,8 +427,8 @@ class EncoderWeights:
         for i in list(range(5)) + [None]:
             p = "repeat_3.%d" % i if i is not None else "block8"
             P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0"], d, block_n=192)            # N = 384
-            P[p + ".b1a"] = pack_basic(sd, [p + ".branch1.1"], d)
-            P[p + ".b1b"] = pack_basic(sd, [p + ".branch1.2"], d)
+            P[p + ".b1a"] = pack_basic(sd, [p + ".branch1.1"], d, block_n=B8_BLOCK_N)
+            P[p + ".b1b"] = pack_basic(sd, [p + ".branch1.2"], d, block_n=B8_BLOCK_N)
             P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.20 if i is not None else 1.0, d)
         # last_linear (no bias) + last_bn folded (inception_resnet_v1.py:296-297)
         g, b = sd["last_bn.weight"].float(), sd["last_bn.bias"].float()
