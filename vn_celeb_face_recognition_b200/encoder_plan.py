@@ -38,6 +38,8 @@ for _c in os.environ.get("VNFR_SV_OFF_CIN", "").split(","):      # experiments: 
 SV_MIN_USEFUL = float(os.environ.get("VNFR_SV_MIN_USEFUL", "0.7"))
 
 USE_GRAPHS = not os.environ.get("VNFR_NO_GRAPH")
+#: N tile of mixed_7a's two 3x3 / stride-2 convolutions with 256 outputs (8x8 -> 3x3 maps: 54 row tiles)
+M7A_BLOCK_N = int(os.environ.get("VNFR_M7A_BLOCK_N", "128")) or None      # measured: 256 -> 21.5 us, 128 -> 19.0 us, 64 -> 30.9 us per launch
 #: N tile of Block8's 1x3 / 3x1 convolutions (192 channels on 54 row tiles: one N tile leaves 94 SMs idle)
 B8_BLOCK_N = int(os.environ.get("VNFR_B8_BLOCK_N", "96")) or None      # measured: 192 -> 126 us, 96 -> 116 us, 64 -> 152 us (12 launches)
 #: Block17 as one fused kernel per block (csrc/block17_fused.cu) when its map is 8x8 (160x160 crops); VNFR_NO_FUSED_B17=1
@@ -421,9 +423,9 @@ class EncoderWeights:
             P[p + ".out"] = pack_projection(sd, p + ".conv2d", 0.10, d)
         P["m7a.in"] = pack_basic(sd, ["mixed_7a.branch0.0", "mixed_7a.branch1.0", "mixed_7a.branch2.0"], d)   # N = 768
         P["m7a.b0"] = pack_basic(sd, ["mixed_7a.branch0.1"], d)
-        P["m7a.b1"] = pack_basic(sd, ["mixed_7a.branch1.1"], d)
+        P["m7a.b1"] = pack_basic(sd, ["mixed_7a.branch1.1"], d, block_n=M7A_BLOCK_N)
         P["m7a.b2a"] = pack_basic(sd, ["mixed_7a.branch2.1"], d)
-        P["m7a.b2b"] = pack_basic(sd, ["mixed_7a.branch2.2"], d)
+        P["m7a.b2b"] = pack_basic(sd, ["mixed_7a.branch2.2"], d, block_n=M7A_BLOCK_N)
         for i in list(range(5)) + [None]:
             p = "repeat_3.%d" % i if i is not None else "block8"
             P[p + ".in"] = pack_basic(sd, [p + ".branch0", p + ".branch1.0"], d, block_n=192)            # N = 384
