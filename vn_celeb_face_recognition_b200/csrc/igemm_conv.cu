@@ -36,6 +36,14 @@ __device__ long long* g_ig_dbg = nullptr;
 #define IG_T0() (dbg ? clock64() : 0ll)
 #define IG_ACC(i, t0) do { if (dbg) dbg[i] += clock64() - (t0); } while (0)
 
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 template <bool F16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a,
@@ -58,7 +66,7 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
   // TMA-fed A (1x1 convs): warps 0-7 have no gather work, so thread 0 becomes a dedicated C-store thread -- the epilogue
   // warps then never wait for a store to drain and need no CTA-level barrier before it (ncu: "barrier" was the top stall
   // of the projection convs: 5-10 stalled warps per issue)
-  const bool store_thread = p.epi_mode && p.a_mode == 1;
+  const bool store_thread = p.epi_mode && p.a_mode != 0;
   float* s_bias = reinterpret_cast<float*>(smem_raw + (smem_bias - smem_u32(smem_raw)));
 
   const int tid = threadIdx.x;
@@ -271,6 +279,10 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % n_tiles_n) * p.block_n;
         const int m0 = (tile / n_tiles_n) * BLOCK_M;
+        // base pixel of the tile for the im2col loads: input coordinates of output pixel m0 at tap (0, 0)
+        const int chunks = p.cin >> 6;
+        const int bn = m0 / (p.out_h * p.out_w), brem = m0 - bn * (p.out_h * p.out_w);
+        const int bh = (brem / p.out_w) * p.stride - p.pad_h, bw = (brem % p.out_w) * p.stride - p.pad_w;
         for (int kb = 0; kb < KB; ++kb) {
           const long long p0 = IG_T0();
           mbar_wait(bar_empty + 8u * s, ph);
@@ -279,6 +291,15 @@ igemm_conv_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_const
             // 1x1 convolution: the A tile is a plain 2-D box of the [M][pitch] activation matrix
             mbar_arrive_expect_tx(bar_full + 8u * s, (p.b_res ? 0u : b_stage_bytes) + A_STAGE_BYTES);
             tma_load_2d(smem_a + (uint32_t)s * A_STAGE_BYTES, &tmap_a, bar_full + 8u * s, kb * BLOCK_K, m0);
+          } else if (p.a_mode == 2) {
+            // k x k convolution, cin a multiple of 64: K block kb = (tap, 64-channel chunk) is ONE im2col TMA load of the 128
+            // output pixels that follow the tile's first one in (img, oy, ox) order (the unit walks the rows / images itself
+            // and zero-fills the padding).  The cp.async gather this replaces moved ~13 B/clk/SM.
+            const int tap = kb / chunks, chunk = kb - tap * chunks;
+            const int ky = tap / p.kw, kx = tap - ky * p.kw;
+            mbar_arrive_expect_tx(bar_full + 8u * s, (p.b_res ? 0u : b_stage_bytes) + A_STAGE_BYTES);
+            tma_load_im2col_4d(smem_a + (uint32_t)s * A_STAGE_BYTES, &tmap_a, bar_full + 8u * s, chunk * 64, bw, bh, bn,
+                               (uint16_t)kx, (uint16_t)ky);
           } else {
             mbar_arrive_expect_tx(bar_full + 8u * s, b_stage_bytes);
           }
@@ -367,7 +388,10 @@ int staging_bufs(int block_n, int epi_mode) {
   if (!epi_mode) return 0;
   const int one = ((block_n + 63) / 64) * 16384;
   const int stage_bytes = A_STAGE_BYTES + block_n * 128;
-  return (220 * 1024 - 2 * one) / stage_bytes >= 3 ? 2 : 1;
+  // a second C staging buffer only when it still leaves 4 ring stages (measured with 3 -> 4: conv2d_4a 383 -> 360 us,
+  // mixed_6a 3x3 convolutions 113 -> 104 and 161 -> 153 us; nothing else moves).  VNFR_IG_MIN_STAGES overrides.
+  static const int min_stages = getenv("VNFR_IG_MIN_STAGES") ? atoi(getenv("VNFR_IG_MIN_STAGES")) : 4;
+  return (220 * 1024 - 2 * one) / stage_bytes >= min_stages ? 2 : 1;
 }
 int staging_bytes(int block_n, int epi_mode) { return staging_bufs(block_n, epi_mode) * ((block_n + 63) / 64) * 16384; }
 
@@ -487,6 +511,44 @@ extern "C" int vnfr_conv_prepare(VnfrConvOp* op) {
     if (ra == CUDA_SUCCESS) {
       memcpy(op->tmap_a, &ta, sizeof(ta));
       op->a_mode = 1;
+    }
+  }
+  // k x k convolutions whose input channel count is a multiple of 64: the A tile of K block (tap, 64-channel chunk) is one TMA
+  // IM2COL load (cuTensorMapEncodeIm2col: NHWC tensor {C, W, H, N}, bounding box corners = -pad / pad - (k - 1), traversal
+  // stride = convolution stride, 64 channels x 128 pixels per load); the packed weights' K order (tap-major, cin contiguous)
+  // already puts such a block in one 64-wide K block.  VNFR_NO_IM2COL=1 keeps the cp.async gather.
+  if (op->a_mode == 0 && op->kh * op->kw > 1 && op->cin % 64 == 0 && op->in_pitch % 8 == 0 && ((uintptr_t)op->in % 16 == 0) && M > 0 &&
+      op->stride >= 1 && op->stride <= 8 && op->pad_h <= 127 && op->pad_w <= 127 && op->kh <= 128 && op->kw <= 128 &&
+      op->k_pad == op->kh * op->kw * op->cin && getenv("VNFR_NO_IM2COL") == nullptr) {
+    typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                       const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeIm2colFn enc_i2c = nullptr;
+    if (enc_i2c == nullptr) {
+      void* sym = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &sym, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        enc_i2c = reinterpret_cast<EncodeIm2colFn>(sym);
+    }
+    if (enc_i2c != nullptr) {
+      CUtensorMap ta;
+      const cuuint64_t gdim[4] = {(cuuint64_t)op->cin, (cuuint64_t)op->in_w, (cuuint64_t)op->in_h, (cuuint64_t)op->n_img};
+      const cuuint64_t gstr[3] = {(cuuint64_t)op->in_pitch * 2, (cuuint64_t)op->in_w * op->in_pitch * 2,
+                                  (cuuint64_t)op->in_h * op->in_w * op->in_pitch * 2};
+      const int lower[2] = {-op->pad_w, -op->pad_h};                                       // {W, H}
+      const int upper[2] = {op->pad_w - (op->kw - 1), op->pad_h - (op->kh - 1)};
+      const cuuint32_t estr4[4] = {1, (cuuint32_t)op->stride, (cuuint32_t)op->stride, 1};
+      const CUresult ri = enc_i2c(&ta, op->dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                  const_cast<void*>(op->in), gdim, gstr, lower, upper, 64, BLOCK_M, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (ri == CUDA_SUCCESS) {
+        memcpy(op->tmap_a, &ta, sizeof(ta));
+        op->a_mode = 2;
+        // TMA-fed k x k convolutions are bound by the depth of the operand ring (tools/ig_probe.py: the MMA warp waits for a
+        // full stage 38 % of the time with 3 stages): they give the C staging panels' shared memory to the ring and store
+        // rows directly (measured per launch: 192 -> 181, 113 -> 100, 161 -> 150, 52 -> 46, 56 -> 55 us)
+        if (getenv("VNFR_IM2COL_STAGED") == nullptr) op->epi_mode = 0;
+      }
     }
   }
   return VNFR_OK;
