@@ -33,6 +33,18 @@ __device__ __forceinline__ unsigned short pack_h1(float a) {
   return __bfloat16_as_ushort(__float2bfloat16_rn(a));
 }
 
+// element-wise maximum of two packed 16-bit pairs
+template <bool F16>
+__device__ __forceinline__ uint32_t hmax2_16(uint32_t a, uint32_t b) {
+  if (F16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+
 // MaxPool2d(3, stride=2), floor mode, no padding (inception_resnet_v1.py:147, :179, :224).  One thread = 8 channels.
 template <bool F16>
 __global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_img, int in_h, int in_w, int c8, int in_pitch,
@@ -44,25 +56,24 @@ __global__ void maxpool3s2_kernel(const __nv_bfloat16* __restrict__ in, int n_im
     const int ox = (int)(t % out_w); t /= out_w;
     const int oy = (int)(t % out_h);
     const int img = (int)(t / out_h);
-    float m[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) m[e] = -CUDART_INF_F;
+    // packed 16-bit maxima (HMNMX2): all nine 16-byte loads are issued before the first use; converting to fp32 and back cost
+    // four times the instructions for the same (exact) result
+    uint4 v[9];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const size_t px = ((size_t)img * in_h + (2 * oy + ky)) * in_w + (2 * ox + kx);
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + px * in_pitch + cg * 8));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          m[2 * e] = fmaxf(m[2 * e], h_lo<F16>(w[e]));
-          m[2 * e + 1] = fmaxf(m[2 * e + 1], h_hi<F16>(w[e]));
-        }
+        v[ky * 3 + kx] = __ldg(reinterpret_cast<const uint4*>(in + px * in_pitch + cg * 8));
       }
+    uint4 m = v[0];
+#pragma unroll
+    for (int t = 1; t < 9; ++t) {
+      m.x = hmax2_16<F16>(m.x, v[t].x); m.y = hmax2_16<F16>(m.y, v[t].y);
+      m.z = hmax2_16<F16>(m.z, v[t].z); m.w = hmax2_16<F16>(m.w, v[t].w);
+    }
     const size_t opx = ((size_t)img * out_h + oy) * out_w + ox;
-    *reinterpret_cast<uint4*>(out + opx * out_pitch + cg * 8) =
-        make_uint4(pack_h2<F16>(m[0], m[1]), pack_h2<F16>(m[2], m[3]), pack_h2<F16>(m[4], m[5]), pack_h2<F16>(m[6], m[7]));
+    *reinterpret_cast<uint4*>(out + opx * out_pitch + cg * 8) = m;
   }
 }
 
