@@ -461,8 +461,9 @@ bool sv_plan(const VnfrConvOp* op, SvParams* q) {
   // narrow tiles whose destination rows are exactly the pixel (no channel slice of a wider buffer): staged stores
   const bool narrow = (op->cout == 32 || op->cout == 64) && op->residual == nullptr && (op->out_f32 != nullptr || op->n_split >= op->cout) &&
                       getenv("VNFR_SV_NO_EPI_SPLIT") == nullptr;
-  // (64-wide rows only: for the 32-wide stem layers the slots cost band-buffer space -- conv2d_1a 141 -> 167 us -- and gain
-  // little, conv2d_2a 179 -> 173 us; conv2d_2b, 64 wide: 245 -> 217 us)
+  // (64-wide rows only: for the 32-wide stem layers the staged path is slower even when the slots cost no band space --
+  // conv2d_1a 141 -> 170 us, conv2d_2a 179 -> 187 us: 64-byte rows already share their 128-byte lines pairwise; conv2d_2b,
+  // 64 wide: 245 -> 217 us)
   int stage_bytes = (narrow && op->cout == 64 && op->out_f32 == nullptr && op->out0 != nullptr && op->out0_pitch == op->cout && op->prelu_alpha == nullptr &&
                      ((uintptr_t)op->out0 % 16) == 0 && getenv("VNFR_SV_NO_STAGE") == nullptr) ? 32 * op->cout * 2 : 0;
   // fp32 destinations: O-Net conv2 only (64 floats per row, 32-channel planes).  Measured per half batch (ncu): O-Net conv2
