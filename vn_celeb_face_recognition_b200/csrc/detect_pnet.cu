@@ -227,29 +227,39 @@ __global__ void __launch_bounds__(NTHR, TC ? PNET_TC_CTAS : PNET_MIN_CTAS) pnet_
           for (int y = 0; y < 4; ++y)
 #pragma unroll
             for (int x = 0; x < 4; ++x) patch[c][y][x] = s_buf[(c * IT + 2 * py + y) * ITP + 2 * px + x];
-        float acc[4][10];
+        // packed fp32 pairs (fma.rn.f32x2): accp[q][h] = channels (2h, 2h+1) of conv position q
+        unsigned long long accp[4][5];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int co = 0; co < 10; ++co) acc[q][co] = s_w[D_B1 + co];
+        for (int h = 0; h < 5; ++h) {
+          const unsigned long long b2 = *reinterpret_cast<const unsigned long long*>(s_w + D_B1 + 2 * h);
+          accp[0][h] = b2; accp[1][h] = b2; accp[2][h] = b2; accp[3][h] = b2;
+        }
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const float4* wr = reinterpret_cast<const float4*>(s_w + D_W1 + ((ci * 3 + ky) * 3 + kx) * 12);
-              const float4 wa = wr[0], wb = wr[1];
-              const float2 wc = *reinterpret_cast<const float2*>(wr + 2);
-              const float w[10] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y};
+              const unsigned long long* wr = reinterpret_cast<const unsigned long long*>(s_w + D_W1 + ((ci * 3 + ky) * 3 + kx) * 12);
+              const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wr), wb = *reinterpret_cast<const ulonglong2*>(wr + 2);
+              const unsigned long long w[5] = {wa.x, wa.y, wb.x, wb.y, wr[4]};
+              const float pv[4] = {patch[ci][ky][kx], patch[ci][ky][kx + 1], patch[ci][ky + 1][kx], patch[ci][ky + 1][kx + 1]};
 #pragma unroll
-              for (int co = 0; co < 10; ++co) {
-                acc[0][co] = fmaf(w[co], patch[ci][ky][kx], acc[0][co]);
-                acc[1][co] = fmaf(w[co], patch[ci][ky][kx + 1], acc[1][co]);
-                acc[2][co] = fmaf(w[co], patch[ci][ky + 1][kx], acc[2][co]);
-                acc[3][co] = fmaf(w[co], patch[ci][ky + 1][kx + 1], acc[3][co]);
+              for (int q = 0; q < 4; ++q) {
+                const unsigned vb = __float_as_uint(pv[q]);
+                const unsigned long long vv = (unsigned long long)vb | ((unsigned long long)vb << 32);
+#pragma unroll
+                for (int h = 0; h < 5; ++h) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(accp[q][h]) : "l"(w[h]), "l"(vv));
               }
             }
+        float acc[4][10];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int h = 0; h < 5; ++h) {
+            acc[q][2 * h] = __uint_as_float((unsigned)(accp[q][h] & 0xffffffffull));
+            acc[q][2 * h + 1] = __uint_as_float((unsigned)(accp[q][h] >> 32));
+          }
         const int cy = 2 * (ty0 + py), cx = 2 * (tx0 + px);
         const bool vy1 = cy + 1 < c1h, vx1 = cx + 1 < c1w, v00 = cy < c1h && cx < c1w;
 #pragma unroll
