@@ -92,16 +92,25 @@ __device__ __forceinline__ void pnet_cell_epilogue(const PnetParams& p, const fl
                                                    int* __restrict__ cand_count, uint32_t* __restrict__ cand_cell,
                                                    float* __restrict__ cand_score, float4* __restrict__ cand_reg,
                                                    float* __restrict__ dense_prob, float* __restrict__ dense_reg) {
-  float o[8];
+  // the six head outputs as three packed fp32 pairs (fma.rn.f32x2: bit-identical, half the FMA issue slots)
+  unsigned long long op[3];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = s_w[D_B4 + j];
+  for (int j = 0; j < 3; ++j) op[j] = *reinterpret_cast<const unsigned long long*>(s_w + D_B4 + 2 * j);
 #pragma unroll
   for (int co = 0; co < 32; ++co) {
-    const float v = prelu(acc[co], s_w[D_A3 + co]);
-    const float4 wa = *reinterpret_cast<const float4*>(s_w + D_W4 + co * 8);
-    const float4 wb = *reinterpret_cast<const float4*>(s_w + D_W4 + co * 8 + 4);
-    o[0] = fmaf(wa.x, v, o[0]); o[1] = fmaf(wa.y, v, o[1]); o[2] = fmaf(wa.z, v, o[2]); o[3] = fmaf(wa.w, v, o[3]);
-    o[4] = fmaf(wb.x, v, o[4]); o[5] = fmaf(wb.y, v, o[5]);
+    const unsigned vb = __float_as_uint(prelu(acc[co], s_w[D_A3 + co]));
+    const unsigned long long vv = (unsigned long long)vb | ((unsigned long long)vb << 32);
+    const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(s_w + D_W4 + co * 8);
+    const unsigned long long wb = *reinterpret_cast<const unsigned long long*>(s_w + D_W4 + co * 8 + 4);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(op[0]) : "l"(wa.x), "l"(vv));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(op[1]) : "l"(wa.y), "l"(vv));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(op[2]) : "l"(wb), "l"(vv));
+  }
+  float o[6];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    o[2 * j] = __uint_as_float((unsigned)(op[j] & 0xffffffffull));
+    o[2 * j + 1] = __uint_as_float((unsigned)(op[j] >> 32));
   }
   // softmax over the two logits (torch: exp(x - max) / sum)
   const float mx = fmaxf(o[0], o[1]);
