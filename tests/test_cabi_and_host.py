@@ -217,3 +217,40 @@ def test_frame_batcher_follows_demo_video_queue():
     assert [int(f[j, 0, 0, 0]) for f, _ in out for j in range(f.shape[0])] == [0, 1, 2, 3, 4]
     assert list(video.FrameBatcher(Cap(0), 4)) == []
     assert [f.shape[0] for f, _ in video.FrameBatcher(Cap(4), 4)] == [4]
+
+
+def test_heads_back_split_weights_layout():
+    """models.mtcnn.HeadsBackWeights (VnfrHeadsBack, csrc/heads_chain.cu): hi + lo planes reproduce the fp32 weights to 2^-22,
+    the 2x2 convolution's K order is (tap = ky*2 + kx, 64 channels, zero padded), the dense layer is torch's matrix as is
+    (the reference's (W,H,C) flatten, mtcnn.py:93-94 / :150-151), the heads are stacked in output order."""
+    from vn_celeb_face_recognition_b200.models import mtcnn as M
+    torch.manual_seed(0)
+    for onet, net in ((False, M.RNet(pretrained=False)), (True, M.ONet(pretrained=False))):
+        sd = {k: torch.randn_like(v) for k, v in net.state_dict().items()}
+        hb = M.HeadsBackWeights(sd, onet, "cpu")
+        conv, fc = ("conv4", "dense5") if onet else ("conv3", "dense4")
+        heads = ["dense6_1", "dense6_2", "dense6_3"] if onet else ["dense5_1", "dense5_2"]
+        L1, L2, L3 = hb.layers
+        co, ci = sd[conv + ".weight"].shape[:2]
+        assert (L1.N, L1.K, L1.N_pad) == (co, 256, 128) and tuple(L1.w.shape) == (256, 256)
+        w1 = (L1.w[:co].float() + L1.w[128:128 + co].float()).reshape(co, 2, 2, 64)
+        ref = sd[conv + ".weight"].permute(0, 2, 3, 1)                         # co, ky, kx, c
+        assert (w1[..., :ci] - ref).abs().max() <= 2.0 ** -21 * ref.abs().max() and (w1[..., ci:] == 0).all()
+        assert (L1.w[co:128] == 0).all() and (L1.w[128 + co:] == 0).all()      # N padding rows
+        w2 = L2.w[:L2.N].float() + L2.w[L2.N_pad:L2.N_pad + L2.N].float()
+        assert tuple(w2.shape) == tuple(sd[fc + ".weight"].shape) == (L2.N, 9 * co)
+        assert (w2 - sd[fc + ".weight"]).abs().max() <= 2.0 ** -21 * sd[fc + ".weight"].abs().max()
+        w3 = L3.w[:L3.N].float() + L3.w[128:128 + L3.N].float()
+        assert torch.allclose(w3, torch.cat([sd[h + ".weight"] for h in heads]), atol=1e-5) and L3.N == (16 if onet else 6)
+        assert torch.equal(L3.bias[:L3.N], torch.cat([sd[h + ".bias"] for h in heads]))
+        assert torch.equal(hb.alpha[0][:co], sd["prelu" + conv[-1] + ".weight"]) and (hb.alpha[0][co:] == 0).all()
+        assert torch.equal(hb.alpha[1][:L2.N], sd["prelu" + fc[-1] + ".weight"])
+        s = hb.struct(torch.zeros(8))
+        assert s.w[0] == L1.w.data_ptr() and s.bias[2] == L3.bias.data_ptr() and s.alpha[1] == hb.alpha[1].data_ptr()
+
+
+def test_trainer_accuracy_metric():
+    """losses/metrics.py:3-7"""
+    from vn_celeb_face_recognition_b200.trainer import accuracy
+    out = torch.tensor([[0.1, 0.9], [0.8, 0.2], [0.3, 0.7], [0.6, 0.4]]).log()
+    assert accuracy(out, torch.tensor([1, 0, 0, 0])) == 0.75
