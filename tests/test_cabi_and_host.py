@@ -254,3 +254,45 @@ def test_trainer_accuracy_metric():
     from vn_celeb_face_recognition_b200.trainer import accuracy
     out = torch.tensor([[0.1, 0.9], [0.8, 0.2], [0.3, 0.7], [0.6, 0.4]]).log()
     assert accuracy(out, torch.tensor([1, 0, 0, 0])) == 0.75
+
+
+def test_grouped_block35_packing_is_the_two_convolutions():
+    """encoder_plan.pack_basic_grouped: Block35's branch1.1 / branch2.1 (3x3, 32 -> 32 each, inception_resnet_v1.py:44-51) as one
+    block-diagonal 64 -> 64 convolution: unpacking the K-major weights ([cout][ky][kx][cin]) and running torch's conv2d gives the
+    two branch outputs (eval-mode BN folded)."""
+    from vn_celeb_face_recognition_b200 import encoder_plan as ep
+    g = torch.Generator().manual_seed(5)
+    sd = {}
+    for p in ("a", "b"):
+        sd[p + ".conv.weight"] = torch.randn(32, 32, 3, 3, generator=g) * 0.1
+        sd[p + ".bn.weight"] = torch.rand(32, generator=g) + 0.5
+        sd[p + ".bn.bias"] = torch.randn(32, generator=g) * 0.1
+        sd[p + ".bn.running_mean"] = torch.randn(32, generator=g) * 0.1
+        sd[p + ".bn.running_var"] = torch.rand(32, generator=g) + 0.5
+    pc = ep.pack_basic_grouped(sd, ["a", "b"], "cpu", dtype=torch.float32)
+    assert (pc.cout, pc.cin, pc.kh, pc.kw) == (64, 64, 3, 3) and tuple(pc.w.shape) == (64, 576)
+    w = pc.w.reshape(64, 3, 3, 64).permute(0, 3, 1, 2)                       # -> [cout][cin][ky][kx]
+    x = torch.randn(2, 64, 9, 9, generator=g)
+    got = torch.nn.functional.conv2d(x, w, pc.bias[:64], padding=1)
+    for i, p in enumerate(("a", "b")):
+        wf, s, b = ep.fold_bn(sd, p)
+        ref = torch.nn.functional.conv2d(x[:, 32 * i:32 * i + 32], wf * s.view(-1, 1, 1, 1), b, padding=1)
+        assert torch.allclose(got[:, 32 * i:32 * i + 32], ref, atol=1e-5)
+    assert (w[:32, 32:] == 0).all() and (w[32:, :32] == 0).all()             # off-diagonal blocks
+
+
+def test_split_linear_planes_and_split_k_choice():
+    """tail.SplitLinear: rows [0, N_pad) = fp16(w), rows [N_pad, 2 N_pad) = fp16(w - hi), K padded to 64 / N to 128 with zeros;
+    tail.pick_split_k covers the SMs with (m tiles x n tiles x splits) without leaving a split fewer than two K blocks."""
+    from vn_celeb_face_recognition_b200 import tail
+    g = torch.Generator().manual_seed(6)
+    w, b = torch.randn(1001, 500, generator=g), torch.randn(1001, generator=g)
+    L = tail.SplitLinear(w, b, "cpu")
+    assert (L.N, L.K, L.K_real, L.N_pad) == (1001, 512, 500, 1024) and tuple(L.w.shape) == (2048, 512)
+    rec = L.w[:1001, :500].float() + L.w[1024:2025, :500].float()
+    assert (rec - w).abs().max() <= 2.0 ** -21 * w.abs().max()
+    assert (L.w[:, 500:] == 0).all() and (L.w[1001:1024] == 0).all() and (L.w[2025:] == 0).all()
+    assert torch.equal(L.bias[:1001], b) and (L.bias[1001:] == 0).all()
+    for m_tiles, n_tiles, kb in ((6, 4, 28), (6, 16, 8), (1, 8, 32), (32, 8, 8), (1, 1, 3)):
+        s = tail.pick_split_k(m_tiles, n_tiles, kb)
+        assert 1 <= s <= 8 and (s == 1 or kb // s >= 2) and m_tiles * n_tiles * s <= max(148, m_tiles * n_tiles)
